@@ -1,0 +1,197 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- CPU oracle for the path-shadowing scan.
+ *
+ * A plain-C restatement of the reference algorithm (RudyMorel/shadowing @ 751a800) for
+ * Identity embedding + RelativeMSE distance + PredictionContext + running top-k.  It is the
+ * checker for the CUDA path (tests/, __graft_entry__.smoke(), bench.py's cpu_baseline /
+ * --impl reference legs) and is never imported, linked or executed by the product package
+ * `shadowing_b200`.  Parity pin: tests/golden/ fixtures generated from the live reference
+ * (tests/gen_golden.py) -- distances AND indices bit-equal, see tests/test_oracle.py.
+ *
+ * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off: the arithmetic below must NOT be
+ * contracted to FMA or re-associated).
+ *
+ * Arithmetic spec (measured against the reference on torch-CPU):
+ *   windows   y[r, t .. t+W-1], t < T' = T-W-H+1            path_embedding.py:117-139,48-51
+ *             (conv1d with eye(W) zero-padded by H == exact sliding windows)
+ *   numerator s = 0; for j = 0..W-1 (ascending): s = fl(s + fl(fl(q_j - y_{t+j})^2))
+ *             num = sqrtf(s)                                  path_distance.py:62-65 (x-y).norm(dim=-1)
+ *   denominator ||q||: 8 interleaved partial sums acc[j%8] += q_j^2 over the first 8*floor(W/8)
+ *             elements, lanes summed 0..7, scalar tail, sqrtf  path_distance.py:65 x.norm(dim=-1)
+ *   distance  d = fl(num / den)                               path_distance.py:65
+ *   top-k     k smallest over all (r,t), ascending            path_shadowing.py:143-173
+ *             tie order: (distance, r*T'+t) ascending (the reference's is unspecified)
+ *   indices   (r, t) int32                                    path_shadowing.py:43-58,166-167
+ *   paths     dataset[r, t .. t+W+H-1]                        path_shadowing.py:210-216
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef struct { uint32_t dbits; uint32_t pad; int64_t flat; } rec_t;
+
+static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+/* a < b in (distance, flat index) order; distances are >= 0 (or +inf / NaN: NaN sorts last
+ * through its bit pattern, which is all this checker needs) */
+static inline int rec_less(const rec_t *a, const rec_t *b) {
+    if (a->dbits != b->dbits) return a->dbits < b->dbits;
+    return a->flat < b->flat;
+}
+
+/* ||q||_2 exactly as torch's contiguous-last-dim vector_norm produces it (path_distance.py:65) */
+float orc_qnorm(const float *q, int W) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int n8 = (W / 8) * 8;
+    for (int j = 0; j < n8; ++j) {
+        float sq = q[j] * q[j];
+        acc[j & 7] = acc[j & 7] + sq;
+    }
+    float s = 0.0f;
+    for (int l = 0; l < 8; ++l) s = s + acc[l];
+    for (int j = n8; j < W; ++j) {
+        float sq = q[j] * q[j];
+        s = s + sq;
+    }
+    return sqrtf(s);
+}
+
+/* All RelativeMSE distances of one query against rows [r0, r1): out[(r-r0)*T' + t].
+ * target_clones: the prebuilt .so travels to a host with an unknown CPU; every clone performs
+ * the same IEEE operations per element (no contraction, no re-association). */
+__attribute__((target_clones("avx512f", "avx2", "default")))
+void orc_distances(const float *ds, int64_t row_stride, int64_t T, int64_t r0, int64_t r1,
+                   const float *q, int W, int H, float *out) {
+    int64_t Tp = T - W - H + 1;
+    if (Tp <= 0) return;
+    float den = orc_qnorm(q, W);
+    for (int64_t r = r0; r < r1; ++r) {
+        const float *y = ds + r * row_stride;
+        float *s = out + (r - r0) * Tp;
+        for (int64_t t = 0; t < Tp; ++t) s[t] = 0.0f;
+        for (int j = 0; j < W; ++j) {          /* j ascending: the reference's reduction order */
+            float qj = q[j];
+            const float *yj = y + j;
+            for (int64_t t = 0; t < Tp; ++t) {  /* vectorises across t, no cross-t dependence */
+                float df = qj - yj[t];
+                float sq = df * df;
+                s[t] = s[t] + sq;
+            }
+        }
+        for (int64_t t = 0; t < Tp; ++t) s[t] = sqrtf(s[t]) / den;
+    }
+}
+
+/* bounded max-heap of the k smallest records */
+static void heap_sift_down(rec_t *h, int64_t n, int64_t i) {
+    for (;;) {
+        int64_t l = 2 * i + 1, r = l + 1, m = i;
+        if (l < n && rec_less(&h[m], &h[l])) m = l;
+        if (r < n && rec_less(&h[m], &h[r])) m = r;
+        if (m == i) return;
+        rec_t tmp = h[i]; h[i] = h[m]; h[m] = tmp;
+        i = m;
+    }
+}
+static void heap_sift_up(rec_t *h, int64_t i) {
+    while (i > 0) {
+        int64_t p = (i - 1) / 2;
+        if (!rec_less(&h[p], &h[i])) return;
+        rec_t tmp = h[i]; h[i] = h[p]; h[p] = tmp;
+        i = p;
+    }
+}
+static inline void heap_offer(rec_t *h, int64_t *n, int64_t k, rec_t x) {
+    if (*n < k) { h[*n] = x; heap_sift_up(h, *n); ++*n; }
+    else if (rec_less(&x, &h[0])) { h[0] = x; heap_sift_down(h, k, 0); }
+}
+static int rec_cmp(const void *a, const void *b) {
+    const rec_t *x = a, *y = b;
+    return rec_less(x, y) ? -1 : (rec_less(y, x) ? 1 : 0);
+}
+
+/*
+ * shadow scan: the k closest windows to each of B queries (path_shadowing.py:97-179 with the
+ * split loop collapsed -- the merge of per-split top-k's equals the global top-k).
+ *   ds (R rows, row_stride floats apart, T valid), q (B, W) contiguous,
+ *   out_d (B, k) ascending, out_idx (B, k, 2) int32 [r + row_offset, t].
+ * returns 0, or -1 if k exceeds the number of windows (the reference raises there).
+ */
+int orc_shadow_topk(const float *ds, int64_t R, int64_t T, int64_t row_stride,
+                    const float *q, int B, int W, int H, int64_t k, int32_t row_offset,
+                    float *out_d, int32_t *out_idx, int nthreads) {
+    int64_t Tp = T - W - H + 1;
+    if (Tp <= 0 || k <= 0 || k > R * Tp) return -1;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+    for (int b = 0; b < B; ++b) {
+        const float *qb = q + (int64_t)b * W;
+        rec_t *heaps = malloc(sizeof(rec_t) * (size_t)k * (size_t)nthreads);
+        int64_t *hn = calloc((size_t)nthreads, sizeof(int64_t));
+        if (!heaps || !hn) { free(heaps); free(hn); return -2; }
+#pragma omp parallel num_threads(nthreads)
+        {
+#ifdef _OPENMP
+            int tid = omp_get_thread_num();
+#else
+            int tid = 0;
+#endif
+            rec_t *h = heaps + (size_t)tid * (size_t)k;
+            int64_t n = 0;
+            float *buf = malloc(sizeof(float) * (size_t)Tp);
+#pragma omp for schedule(dynamic, 16)
+            for (int64_t r = 0; r < R; ++r) {
+                orc_distances(ds, row_stride, T, r, r + 1, qb, W, H, buf);
+                for (int64_t t = 0; t < Tp; ++t) {
+                    rec_t x; x.dbits = f2u(buf[t]); x.pad = 0; x.flat = r * Tp + t;
+                    if (n == k && !(x.dbits < h[0].dbits || (x.dbits == h[0].dbits && x.flat < h[0].flat))) continue;
+                    heap_offer(h, &n, k, x);
+                }
+            }
+            hn[tid] = n;
+            free(buf);
+        }
+        /* merge thread heaps */
+        int64_t tot = 0;
+        for (int t = 0; t < nthreads; ++t) tot += hn[t];
+        rec_t *all = malloc(sizeof(rec_t) * (size_t)tot);
+        int64_t o = 0;
+        for (int t = 0; t < nthreads; ++t) {
+            memcpy(all + o, heaps + (size_t)t * (size_t)k, sizeof(rec_t) * (size_t)hn[t]);
+            o += hn[t];
+        }
+        qsort(all, (size_t)tot, sizeof(rec_t), rec_cmp);
+        for (int64_t i = 0; i < k; ++i) {
+            out_d[(int64_t)b * k + i] = u2f(all[i].dbits);
+            out_idx[((int64_t)b * k + i) * 2 + 0] = (int32_t)(all[i].flat / Tp) + row_offset;
+            out_idx[((int64_t)b * k + i) * 2 + 1] = (int32_t)(all[i].flat % Tp);
+        }
+        free(all); free(heaps); free(hn);
+    }
+    return 0;
+}
+
+/* paths[b, i, :] = ds[r, t .. t+L-1], L = W+H  (path_shadowing.py:210-216, C = 1) */
+void orc_gather_paths(const float *ds, int64_t row_stride, const int32_t *idx, int64_t n,
+                      int L, float *out) {
+    for (int64_t i = 0; i < n; ++i) {
+        const float *src = ds + (int64_t)idx[2 * i] * row_stride + idx[2 * i + 1];
+        memcpy(out + i * L, src, sizeof(float) * (size_t)L);
+    }
+}
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
