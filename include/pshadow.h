@@ -1,0 +1,118 @@
+/*
+ * pshadow.h -- C ABI of libpshadow.so: the B200 (sm_100a) path-shadowing scan.
+ *
+ * The reference (RudyMorel/shadowing @ 751a800) is pure Python and has no FFI of its own; its
+ * plugin surface is the Python classes in shadowing/path_shadowing/*.py.  This header is the
+ * boundary a binding for that path would target: every entry point names the reference code it
+ * replaces.  Plain pointers and sizes only; all pointers prefixed d_ are DEVICE pointers owned
+ * by the caller; all work is enqueued on the caller's cudaStream_t (passed as void*).
+ *
+ * Return value of every int function: 0 = ok, < 0 = PSH_E_* argument/state error,
+ * > 0 = a cudaError_t raised by the runtime.  Nothing here throws, aborts or prints.
+ */
+#ifndef PSHADOW_H
+#define PSHADOW_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSH_VERSION 100 /* 0.1.0 */
+
+enum {
+    PSH_OK = 0,
+    PSH_E_ARG = -1,        /* null pointer / non-positive size / W+H > T                      */
+    PSH_E_K = -2,          /* k exceeds the number of windows (reference: torch.topk raises)  */
+    PSH_E_WORKSPACE = -3,  /* workspace smaller than psh_scan_workspace_bytes()               */
+    PSH_E_TOO_LARGE = -4,  /* R*T' >= 2^32 windows in one call: shard the rows and merge      */
+    PSH_E_UNSUPPORTED = -5 /* context length beyond the shared-memory budget of the scan      */
+};
+
+/* scan modes */
+enum {
+    PSH_MODE_EXACT = 0, /* every window evaluated with the reference's exact fp32 sequence    */
+    PSH_MODE_FILTER = 1 /* 1-FMA/element lower-bound filter, exact re-rank of the survivors;  */
+                        /* results identical to PSH_MODE_EXACT by construction                */
+};
+
+int psh_version(void);
+const char *psh_error_string(int code);
+
+/* Bytes of device scratch psh_scan_topk_f32 needs for these sizes (0 on invalid sizes). */
+size_t psh_scan_workspace_bytes(int64_t R, int64_t T, int B, int W, int H, int64_t k);
+
+/*
+ * The scan: replaces PathShadowing.batched_distance (path_shadowing.py:97-179) for
+ * Identity embedding (path_embedding.py:117-139 + pad_context :48-51) and RelativeMSE
+ * (path_distance.py:62-65), including the per-split torch.topk + running merge (:165-173)
+ * and select_cartesian_product (:43-58).
+ *
+ *   d_dataset   (R rows, row_stride floats apart, T valid samples each), fp32
+ *   d_queries   (B, W) contiguous fp32 contexts
+ *   H           PredictionContext horizon (0 for None): windows t = 0 .. T-W-H
+ *   k           neighbours kept per query
+ *   row_offset  added to the returned trajectory index (rank's first global row when sharded)
+ *   d_out_dist  (B, k) fp32, ascending
+ *   d_out_idx   (B, k, 2) int32 [trajectory, offset]; ties ordered by (distance, r*T'+t)
+ *   d_ws        scratch of >= psh_scan_workspace_bytes(...) bytes, 256-byte aligned
+ *
+ * Distances carry the reference's CPU bit pattern: s = sum_j fl(fl(q_j - y_{t+j})^2)
+ * accumulated sequentially in fp32 without FMA, sqrt, IEEE divide by ||q|| (8-lane order).
+ * Synchronises the stream once before returning (overflow check of the candidate buffers).
+ */
+int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride,
+                      const float *d_queries, int B, int W, int H, int64_t k,
+                      int32_t row_offset, int mode,
+                      float *d_out_dist, int32_t *d_out_idx,
+                      void *d_ws, size_t ws_bytes, void *stream);
+
+/*
+ * k-way merge of G per-shard results into the global top-k: replaces the cat + topk +
+ * fancy-index merge (path_shadowing.py:170-173) across GPUs.
+ *   d_dist_parts (G, B, k) fp32, d_idx_parts (G, B, k, 2) int32 (global trajectory ids)
+ *   Tp           windows per trajectory (tie order is (distance, r*Tp+t))
+ */
+int psh_merge_topk(const float *d_dist_parts, const int32_t *d_idx_parts, int G, int B,
+                   int64_t k, int64_t Tp, float *d_out_dist, int32_t *d_out_idx, void *stream);
+
+/*
+ * Gather the winning paths with their out-context: replaces path_shadowing.py:210-216.
+ *   d_idx (n, 2) int32 [trajectory - row_offset must be in [0,R)], d_out (n, L) fp32, L = W+H.
+ *   Rows whose trajectory falls outside [row_offset, row_offset+R) are written as zeros
+ *   (sharded gather: the owner writes, a sum over ranks assembles).
+ */
+int psh_gather_paths(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride,
+                     const int32_t *d_idx, int64_t n, int32_t row_offset, int L,
+                     float *d_out, void *stream);
+
+/*
+ * Fused realised-variance + weighted aggregation: replaces predict_from_paths
+ * (path_shadowing.py:234-254) for to_predict = realized_variance(., Ts, vol)[:, :, 0, :]
+ * (statistics.py:5-16) and proba Uniform / Softmax (scatspectra; w ~ exp(-d^2 / 2 eta^2)).
+ *   d_paths (B, k, L) fp32, the last H samples are the out-context; d_dist (B, k)
+ *   d_Ts (nT) int32 maturities (<= H);  proba: 0 uniform, 1 softmax;  vol: 0/1
+ *   d_mean, d_std (B, nT) fp32
+ */
+int psh_rv_aggregate(const float *d_paths, const float *d_dist, int B, int64_t k, int L, int H,
+                     const int32_t *d_Ts, int nT, float eta, int proba, int vol,
+                     float *d_mean, float *d_std, void *stream);
+
+/* Number of kernels libpshadow has launched in this process (bench.py's gpu_launches). */
+uint64_t psh_launch_count(void);
+
+/*
+ * Measurement hooks (no reference counterpart): between begin and end every kernel the library
+ * launches is bracketed by CUDA events on the caller's stream.  psh_profile_end waits for them
+ * and returns summed milliseconds and launch counts per kind: 0 = scan kernels, 1 = select /
+ * re-rank / finalise kernels.  Not thread-safe; for bench.py's roofline leg only.
+ */
+void psh_profile_begin(void);
+int psh_profile_end(double *ms_by_kind, uint64_t *launches_by_kind, int nkinds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSHADOW_H */

@@ -1,0 +1,142 @@
+"""ctypes binding of libpshadow.so (include/pshadow.h).  No fallback: if the CUDA library is
+missing or no CUDA device is present, every entry point raises."""
+from __future__ import annotations
+
+import ctypes
+from pathlib import Path
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libpshadow.so"
+
+PSH_MODE_EXACT = 0
+PSH_MODE_FILTER = 1
+
+_lib = None
+
+
+class PshadowError(RuntimeError):
+    def __init__(self, code: int, where: str):
+        self.code = code
+        msg = lib().psh_error_string(code).decode()
+        super().__init__(f"{where}: {msg} (code {code})")
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(
+                f"{LIB_PATH} is not built. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). shadowing_b200 has no CPU fallback.")
+        L = ctypes.CDLL(str(LIB_PATH))
+        vp, i64, i32, ci, sz, f32 = (ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int,
+                                     ctypes.c_size_t, ctypes.c_float)
+        L.psh_version.restype = ci
+        L.psh_version.argtypes = []
+        L.psh_error_string.restype = ctypes.c_char_p
+        L.psh_error_string.argtypes = [ci]
+        L.psh_launch_count.restype = ctypes.c_uint64
+        L.psh_launch_count.argtypes = []
+        L.psh_scan_workspace_bytes.restype = sz
+        L.psh_scan_workspace_bytes.argtypes = [i64, i64, ci, ci, ci, i64]
+        L.psh_scan_topk_f32.restype = ci
+        L.psh_scan_topk_f32.argtypes = [vp, i64, i64, i64, vp, ci, ci, ci, i64, i32, ci, vp, vp, vp, sz, vp]
+        L.psh_merge_topk.restype = ci
+        L.psh_merge_topk.argtypes = [vp, vp, ci, ci, i64, i64, vp, vp, vp]
+        L.psh_gather_paths.restype = ci
+        L.psh_gather_paths.argtypes = [vp, i64, i64, i64, vp, i64, i32, ci, vp, vp]
+        L.psh_rv_aggregate.restype = ci
+        L.psh_rv_aggregate.argtypes = [vp, vp, ci, i64, ci, ci, vp, ci, f32, ci, ci, vp, vp, vp]
+        _lib = L
+    return _lib
+
+
+def require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("shadowing_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def _check(rc: int, where: str) -> None:
+    if rc != 0:
+        raise PshadowError(rc, where)
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib().psh_launch_count())
+
+
+def scan_topk(ds: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int, row_offset: int = 0,
+              mode: int = PSH_MODE_FILTER, workspace: torch.Tensor | None = None):
+    """ds (R, row_stride) f32 cuda, q (B, W) f32 cuda -> (dist (B,k) f32, idx (B,k,2) i32) cuda."""
+    L = lib()
+    assert ds.is_cuda and q.is_cuda and ds.dtype == torch.float32 and q.dtype == torch.float32
+    assert ds.dim() == 2 and ds.stride(1) == 1 and q.is_contiguous()
+    R, row_stride = ds.shape[0], ds.stride(0)
+    B, W = q.shape
+    need = L.psh_scan_workspace_bytes(R, T, B, W, H, k)
+    if need == 0:
+        # invalid sizes: let the library name the error
+        need = 256
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=ds.device)
+    dist = torch.empty((B, k), dtype=torch.float32, device=ds.device)
+    idx = torch.empty((B, k, 2), dtype=torch.int32, device=ds.device)
+    with torch.cuda.device(ds.device):
+        rc = L.psh_scan_topk_f32(ds.data_ptr(), R, T, row_stride, q.data_ptr(), B, W, H, k, row_offset, mode,
+                                 dist.data_ptr(), idx.data_ptr(), workspace.data_ptr(), workspace.numel(),
+                                 _stream(ds))
+    _check(rc, "psh_scan_topk_f32")
+    return dist, idx, workspace
+
+
+def merge_topk(dist_parts: torch.Tensor, idx_parts: torch.Tensor, Tp: int):
+    """(G,B,k) f32 + (G,B,k,2) i32 -> merged (B,k), (B,k,2)."""
+    L = lib()
+    G, B, k = dist_parts.shape
+    dist_parts = dist_parts.contiguous()
+    idx_parts = idx_parts.contiguous()
+    dist = torch.empty((B, k), dtype=torch.float32, device=dist_parts.device)
+    idx = torch.empty((B, k, 2), dtype=torch.int32, device=dist_parts.device)
+    with torch.cuda.device(dist_parts.device):
+        rc = L.psh_merge_topk(dist_parts.data_ptr(), idx_parts.data_ptr(), G, B, k, Tp, dist.data_ptr(),
+                              idx.data_ptr(), _stream(dist_parts))
+    _check(rc, "psh_merge_topk")
+    return dist, idx
+
+
+def gather_paths(ds: torch.Tensor, T: int, idx: torch.Tensor, L_out: int, row_offset: int = 0) -> torch.Tensor:
+    """idx (B,k,2) i32 -> paths (B,k,1,L) f32 (rows outside this shard are zeros)."""
+    L = lib()
+    B, k, _ = idx.shape
+    idx = idx.contiguous()
+    out = torch.empty((B, k, 1, L_out), dtype=torch.float32, device=ds.device)
+    with torch.cuda.device(ds.device):
+        rc = L.psh_gather_paths(ds.data_ptr(), ds.shape[0], T, ds.stride(0), idx.data_ptr(), B * k, row_offset,
+                                L_out, out.data_ptr(), _stream(ds))
+    _check(rc, "psh_gather_paths")
+    return out
+
+
+def rv_aggregate(paths: torch.Tensor, dist: torch.Tensor, H: int, Ts: torch.Tensor, eta: float, proba: int,
+                 vol: bool):
+    """paths (B,k,1,L), dist (B,k), Ts (nT) i32 ascending -> mean, std (B,nT) f32."""
+    L = lib()
+    B, k = dist.shape
+    Lp = paths.shape[-1]
+    paths = paths.contiguous()
+    dist = dist.contiguous()
+    nT = Ts.numel()
+    mean = torch.empty((B, nT), dtype=torch.float32, device=paths.device)
+    std = torch.empty((B, nT), dtype=torch.float32, device=paths.device)
+    with torch.cuda.device(paths.device):
+        rc = L.psh_rv_aggregate(paths.data_ptr(), dist.data_ptr(), B, k, Lp, H, Ts.data_ptr(), nT,
+                                float(eta if eta is not None else 0.0), proba, 1 if vol else 0, mean.data_ptr(),
+                                std.data_ptr(), _stream(paths))
+    _check(rc, "psh_rv_aggregate")
+    return mean, std

@@ -1,0 +1,933 @@
+// pshadow.cu -- B200 (sm_100a) path-shadowing scan: kernels + the C ABI of include/pshadow.h.
+//
+// Replaces, for Identity + RelativeMSE + PredictionContext, the reference hot path
+//   PathShadowing.batched_distance   path_shadowing.py:97-179
+//   PathShadowing.shadow (gather)    path_shadowing.py:210-216
+//   predict_from_paths               path_shadowing.py:234-254 (+ statistics.py:5-16)
+// The reference materialises all R*T' windows (conv1d with eye(W)), subtracts, norms, divides,
+// top-k's per split and merges.  Here the ensemble rows are streamed once per query group:
+// each warp stages a row segment in shared memory with a TMA bulk copy (cp.async.bulk +
+// mbarrier, double buffered), every lane slides WPT consecutive windows through registers, and
+// windows that beat the running threshold are appended to a per-query candidate list from
+// which a radix select keeps the k best.  The distance arithmetic reproduces the reference's
+// CPU bit pattern (sequential, non-fused fp32), so indices and distances are bit-identical.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <atomic>
+#include <vector>
+
+#include "pshadow.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// constants
+// ------------------------------------------------------------------------------------------
+constexpr int WPT = 12;              // consecutive windows per lane (48-byte lane stride: LDS.128 conflict-free)
+constexpr int SEG = 32 * WPT;        // windows per warp task
+constexpr int RING = 16;             // register ring of staged samples (WPT + one float4 in flight)
+constexpr int SCAN_WARPS = 8;        // warps per scan CTA
+constexpr int SCAN_THREADS = SCAN_WARPS * 32;
+constexpr int SEL_THREADS = 1024;
+constexpr int SORT_SMEM_MAX = 16384; // keys sorted in shared memory (128 KiB); larger k sorts in global
+constexpr int QG_MAX = 32;           // queries staged per scan launch
+constexpr unsigned FULL = 0xffffffffu;
+
+std::atomic<uint64_t> g_launches{0};
+
+struct QState {
+    unsigned long long tau_key;  // inclusive threshold on (distance bits << 32 | flat window index)
+    float s_thr;                 // largest squared numerator whose distance is <= tau's distance
+    float qnorm;                 // ||q|| in the reference's 8-lane order
+    unsigned int count;          // keys appended to the current buffer (may exceed cap: overflow)
+    unsigned int overflow;
+    unsigned int cur;            // current ping-pong buffer
+    unsigned int pad;
+};
+static_assert(sizeof(QState) == 32, "QState layout");
+
+struct ScanParams {
+    const float *ds;
+    long long row_stride;
+    int T, Tp, W, nseg;
+    long long R;
+    long long i0, i1;      // range of permuted row slots scanned by this launch
+    long long perm;        // row = (slot * perm) % R, gcd(perm, R) = 1
+    const float *queries;  // (nq, W)
+    int nq;
+    QState *st;            // (nq)
+    unsigned long long *keys;  // (nq, 2, cap)
+    unsigned int cap;
+    int bulk_ok;           // rows are 16-byte aligned: TMA bulk staging
+    int buf_floats;        // floats per staging buffer (multiple of 4)
+    int wpad;              // padded query stride in shared memory
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA bulk copy (SASS: SYNCS / UBLKCP)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "PSH_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra PSH_DONE;\n"
+        "bra PSH_WAIT;\n"
+        "PSH_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ float ld_volatile_f32(const float *p) {
+    return *reinterpret_cast<const volatile float *>(p);
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
+    return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+
+// the reference's distance from its squared numerator: sqrt then IEEE divide (path_distance.py:65)
+__device__ __forceinline__ float dist_from_s(float s, float qn) { return __fdiv_rn(__fsqrt_rn(s), qn); }
+
+// ------------------------------------------------------------------------------------------
+// query preparation: ||q|| in torch's contiguous-reduction order (8 interleaved partial sums,
+// lanes added 0..7, scalar tail), state reset.  path_distance.py:65 `x.norm(dim=-1)`.
+// ------------------------------------------------------------------------------------------
+__global__ void qprep_kernel(const float *__restrict__ q, int W, int nq, QState *st) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nq) return;
+    const float *x = q + (size_t)b * W;
+    float acc[8];
+#pragma unroll
+    for (int l = 0; l < 8; ++l) acc[l] = 0.0f;
+    int n8 = (W / 8) * 8;
+    for (int j = 0; j < n8; j += 8) {
+#pragma unroll
+        for (int l = 0; l < 8; ++l) acc[l] = __fadd_rn(acc[l], __fmul_rn(x[j + l], x[j + l]));
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) s = __fadd_rn(s, acc[l]);
+    for (int j = n8; j < W; ++j) s = __fadd_rn(s, __fmul_rn(x[j], x[j]));
+    QState z;
+    z.tau_key = ~0ull;
+    z.s_thr = __int_as_float(0x7f800000);
+    z.qnorm = __fsqrt_rn(s);
+    z.count = 0;
+    z.overflow = 0;
+    z.cur = 0;
+    z.pad = 0;
+    st[b] = z;
+}
+
+// ------------------------------------------------------------------------------------------
+// exact scan
+// ------------------------------------------------------------------------------------------
+// One block of up to RING reduction steps j = j0 .. j0+RING-1 for the WPT windows of a lane.
+// ring[m & 15] holds sample (j0 + m) of the lane's run; a float4 of new samples and of query
+// values is fetched every 4 steps.  Arithmetic is strictly sub -> mul -> add (never FMA), j
+// ascending: the reference's reduction order, hence its bits.
+template <bool GUARD>
+__device__ __forceinline__ void exact_block(float (&acc)[WPT], float (&ring)[RING], const float *__restrict__ yb,
+                                            const float *__restrict__ qs, int rem) {
+    float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int jj = 0; jj < RING; ++jj) {
+        if (GUARD && jj >= rem) break;
+        if ((jj & 3) == 0) {
+            const float4 v = *reinterpret_cast<const float4 *>(yb + jj + WPT);
+            ring[(jj + WPT + 0) & (RING - 1)] = v.x;
+            ring[(jj + WPT + 1) & (RING - 1)] = v.y;
+            ring[(jj + WPT + 2) & (RING - 1)] = v.z;
+            ring[(jj + WPT + 3) & (RING - 1)] = v.w;
+            q4 = *reinterpret_cast<const float4 *>(qs + jj);
+        }
+        const float qj = (jj & 3) == 0 ? q4.x : (jj & 3) == 1 ? q4.y : (jj & 3) == 2 ? q4.z : q4.w;
+#pragma unroll
+        for (int w = 0; w < WPT; ++w) {
+            const float df = __fsub_rn(qj, ring[(jj + w) & (RING - 1)]);
+            acc[w] = __fadd_rn(acc[w], __fmul_rn(df, df));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS, 2) scan_exact_kernel(const ScanParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *qs_all = reinterpret_cast<float *>(smem_raw);
+    float *bufs = qs_all + (size_t)p.nq * p.wpad;
+    unsigned long long *bars =
+        reinterpret_cast<unsigned long long *>(bufs + (size_t)SCAN_WARPS * 2 * p.buf_floats);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *mybuf = bufs + (size_t)warp * 2 * p.buf_floats;
+    const uint32_t bar0 = smem_u32(&bars[warp * 2]);
+
+    // stage the queries (zero padded to wpad so the float4 fetch of the tail stays in bounds)
+    for (int i = threadIdx.x; i < p.nq * p.wpad; i += SCAN_THREADS) {
+        int b = i / p.wpad, j = i - b * p.wpad;
+        qs_all[i] = j < p.W ? p.queries[(size_t)b * p.W + j] : 0.0f;
+    }
+    if (p.bulk_ok && lane == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const long long ntasks = (p.i1 - p.i0) * (long long)p.nseg;
+    const long long gw = (long long)blockIdx.x * SCAN_WARPS + warp;
+    const long long nw = (long long)gridDim.x * SCAN_WARPS;
+    const int need = SEG + p.W - 1;  // samples a full segment touches
+
+    auto task_src = [&](long long task, long long &row, int &t0, int &nvalid) {
+        long long slot = p.i0 + task / p.nseg;
+        int s = (int)(task - (task / p.nseg) * p.nseg);
+        row = (long long)(((unsigned long long)slot * (unsigned long long)p.perm) % (unsigned long long)p.R);
+        t0 = s * SEG;
+        nvalid = min(need, p.T - t0);
+    };
+    auto issue = [&](long long task, int which) {  // lane 0 only
+        long long row; int t0, nvalid;
+        task_src(task, row, t0, nvalid);
+        uint32_t bytes = (uint32_t)((nvalid + 3) & ~3) * 4u;
+        uint32_t bar = bar0 + 8u * which;
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(smem_u32(mybuf + (size_t)which * p.buf_floats), p.ds + row * p.row_stride + t0, bytes, bar);
+    };
+
+    uint32_t phase0 = 0, phase1 = 0;
+    if (p.bulk_ok && gw < ntasks && lane == 0) issue(gw, 0);
+
+    int n = 0;
+    for (long long task = gw; task < ntasks; task += nw, ++n) {
+        const int cur = n & 1;
+        long long row; int t0, nvalid;
+        task_src(task, row, t0, nvalid);
+        float *buf = mybuf + (size_t)cur * p.buf_floats;
+        if (p.bulk_ok) {
+            if (task + nw < ntasks && lane == 0) issue(task + nw, cur ^ 1);
+            if (cur == 0) { mbar_wait(bar0, phase0); phase0 ^= 1; }
+            else { mbar_wait(bar0 + 8, phase1); phase1 ^= 1; }
+        } else {
+            const float *src = p.ds + row * p.row_stride + t0;
+            for (int i = lane; i < nvalid; i += 32) buf[i] = __ldg(src + i);
+            __syncwarp();
+        }
+
+        const float *yb = buf + lane * WPT;
+        const int tl = t0 + lane * WPT;  // first window of this lane
+        const unsigned int flat0 = (unsigned int)((unsigned long long)row * (unsigned long long)p.Tp + (unsigned long long)tl);
+
+        for (int b = 0; b < p.nq; ++b) {
+            const float *qs = qs_all + (size_t)b * p.wpad;
+            float acc[WPT], ring[RING];
+#pragma unroll
+            for (int w = 0; w < WPT; ++w) acc[w] = 0.0f;
+            {
+                const float4 a = *reinterpret_cast<const float4 *>(yb + 0);
+                const float4 c = *reinterpret_cast<const float4 *>(yb + 4);
+                const float4 e = *reinterpret_cast<const float4 *>(yb + 8);
+                ring[0] = a.x; ring[1] = a.y; ring[2] = a.z; ring[3] = a.w;
+                ring[4] = c.x; ring[5] = c.y; ring[6] = c.z; ring[7] = c.w;
+                ring[8] = e.x; ring[9] = e.y; ring[10] = e.z; ring[11] = e.w;
+                ring[12] = ring[13] = ring[14] = ring[15] = 0.0f;
+            }
+            int j0 = 0;
+#pragma unroll 1
+            for (; j0 + RING <= p.W; j0 += RING) exact_block<false>(acc, ring, yb + j0, qs + j0, RING);
+            if (j0 < p.W) exact_block<true>(acc, ring, yb + j0, qs + j0, p.W - j0);
+
+            // ---- epilogue: rare candidates go to the per-query key list ----
+            const float s_thr = ld_volatile_f32(&p.st[b].s_thr);
+            unsigned int mask = 0;
+#pragma unroll
+            for (int w = 0; w < WPT; ++w)
+                if (tl + w < p.Tp && acc[w] <= s_thr) mask |= 1u << w;
+            if (__any_sync(FULL, mask != 0)) {
+                const float qn = p.st[b].qnorm;
+                const unsigned long long tau = ld_volatile_u64(&p.st[b].tau_key);
+                unsigned long long key[WPT];
+#pragma unroll
+                for (int w = 0; w < WPT; ++w) {
+                    key[w] = 0;
+                    if (mask & (1u << w)) {
+                        const float d = dist_from_s(acc[w], qn);
+                        key[w] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(flat0 + w);
+                        if (key[w] > tau) mask &= ~(1u << w);
+                    }
+                }
+                const int cnt = __popc(mask);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int v = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int total = __shfl_sync(FULL, incl, 31);
+                if (total > 0) {
+                    unsigned int base = 0;
+                    if (lane == 31) base = atomicAdd(&p.st[b].count, (unsigned int)total);
+                    base = __shfl_sync(FULL, base, 31);
+                    unsigned int pos = base + (unsigned int)(incl - cnt);
+                    unsigned long long *dst = p.keys + ((size_t)b * 2 + p.st[b].cur) * p.cap;
+#pragma unroll
+                    for (int w = 0; w < WPT; ++w)
+                        if (mask & (1u << w)) {
+                            if (pos < p.cap) dst[pos] = key[w];
+                            ++pos;
+                        }
+                }
+            }
+        }
+        __syncwarp();  // every lane is done with buf before it is refilled
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// select: keep the k smallest keys of a query's candidate list (MSB-first radix select on the
+// 64-bit key, compaction into the other ping-pong buffer), publish the new thresholds.
+// Replaces torch.topk + cat + topk (path_shadowing.py:165,170-173).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void hist_add(unsigned int *hist, unsigned int digit, bool active) {
+    // warp-aggregated shared-memory histogram increment
+    unsigned int act = __ballot_sync(FULL, active);
+    if (!active) return;
+    unsigned int peers = __match_any_sync(act, digit);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned int)__popc(peers));
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) select_kernel(QState *st_all, unsigned long long *keys_all,
+                                                              unsigned int cap, unsigned int k) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned int s_need, s_done, s_out;
+    QState *st = st_all + blockIdx.x;
+    const unsigned int cnt_raw = st->count;
+    const unsigned int M = min(cnt_raw, cap);
+    const unsigned int cur = st->cur;
+    const unsigned long long *src = keys_all + ((size_t)blockIdx.x * 2 + cur) * cap;
+    unsigned long long *dst = keys_all + ((size_t)blockIdx.x * 2 + (cur ^ 1)) * cap;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        if (cnt_raw > cap) st->overflow = 1;
+        s_prefix = 0; s_need = k; s_done = 0; s_out = 0;
+    }
+    if (M <= k) {  // nothing to drop yet (uniform branch: M, k are block-uniform)
+        if (tid == 0) st->count = M;
+        return;
+    }
+    __syncthreads();
+    unsigned long long tau = ~0ull;
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 56 - 8 * pass;
+        for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        const unsigned int Mr = (M + 31u) & ~31u;
+        for (unsigned int i = tid; i < Mr; i += SEL_THREADS) {
+            bool act = i < M;
+            unsigned long long key = act ? src[i] : 0ull;
+            if (pass > 0) act = act && ((key >> (shift + 8)) == (prefix >> (shift + 8)));
+            hist_add(hist, (unsigned int)(key >> shift) & 255u, act);
+        }
+        __syncthreads();
+        if (tid < 32) {  // warp 0: locate the bin holding the need-th smallest key
+            unsigned int need = s_need;
+            unsigned int loc[8], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { loc[i] = hist[tid * 8 + i]; sum += loc[i]; }
+            unsigned int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned int v = __shfl_up_sync(FULL, incl, o);
+                if (tid >= o) incl += v;
+            }
+            unsigned int excl = incl - sum;
+            if (excl < need && need <= incl) {  // exactly one lane
+                unsigned int c = excl;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (c < need && need <= c + loc[i]) {
+                        s_prefix = prefix | ((unsigned long long)(tid * 8 + i) << shift);
+                        s_need = need - c;
+                        s_done = (loc[i] == need - c) ? 1u : 0u;
+                    }
+                    c += loc[i];
+                }
+            }
+        }
+        __syncthreads();
+        if (s_done || pass == 7) {
+            tau = s_prefix | (shift ? ((1ull << shift) - 1ull) : 0ull);
+            break;
+        }
+    }
+    // compaction: exactly k keys are <= tau
+    for (unsigned int i = tid; i < ((M + 31u) & ~31u); i += SEL_THREADS) {
+        bool keep = false;
+        unsigned long long key = 0;
+        if (i < M) { key = src[i]; keep = key <= tau; }
+        unsigned int bal = __ballot_sync(FULL, keep);
+        if (bal) {
+            unsigned int base = 0;
+            if ((tid & 31) == 0) base = atomicAdd(&s_out, (unsigned int)__popc(bal));
+            base = __shfl_sync(FULL, base, 0);
+            if (keep) dst[base + __popc(bal & ((1u << (tid & 31)) - 1u))] = key;
+        }
+    }
+    __syncthreads();
+    if (tid < 32) {
+        // s_thr: the largest float s with dist_from_s(s) <= tau's distance (monotone map)
+        const float qn = st->qnorm;
+        const float taud = __uint_as_float((unsigned int)(tau >> 32));
+        float s_thr;
+        if (!(taud < __int_as_float(0x7f800000)) || !(qn > 0.0f)) {
+            s_thr = __int_as_float(0x7f800000);
+        } else {
+            const float est = __fmul_rn(__fmul_rn(taud, qn), __fmul_rn(taud, qn));
+            unsigned int eb = __float_as_uint(est);
+            // probe est-16 .. est+15 ulps in parallel, fall back to bisection outside that band
+            unsigned int lo_b = eb > 16u ? eb - 16u : 0u;
+            unsigned int cand = min(lo_b + (unsigned int)tid, 0x7f800000u);
+            bool ok = dist_from_s(__uint_as_float(cand), qn) <= taud;
+            unsigned int okm = __ballot_sync(FULL, ok);
+            if (okm != 0u && okm != FULL) {
+                int hi = 31 - __clz(okm);  // monotone: ok lanes form a prefix
+                s_thr = __uint_as_float(min(lo_b + (unsigned int)hi, 0x7f800000u));
+            } else {
+                unsigned int lo = 0u, hi = 0x7f800000u;  // invariant: f(lo) ok (s=0 -> d=0), answer in [lo,hi]
+                while (lo < hi) {
+                    unsigned int mid = lo + (hi - lo + 1u) / 2u;
+                    if (dist_from_s(__uint_as_float(mid), qn) <= taud) lo = mid; else hi = mid - 1u;
+                }
+                s_thr = __uint_as_float(lo);
+            }
+        }
+        if (tid == 0) {
+            st->tau_key = tau;
+            st->s_thr = s_thr;
+            st->count = s_out;
+            st->cur = cur ^ 1u;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// bitonic sort of n (power of two) 64-bit keys by one CTA; data in shared or global memory
+// ------------------------------------------------------------------------------------------
+__device__ void bitonic_sort_cta(unsigned long long *a, unsigned int n) {
+    for (unsigned int size = 2; size <= n; size <<= 1) {
+        for (unsigned int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (unsigned int i = threadIdx.x; i < (n >> 1); i += blockDim.x) {
+                unsigned int lo = 2 * i - (i & (stride - 1));
+                unsigned int hi = lo + stride;
+                bool up = (lo & size) == 0;
+                unsigned long long x = a[lo], y = a[hi];
+                if ((x > y) == up) { a[lo] = y; a[hi] = x; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// final ordering of a query's k keys and decoding into (distance, [trajectory, offset])
+__global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const QState *st_all, unsigned long long *keys_all,
+                                                                unsigned int cap, unsigned int k, unsigned int npow2,
+                                                                int use_smem, unsigned int Tp, int row_offset,
+                                                                float *out_d, int *out_idx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const QState *st = st_all + blockIdx.x;
+    unsigned long long *src = keys_all + ((size_t)blockIdx.x * 2 + st->cur) * cap;
+    unsigned long long *other = keys_all + ((size_t)blockIdx.x * 2 + (st->cur ^ 1u)) * cap;
+    const unsigned int M = min(st->count, cap);
+    unsigned long long *a = use_smem ? reinterpret_cast<unsigned long long *>(smem_raw) : other;
+    for (unsigned int i = threadIdx.x; i < npow2; i += blockDim.x) a[i] = i < M ? src[i] : ~0ull;
+    bitonic_sort_cta(a, npow2);
+    for (unsigned int i = threadIdx.x; i < k; i += blockDim.x) {
+        unsigned long long key = a[i];
+        unsigned int flat = (unsigned int)key;
+        out_d[(size_t)blockIdx.x * k + i] = __uint_as_float((unsigned int)(key >> 32));
+        out_idx[((size_t)blockIdx.x * k + i) * 2 + 0] = (int)(flat / Tp) + row_offset;
+        out_idx[((size_t)blockIdx.x * k + i) * 2 + 1] = (int)(flat % Tp);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// merge of G sorted shard results (multi-GPU): path_shadowing.py:170-173 across ranks
+// keys are rebuilt as (distance bits, global r*Tp+t) -- 96 bits do not fit one word, so the
+// sort key is (dbits << 32 | slot) with slot = g*k+i and ties in distance are re-ordered by the
+// global flat index in a final pass over equal-distance runs.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEL_THREADS) merge_kernel(const float *d_parts, const int *i_parts, int G, int B,
+                                                             unsigned int k, unsigned long long Tp, unsigned int npow2,
+                                                             unsigned long long *scratch, int use_smem,
+                                                             float *out_d, int *out_idx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x;
+    unsigned long long *a = use_smem ? reinterpret_cast<unsigned long long *>(smem_raw)
+                                     : scratch + (size_t)b * npow2;
+    const unsigned int n = (unsigned int)G * k;
+    for (unsigned int i = threadIdx.x; i < npow2; i += blockDim.x) {
+        unsigned long long key = ~0ull;
+        if (i < n) {
+            unsigned int g = i / k, j = i - g * k;
+            float d = d_parts[((size_t)g * B + b) * k + j];
+            key = ((unsigned long long)__float_as_uint(d) << 32) | i;
+        }
+        a[i] = key;
+    }
+    bitonic_sort_cta(a, npow2);
+    // fix the order inside runs of equal distance: rank by global flat index (runs are tiny)
+    for (unsigned int i = threadIdx.x; i < k; i += blockDim.x) {
+        unsigned long long key = a[i];
+        unsigned int db = (unsigned int)(key >> 32);
+        unsigned int lo = i, hi = i;
+        while (lo > 0 && (unsigned int)(a[lo - 1] >> 32) == db) --lo;
+        while (hi + 1 < n && (unsigned int)(a[hi + 1] >> 32) == db) ++hi;
+        unsigned int slot = (unsigned int)key;
+        if (lo != hi) {
+            // rank of this element's flat index among the run -> the element that belongs at i
+            unsigned int want = i - lo;
+            for (unsigned int c = lo; c <= hi; ++c) {
+                unsigned int sc = (unsigned int)a[c];
+                unsigned int gc = sc / k, jc = sc - gc * k;
+                const int *ic = i_parts + (((size_t)gc * B + b) * k + jc) * 2;
+                unsigned long long fc = (unsigned long long)ic[0] * Tp + (unsigned long long)ic[1];
+                unsigned int rank = 0;
+                for (unsigned int e = lo; e <= hi; ++e) {
+                    unsigned int se = (unsigned int)a[e];
+                    unsigned int ge = se / k, je = se - ge * k;
+                    const int *ie = i_parts + (((size_t)ge * B + b) * k + je) * 2;
+                    unsigned long long fe = (unsigned long long)ie[0] * Tp + (unsigned long long)ie[1];
+                    rank += (fe < fc) ? 1u : 0u;
+                }
+                if (rank == want) { slot = sc; break; }
+            }
+        }
+        unsigned int g = slot / k, j = slot - g * k;
+        const int *src = i_parts + (((size_t)g * B + b) * k + j) * 2;
+        out_d[(size_t)b * k + i] = __uint_as_float(db);
+        out_idx[((size_t)b * k + i) * 2 + 0] = src[0];
+        out_idx[((size_t)b * k + i) * 2 + 1] = src[1];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// gather: paths[i, :] = dataset[r, t : t+L]   (path_shadowing.py:210-216), one warp per path
+// ------------------------------------------------------------------------------------------
+__global__ void gather_kernel(const float *__restrict__ ds, long long R, long long row_stride,
+                              const int *__restrict__ idx, long long n, int row_offset, int L,
+                              float *__restrict__ out) {
+    long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int lane = threadIdx.x & 31;
+    long long r = (long long)idx[2 * i] - row_offset;
+    const int t = idx[2 * i + 1];
+    float *o = out + i * L;
+    if (r < 0 || r >= R) {
+        for (int j = lane; j < L; j += 32) o[j] = 0.0f;
+        return;
+    }
+    const float *src = ds + r * row_stride + t;
+    for (int j = lane; j < L; j += 32) o[j] = __ldg(src + j);
+}
+
+// ------------------------------------------------------------------------------------------
+// realised variance + weighted aggregation: one CTA per query
+//   x_i(path) = 252 * mean(path_out[:T_i]^2) (sqrt if vol)             statistics.py:5-16
+//   w(path) ~ exp(-d^2 / (2 eta^2)) (softmax) or 1/k (uniform)          scatspectra (unpinned)
+//   mean_i = sum w x_i ; std_i = sqrt(sum w x_i^2 - mean_i^2)           path_shadowing.py:248-252
+// accumulated in fp64 (k*H values per query: negligible work), rounded once to fp32.
+// ------------------------------------------------------------------------------------------
+constexpr int AGG_THREADS = 256;
+constexpr int AGG_MAX_T = 16;
+
+__device__ __forceinline__ double block_sum(double v, double *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int i = 0; i < AGG_THREADS / 32; ++i) s += red[i];
+    return s;
+}
+
+__global__ void __launch_bounds__(AGG_THREADS) rv_aggregate_kernel(const float *__restrict__ paths,
+                                                                   const float *__restrict__ dist, long long k, int L,
+                                                                   int H, const int *__restrict__ Ts, int nT, float eta,
+                                                                   int proba, int vol, float *out_mean, float *out_std) {
+    __shared__ double red[AGG_THREADS / 32];
+    __shared__ int sT[AGG_MAX_T];
+    const int b = blockIdx.x;
+    if (threadIdx.x < nT) sT[threadIdx.x] = Ts[threadIdx.x];
+    __syncthreads();
+    const float *dq = dist + (size_t)b * k;
+    // minimum squared distance: the shift that keeps exp() in range (cancels in the ratio)
+    double dmin = 1e300;
+    for (long long i = threadIdx.x; i < k; i += AGG_THREADS) {
+        double d = (double)dq[i];
+        dmin = fmin(dmin, d * d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(FULL, dmin, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dmin;
+    __syncthreads();
+    dmin = red[0];
+    for (int i = 1; i < AGG_THREADS / 32; ++i) dmin = fmin(dmin, red[i]);
+    const double inv2e2 = proba == 1 ? 1.0 / (2.0 * (double)eta * (double)eta) : 0.0;
+
+    double sw = 0.0, swx[AGG_MAX_T], swxx[AGG_MAX_T];
+#pragma unroll
+    for (int i = 0; i < AGG_MAX_T; ++i) { swx[i] = 0.0; swxx[i] = 0.0; }
+    for (long long i = threadIdx.x; i < k; i += AGG_THREADS) {
+        const float *o = paths + ((size_t)b * k + i) * L + (L - H);
+        double d = (double)dq[i];
+        double w = proba == 1 ? exp(-(d * d - dmin) * inv2e2) : 1.0;
+        sw += w;
+        double run = 0.0;
+        int j = 0;
+#pragma unroll
+        for (int ti = 0; ti < AGG_MAX_T; ++ti) {
+            if (ti < nT) {
+                // maturities are sorted ascending by the host wrapper: extend the running sum
+                // numpy's x2[..., :T] clips at the out-context length (statistics.py:13)
+                const int Te = sT[ti] < H ? sT[ti] : H;
+                for (; j < Te; ++j) { double v = (double)o[j]; run += v * v; }
+                double x = run / (double)Te * 252.0;
+                if (vol) x = sqrt(x);
+                swx[ti] += w * x;
+                swxx[ti] += w * x * x;
+            }
+        }
+    }
+    sw = block_sum(sw, red);
+    for (int ti = 0; ti < nT; ++ti) {
+        double a = block_sum(swx[ti < AGG_MAX_T ? ti : 0], red) / sw;
+        double c = block_sum(swxx[ti < AGG_MAX_T ? ti : 0], red) / sw;
+        if (threadIdx.x == 0) {
+            double var = c - a * a;
+            out_mean[(size_t)b * nT + ti] = (float)a;
+            out_std[(size_t)b * nT + ti] = (float)sqrt(var > 0.0 ? var : 0.0);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+long long gcd_ll(long long a, long long b) { while (b) { long long t = a % b; a = b; b = t; } return a; }
+
+// stride of the row permutation: ~0.618 R, coprime with R, so every prefix of slots is a
+// spread-out sample of the ensemble (the early chunks seed the threshold)
+long long perm_stride(long long R) {
+    if (R <= 2) return 1;
+    long long p = (long long)(0.6180339887498949 * (double)R);
+    if (p < 1) p = 1;
+    while (gcd_ll(p, R) != 1) ++p;
+    return p % R ? p % R : 1;
+}
+
+struct Plan {
+    long long Tp;
+    unsigned long long N;
+    unsigned int cap;
+    long long n0;      // rows of the seeding chunk
+    int growth;
+    size_t off_state, off_keys, total;
+};
+
+constexpr int SEED_FACTOR = 16;  // seeding chunk holds ~16 k windows
+constexpr int GROWTH = 16;       // each later chunk multiplies the scanned prefix by this
+constexpr int CAP_SLACK = 4;     // candidate buffer: 4x the expected appends of a chunk
+
+bool make_plan(long long R, long long T, int B, int W, int H, long long k, Plan &pl) {
+    if (R <= 0 || T <= 0 || B <= 0 || W <= 0 || H < 0 || k <= 0) return false;
+    pl.Tp = T - W - H + 1;
+    if (pl.Tp <= 0) return false;
+    pl.N = (unsigned long long)R * (unsigned long long)pl.Tp;
+    long long n0 = (SEED_FACTOR * k + pl.Tp - 1) / pl.Tp;
+    if (n0 < 1) n0 = 1;
+    if (n0 > R) n0 = R;
+    pl.n0 = n0;
+    pl.growth = GROWTH;
+    unsigned long long cap = (unsigned long long)n0 * pl.Tp + (unsigned long long)k
+                             + (unsigned long long)CAP_SLACK * GROWTH * (unsigned long long)k;
+    if (cap < 2ull * (unsigned long long)k) cap = 2ull * k;
+    // power-of-two room for the global-memory sort of very large k
+    unsigned long long p2 = 1; while (p2 < (unsigned long long)k) p2 <<= 1;
+    if (k > SORT_SMEM_MAX && cap < p2) cap = p2;
+    if (cap > 0xfffffff0ull) return false;
+    pl.cap = (unsigned int)cap;
+    pl.off_state = 0;
+    pl.off_keys = align_up((size_t)B * sizeof(QState), 256);
+    pl.total = pl.off_keys + (size_t)B * 2 * (size_t)pl.cap * sizeof(unsigned long long);
+    return true;
+}
+
+int g_sm_count = 0;
+int sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+// optional per-kernel timing (bench.py's roofline leg): CUDA events on the caller's stream
+struct ProfRec { cudaEvent_t a, b; int kind; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+struct ProfScope {
+    cudaStream_t s; int kind; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(cudaStream_t s_, int kind_) : s(s_), kind(kind_) {
+        if (g_prof_on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); }
+    }
+    ~ProfScope() {
+        if (a) { cudaEventRecord(b, s); g_prof.push_back({a, b, kind}); }
+    }
+};
+
+#define PSH_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+#define PSH_LAUNCHED() do { g_launches.fetch_add(1, std::memory_order_relaxed); cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return (int)e_; } while (0)
+
+}  // namespace
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+int psh_version(void) { return PSH_VERSION; }
+
+const char *psh_error_string(int code) {
+    switch (code) {
+        case PSH_OK: return "ok";
+        case PSH_E_ARG: return "invalid argument (null pointer, non-positive size, or W+H > T)";
+        case PSH_E_K: return "k exceeds the number of windows";
+        case PSH_E_WORKSPACE: return "workspace too small or misaligned";
+        case PSH_E_TOO_LARGE: return "more than 2^32-1 windows in one call: shard the rows and merge";
+        case PSH_E_UNSUPPORTED: return "context length exceeds the shared-memory budget of the scan";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "unknown pshadow error";
+}
+
+uint64_t psh_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+void psh_profile_begin(void) {
+    for (auto &r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    g_prof_on = true;
+}
+
+int psh_profile_end(double *ms_by_kind, uint64_t *launches_by_kind, int nkinds) {
+    g_prof_on = false;
+    for (int i = 0; i < nkinds; ++i) { ms_by_kind[i] = 0.0; launches_by_kind[i] = 0; }
+    int rc = PSH_OK;
+    for (auto &r : g_prof) {
+        float ms = 0.f;
+        cudaError_t e = cudaEventSynchronize(r.b);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.a, r.b);
+        if (e != cudaSuccess) rc = (int)e;
+        if (r.kind >= 0 && r.kind < nkinds) { ms_by_kind[r.kind] += ms; launches_by_kind[r.kind] += 1; }
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    return rc;
+}
+
+size_t psh_scan_workspace_bytes(int64_t R, int64_t T, int B, int W, int H, int64_t k) {
+    Plan pl;
+    if (!make_plan(R, T, B, W, H, k, pl)) return 0;
+    return pl.total;
+}
+
+static int run_scan_group(const float *d_dataset, long long R, long long T, long long row_stride,
+                          const float *d_q, int nq, int W, int H, long long k, int row_offset,
+                          const Plan &pl, QState *st, unsigned long long *keys, bool safe,
+                          float *d_out_dist, int *d_out_idx, cudaStream_t stream) {
+    (void)H;
+    qprep_kernel<<<(nq + 127) / 128, 128, 0, stream>>>(d_q, W, nq, st);
+    PSH_LAUNCHED();
+
+    ScanParams p;
+    p.ds = d_dataset; p.row_stride = row_stride; p.T = (int)T; p.Tp = (int)pl.Tp; p.W = W;
+    p.nseg = (int)((pl.Tp + SEG - 1) / SEG);
+    p.R = R; p.perm = perm_stride(R);
+    p.queries = d_q; p.nq = nq; p.st = st; p.keys = keys; p.cap = pl.cap;
+    p.bulk_ok = ((reinterpret_cast<uintptr_t>(d_dataset) & 15u) == 0 && (row_stride & 3) == 0) ? 1 : 0;
+    p.buf_floats = (int)align_up((size_t)SEG + W - 1 + RING + 4, 4);
+    p.wpad = (int)align_up((size_t)W + 4, 4);
+    const size_t smem = ((size_t)nq * p.wpad + (size_t)SCAN_WARPS * 2 * p.buf_floats) * sizeof(float)
+                        + (size_t)SCAN_WARPS * 2 * sizeof(unsigned long long);
+    if (smem > 200 * 1024) return PSH_E_UNSUPPORTED;
+    PSH_CUDA(cudaFuncSetAttribute(scan_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (ctas_per_sm > 2) ctas_per_sm = 2;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+
+    // chunk schedule over permuted row slots: seed chunk, then geometric growth; in safe mode
+    // every chunk fits the candidate buffer even if all of its windows are appended
+    long long done = 0;
+    long long safe_rows = ((long long)pl.cap - k) / pl.Tp;
+    if (safe_rows < 1) safe_rows = 1;
+    while (done < R) {
+        long long next;
+        if (safe) next = done + safe_rows;
+        else next = done == 0 ? pl.n0 : done * pl.growth;
+        if (next > R) next = R;
+        p.i0 = done; p.i1 = next;
+        long long ntasks = (next - done) * p.nseg;
+        long long ctas = (ntasks + SCAN_WARPS - 1) / SCAN_WARPS;
+        long long max_ctas = (long long)sm_count() * ctas_per_sm;
+        if (ctas > max_ctas) ctas = max_ctas;
+        {
+            ProfScope ps(stream, 0);
+            scan_exact_kernel<<<(unsigned int)ctas, SCAN_THREADS, smem, stream>>>(p);
+        }
+        PSH_LAUNCHED();
+        {
+            ProfScope ps(stream, 1);
+            select_kernel<<<nq, SEL_THREADS, 0, stream>>>(st, keys, pl.cap, (unsigned int)k);
+        }
+        PSH_LAUNCHED();
+        done = next;
+    }
+    unsigned int npow2 = 1; while (npow2 < (unsigned int)k) npow2 <<= 1;
+    int use_smem = npow2 <= SORT_SMEM_MAX ? 1 : 0;
+    size_t fsmem = use_smem ? (size_t)npow2 * sizeof(unsigned long long) : 0;
+    if (fsmem > 48 * 1024)
+        PSH_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    {
+        ProfScope ps(stream, 1);
+        finalize_kernel<<<nq, SEL_THREADS, fsmem, stream>>>(st, keys, pl.cap, (unsigned int)k, npow2, use_smem,
+                                                            (unsigned int)pl.Tp, row_offset, d_out_dist, d_out_idx);
+    }
+    PSH_LAUNCHED();
+    return PSH_OK;
+}
+
+int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride,
+                      const float *d_queries, int B, int W, int H, int64_t k,
+                      int32_t row_offset, int mode,
+                      float *d_out_dist, int32_t *d_out_idx,
+                      void *d_ws, size_t ws_bytes, void *stream_) {
+    (void)mode;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!d_dataset || !d_queries || !d_out_dist || !d_out_idx || !d_ws) return PSH_E_ARG;
+    if (row_stride < T) return PSH_E_ARG;
+    Plan pl;
+    if (!make_plan(R, T, B, W, H, k, pl)) {
+        if (R > 0 && T > 0 && B > 0 && W > 0 && H >= 0 && k > 0 && T - W - H + 1 > 0) return PSH_E_TOO_LARGE;
+        return PSH_E_ARG;
+    }
+    if ((unsigned long long)k > pl.N) return PSH_E_K;
+    if (pl.N >= 0xffffffffull) return PSH_E_TOO_LARGE;
+    if (ws_bytes < pl.total || (reinterpret_cast<uintptr_t>(d_ws) & 255u)) return PSH_E_WORKSPACE;
+
+    unsigned char *ws = static_cast<unsigned char *>(d_ws);
+    QState *st = reinterpret_cast<QState *>(ws + pl.off_state);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(ws + pl.off_keys);
+
+    for (int g0 = 0; g0 < B; g0 += QG_MAX) {
+        int nq = B - g0 < QG_MAX ? B - g0 : QG_MAX;
+        int rc = run_scan_group(d_dataset, R, T, row_stride, d_queries + (size_t)g0 * W, nq, W, H, k, row_offset,
+                                pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, false,
+                                d_out_dist + (size_t)g0 * k, d_out_idx + (size_t)g0 * k * 2, stream);
+        if (rc != PSH_OK) return rc;
+    }
+    // one synchronisation: did any candidate buffer overflow (adversarially ordered data)?
+    static thread_local QState hst[QG_MAX];
+    for (int g0 = 0; g0 < B; g0 += QG_MAX) {
+        int nq = B - g0 < QG_MAX ? B - g0 : QG_MAX;
+        PSH_CUDA(cudaMemcpyAsync(hst, st + g0, sizeof(QState) * nq, cudaMemcpyDeviceToHost, stream));
+        PSH_CUDA(cudaStreamSynchronize(stream));
+        bool ovf = false;
+        for (int i = 0; i < nq; ++i) ovf = ovf || hst[i].overflow != 0;
+        if (ovf) {
+            int rc = run_scan_group(d_dataset, R, T, row_stride, d_queries + (size_t)g0 * W, nq, W, H, k, row_offset,
+                                    pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, true,
+                                    d_out_dist + (size_t)g0 * k, d_out_idx + (size_t)g0 * k * 2, stream);
+            if (rc != PSH_OK) return rc;
+            PSH_CUDA(cudaStreamSynchronize(stream));
+        }
+    }
+    return PSH_OK;
+}
+
+int psh_merge_topk(const float *d_dist_parts, const int32_t *d_idx_parts, int G, int B,
+                   int64_t k, int64_t Tp, float *d_out_dist, int32_t *d_out_idx, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!d_dist_parts || !d_idx_parts || !d_out_dist || !d_out_idx || G <= 0 || B <= 0 || k <= 0 || Tp <= 0)
+        return PSH_E_ARG;
+    unsigned long long n = (unsigned long long)G * (unsigned long long)k;
+    if (n > 0x7fffffffull) return PSH_E_TOO_LARGE;
+    unsigned int npow2 = 1; while (npow2 < n) npow2 <<= 1;
+    int use_smem = npow2 <= SORT_SMEM_MAX ? 1 : 0;
+    size_t smem = use_smem ? (size_t)npow2 * sizeof(unsigned long long) : 0;
+    unsigned long long *scratch = nullptr;
+    if (!use_smem) PSH_CUDA(cudaMallocAsync(&scratch, (size_t)B * npow2 * sizeof(unsigned long long), stream));
+    if (smem > 48 * 1024)
+        PSH_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_kernel<<<B, SEL_THREADS, smem, stream>>>(d_dist_parts, d_idx_parts, G, B, (unsigned int)k,
+                                                   (unsigned long long)Tp, npow2, scratch, use_smem, d_out_dist,
+                                                   d_out_idx);
+    PSH_LAUNCHED();
+    if (scratch) PSH_CUDA(cudaFreeAsync(scratch, stream));
+    return PSH_OK;
+}
+
+int psh_gather_paths(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride,
+                     const int32_t *d_idx, int64_t n, int32_t row_offset, int L,
+                     float *d_out, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!d_dataset || !d_idx || !d_out || R <= 0 || T <= 0 || n < 0 || L <= 0 || L > T || row_stride < T)
+        return PSH_E_ARG;
+    if (n == 0) return PSH_OK;
+    const int warps = 8;
+    gather_kernel<<<(unsigned int)((n + warps - 1) / warps), warps * 32, 0, stream>>>(
+        d_dataset, R, row_stride, d_idx, n, row_offset, L, d_out);
+    PSH_LAUNCHED();
+    return PSH_OK;
+}
+
+int psh_rv_aggregate(const float *d_paths, const float *d_dist, int B, int64_t k, int L, int H,
+                     const int32_t *d_Ts, int nT, float eta, int proba, int vol,
+                     float *d_mean, float *d_std, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!d_paths || !d_dist || !d_Ts || !d_mean || !d_std || B <= 0 || k <= 0 || L <= 0 || H <= 0 || H > L)
+        return PSH_E_ARG;
+    if (nT <= 0 || nT > AGG_MAX_T) return PSH_E_UNSUPPORTED;
+    if (proba != 0 && proba != 1) return PSH_E_ARG;
+    if (proba == 1 && !(eta > 0.0f)) return PSH_E_ARG;
+    rv_aggregate_kernel<<<B, AGG_THREADS, 0, stream>>>(d_paths, d_dist, k, L, H, d_Ts, nT, eta, proba, vol, d_mean,
+                                                       d_std);
+    PSH_LAUNCHED();
+    return PSH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+"""CPU: the C-ABI library loads and exports every symbol include/pshadow.h declares; argument
+validation that needs no device; host-side logic of the Python plugin surface."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = (ROOT / "include" / "pshadow.h").read_text()
+    names = set(re.findall(r"\b(psh_[a-z0-9_]+)\s*\(", hdr))
+    assert {"psh_scan_topk_f32", "psh_merge_topk", "psh_gather_paths", "psh_rv_aggregate",
+            "psh_scan_workspace_bytes", "psh_version", "psh_error_string", "psh_launch_count"} <= names
+    so = ROOT / "shadowing_b200" / "libpshadow.so"
+    assert so.exists(), "build with __graft_entry__.build()"
+    L = ctypes.CDLL(str(so))
+    for n in names:
+        assert hasattr(L, n), n
+
+
+def test_version_errors_and_workspace_sizing():
+    from shadowing_b200 import _lib
+    L = _lib.lib()
+    assert L.psh_version() == 100
+    assert b"k exceeds" in L.psh_error_string(-2)
+    assert L.psh_scan_workspace_bytes(32768, 4096, 1, 252, 20, 1024) > 0
+    assert L.psh_scan_workspace_bytes(32768, 4096, 256, 252, 20, 1024) > L.psh_scan_workspace_bytes(32768, 4096, 1, 252, 20, 1024)
+    assert L.psh_scan_workspace_bytes(10, 100, 1, 90, 20, 4) == 0   # W + H > T
+    assert L.psh_scan_workspace_bytes(0, 100, 1, 10, 0, 4) == 0
+    # null pointers are rejected before any device work
+    assert L.psh_scan_topk_f32(None, 1, 100, 100, None, 1, 10, 0, 1, 0, 0, None, None, None, 0, None) == -1
+    assert L.psh_gather_paths(None, 1, 1, 1, None, 1, 0, 1, None, None) == -1
+    assert L.psh_merge_topk(None, None, 1, 1, 1, 1, None, None, None) == -1
+
+
+def test_plugin_surface_matches_reference_names():
+    import shadowing_b200 as sb
+    for n in ["PathShadowing", "PathEmbedding", "Identity", "PathDistance", "RelativeMSE", "ContextManagerBase",
+              "PredictionContext", "ArrayType", "realized_variance", "Softmax", "Uniform", "DiscreteProba"]:
+        assert hasattr(sb, n)
+    import inspect
+    sig = inspect.signature(sb.PathShadowing.shadow)
+    assert list(sig.parameters)[1:] == ["x_context", "k", "n_splits", "cuda"]
+    sig = inspect.signature(sb.PathShadowing.predict)
+    assert list(sig.parameters)[1:] == ["x_context", "k", "to_predict", "eta", "proba_name", "n_dataset_splits",
+                                        "n_context_splits", "cuda"]
+    assert sig.parameters["proba_name"].default == "softmax"
+    sig = inspect.signature(sb.PathShadowing.__init__)
+    assert list(sig.parameters)[1:5] == ["embedding", "distance", "dataset", "context"]
+
+
+def test_prediction_context_and_identity():
+    import shadowing_b200 as sb
+    c = sb.PredictionContext(5)
+    x = np.arange(20.0).reshape(2, 10)
+    assert np.array_equal(c.select_in_context(x), x[:, :5]) and np.array_equal(c.select_out_context(x), x[:, 5:])
+    assert c.get_out_times() == 5 and sb.PredictionContext().get_out_times() == 0
+    assert sb.PredictionContext().select_out_context(x) is x
+    e = sb.Identity(4)
+    assert e.d == 4 and tuple(e.kernel.shape) == (4, 1, 4)
+    adj = e.adjust_to_context(c)
+    assert tuple(adj.kernel.shape) == (4, 1, 9) and float(adj.kernel[:, :, 4:].abs().sum()) == 0.0
+    y = torch.arange(12.0).reshape(1, 1, 12)
+    emb = adj(y)  # (1, t', 4): exact sliding windows
+    assert tuple(emb.shape) == (1, 4, 4) and torch.equal(emb[0, 2], y[0, 0, 2:6])
+
+
+def test_relative_mse_and_forward_topk_match_reference_fixture():
+    import shadowing_b200 as sb
+    g = load_golden("forward_topk_B8_d34")
+    dist = sb.RelativeMSE()
+    x, y = torch.tensor(g["x"]), torch.tensor(g["y"])
+    ds1, id1 = dist.forward_topk(x, y, k=32, n_splits=4)
+    ds2, id2 = dist.forward_topk(x, y, k=64, n_splits=8)
+    assert torch.equal(ds1, ds2[:, :32]) and torch.equal(id1, id2[:, :32])   # testing.ipynb:43-53
+    assert np.array_equal(ds2.numpy(), g["ds"]) and np.array_equal(id2.numpy(), g["idces"])
+
+
+def test_realized_variance_matches_reference_fixture():
+    import shadowing_b200 as sb
+    g = load_golden("cfg1_R128_T512_W20")
+    out = g["paths"][..., -20:]
+    Ts = [int(t) for t in g["Ts"]]
+    assert np.array_equal(sb.realized_variance(out, Ts, False), g["rv"])
+    assert np.array_equal(sb.realized_variance(out, Ts, True), g["rvol"])
+    assert np.array_equal(sb.RealizedVariance(Ts)(out), g["rv"][:, :, 0, :])
+
+
+def test_softmax_uniform_contracts():
+    import shadowing_b200 as sb
+    from oracle import oracle
+    rng = np.random.default_rng(1)
+    d = np.sort(rng.uniform(0.9, 1.3, (4, 64)).astype(np.float32), 1)
+    x = rng.normal(size=(4, 64, 3)).astype(np.float32)
+    p = sb.PathShadowing.init_averaging_proba("softmax", d[:, :, None], 0.1)
+    w = oracle.softmax_weights(d[:, :, None], 0.1, axis=1)
+    assert np.allclose(p.avg(x, axis=1), (w * x).sum(1), rtol=1e-5, atol=1e-7)
+    var = (w * x * x).sum(1) - (w * x).sum(1) ** 2
+    assert np.allclose(p.std(x, axis=1), np.sqrt(var), rtol=1e-5)
+    u = sb.PathShadowing.init_averaging_proba("uniform", d[:, :, None], None)
+    assert np.allclose(u.avg(x, axis=1), x.mean(1, dtype=np.float64), rtol=1e-5, atol=1e-7)
+    assert np.allclose(u.std(x, axis=1), x.std(1, dtype=np.float64), rtol=1e-5)
+    with pytest.raises(ValueError):
+        sb.PathShadowing.init_averaging_proba("nope", d, 0.1)
+    # plot_utils.py:74-76 pattern: (k,) distances against (k, 1, T) paths over axis 0
+    paths = rng.normal(size=(64, 1, 30)).astype(np.float32)
+    s = sb.Softmax(distances=d[0], eta=0.09)
+    w0 = oracle.softmax_weights(d[0], 0.09, axis=0)
+    assert np.allclose(s.avg(paths, axis=0), (w0[:, None, None] * paths).sum(0), rtol=1e-5, atol=1e-7)
+    assert s.avg(paths, axis=0)[0, :].shape == (30,)
+
+
+def test_select_cartesian_product():
+    import shadowing_b200 as sb
+    a, b = torch.tensor([10, 20, 30]), torch.arange(4)
+    idx = torch.tensor([[0, 5, 11]])
+    out = sb.select_cartesian_product(idx, [a, b])
+    assert torch.equal(out, torch.cartesian_prod(a, b)[idx])
+
+
+def test_no_cpu_fallback_without_device():
+    import shadowing_b200 as sb
+    if torch.cuda.is_available():
+        pytest.skip("device present")
+    obj = sb.PathShadowing(sb.Identity(8), sb.RelativeMSE(), np.zeros((2, 1, 64), np.float32), sb.PredictionContext(2))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        obj.shadow(np.ones((1, 1, 8), np.float32), k=2)

@@ -1,0 +1,241 @@
+"""GPU parity: the CUDA path (through the reference-shaped Python API and the raw C ABI)
+against the live-reference golden fixtures and the CPU oracle.  Integer outputs bit-exact,
+distances bit-exact (the scan reproduces the reference's fp32 sequence), predictions within
+1e-6 relative (north_star's stated tolerance)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_topk_equal, load_golden, make_inputs
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+import shadowing_b200 as sb  # noqa: E402
+from shadowing_b200 import _lib  # noqa: E402
+
+
+def _obj(ds, W, H, **kw):
+    return sb.PathShadowing(sb.Identity(W), sb.RelativeMSE(), ds, sb.PredictionContext(H), **kw)
+
+
+@pytest.mark.parametrize("mode", ["exact", "filter"])
+def test_golden_shadow_bit_exact(golden, mode):
+    obj = _obj(golden["dataset"], golden["W"], golden["H"], scan_mode=mode)
+    d, paths, idx = obj.shadow(golden["x_context"], k=golden["k"], n_splits=golden["n_splits"], cuda=True)
+    assert d.dtype == np.float32 and paths.dtype == np.float32 and idx.dtype == np.int32
+    assert_topk_equal(d, idx, golden["distances"], golden["indices"])
+    assert np.array_equal(idx, golden["indices"])
+    assert paths.shape == golden["paths"].shape
+    assert np.array_equal(paths, golden["paths"])
+
+
+@pytest.mark.parametrize("mode", ["exact", "filter"])
+@pytest.mark.parametrize("R,T,W,H,k,B", [
+    (512, 4096, 252, 20, 1024, 2),    # north-star window/k on a subsample of rows
+    (300, 1000, 100, 0, 77, 3),       # no horizon, odd sizes
+    (64, 4099, 17, 3, 5000, 1),       # T % 4 != 0 (padded row stride), k > SEG
+    (2048, 512, 20, 20, 16, 40),      # many queries: several query groups
+    (5, 300, 252, 20, 1, 2),          # k = 1, fewer rows than seed rows
+    (16, 2000, 1, 0, 9, 2),           # W = 1
+])
+def test_oracle_parity_seeded(R, T, W, H, k, B, mode):
+    ds, q = make_inputs(R, T, W, B, seed=100 + R)
+    obj = _obj(ds, W, H or None, scan_mode=mode)
+    d, paths, idx = obj.shadow(q, k=k)
+    do, po, io = oracle.shadow(ds, q, k, H)
+    assert_topk_equal(d, idx, do, io)
+    assert np.array_equal(paths, po)
+
+
+def test_k_equals_all_windows():
+    ds, q = make_inputs(7, 90, 10, 2, seed=5)
+    n = 7 * (90 - 10 - 5 + 1)
+    d, _, idx = _obj(ds, 10, 5).shadow(q, k=n)
+    do, io = oracle.shadow_topk(ds, q, n, 5)
+    assert_topk_equal(d, idx, do, io)
+
+
+def test_large_k_global_sort_path():
+    ds, q = make_inputs(40, 1500, 30, 1, seed=9)
+    k = 20000  # > 16384: the finalise sort runs in global memory
+    d, _, idx = _obj(ds, 30, 10).shadow(q, k=k)
+    do, io = oracle.shadow_topk(ds, q, k, 10)
+    assert_topk_equal(d, idx, do, io)
+
+
+def test_unaligned_rows_take_the_plain_load_path():
+    """row_stride % 4 != 0: no TMA bulk copy possible, the warp loads its segment itself."""
+    ds, q = make_inputs(33, 1001, 50, 2, seed=21)
+    rows = torch.tensor(ds[:, 0, :]).cuda()  # stride 1001
+    qd = torch.tensor(q[:, 0, :]).cuda()
+    for mode in (_lib.PSH_MODE_EXACT, _lib.PSH_MODE_FILTER):
+        d, idx, _ = _lib.scan_topk(rows, 1001, qd, 7, 300, 0, mode)
+        do, io = oracle.shadow_topk(ds, q, 300, 7)
+        assert_topk_equal(d.cpu().numpy(), idx.cpu().numpy(), do, io)
+
+
+def _perm_stride(R):
+    if R <= 2:
+        return 1
+    p = max(int(0.6180339887498949 * R), 1)
+    while math.gcd(p, R) != 1:
+        p += 1
+    return p % R or 1
+
+
+@pytest.mark.parametrize("mode", ["exact", "filter"])
+def test_adversarial_order_overflows_then_recovers(mode):
+    """Seed rows far, every other row near: the candidate buffer overflows and the scan must
+    re-run in its safe schedule and still return the exact answer."""
+    R, T, W, H, k = 512, 1024, 32, 0, 64
+    ds, q = make_inputs(R, T, W, 1, seed=33)
+    Tp = T - W + 1
+    n0 = min(max(-(-16 * k // Tp), 1), R)
+    P = _perm_stride(R)
+    seed_rows = {(i * P) % R for i in range(n0)}
+    ds = ds * 1e-3
+    for r in seed_rows:
+        ds[r] *= 1e5
+    d, _, idx = _obj(ds, W, None, scan_mode=mode).shadow(q, k=k)
+    do, io = oracle.shadow_topk(ds, q, k, H)
+    assert_topk_equal(d, idx, do, io)
+
+
+def test_ties_are_ordered_by_flat_index():
+    """Identical rows: every distance value appears R times; order must be (d, r*T'+t)."""
+    base, q = make_inputs(1, 600, 40, 1, seed=3)
+    ds = np.repeat(base, 50, axis=0)
+    d, _, idx = _obj(ds, 40, 10).shadow(q, k=333)
+    do, io = oracle.shadow_topk(ds, q, 333, 10)
+    assert np.array_equal(d, do) and np.array_equal(idx, io)
+
+
+def test_zero_query_all_inf():
+    ds, _ = make_inputs(4, 200, 16, 1)
+    d, _, idx = _obj(ds, 16, None).shadow(np.zeros((1, 1, 16), np.float32), k=10)
+    assert np.isinf(d).all()
+    assert np.array_equal(idx[0, :, 0], np.zeros(10)) and np.array_equal(idx[0, :, 1], np.arange(10))
+
+
+def test_input_conventions_and_errors():
+    ds, q = make_inputs(8, 256, 20, 2, seed=1)
+    obj = _obj(ds[:, 0, :], 20, 5)  # 2-D dataset
+    d3, p3, i3 = obj.shadow(q, k=4)
+    d2, p2, i2 = obj.shadow(q[:, 0, :], k=4)            # 2-D contexts
+    d1, p1, i1 = obj.shadow(q[0, 0, :], k=4)            # 1-D context
+    dt, _, _ = obj.shadow(torch.tensor(q), k=4)         # torch input
+    d64, _, _ = obj.shadow(q.astype(np.float64), k=4)   # numpy f64 is cast (path_shadowing.py:33)
+    assert np.array_equal(d3, d2) and np.array_equal(d3[:1], d1) and np.array_equal(d3, dt)
+    assert np.array_equal(d3, d64) and p3.shape == (2, 4, 1, 25) and p1.shape == (1, 4, 1, 25)
+    with pytest.raises(Exception, match="same size as the context"):
+        obj.shadow(q[:, :, :10], k=4)
+    with pytest.raises(RuntimeError):
+        obj.shadow(torch.tensor(q, dtype=torch.float64), k=4)   # torch f64 context (reference raises too)
+    with pytest.raises(RuntimeError):
+        obj.shadow(q, k=8 * 256)                                 # k > number of windows
+    with pytest.raises(ValueError):
+        obj.predict_from_paths(d3, p3, sb.RealizedVariance([2]), "gaussian", 0.1)
+    bad = sb.PathShadowing(sb.PathEmbedding(torch.ones(3, 1, 20)), sb.RelativeMSE(), ds, sb.PredictionContext(5))
+    with pytest.raises(NotImplementedError):
+        bad.shadow(q, k=4)
+
+
+def test_batched_distance_contract():
+    ds, q = make_inputs(16, 300, 24, 3, seed=2)
+    obj = _obj(ds, 24, 6)
+    d, i = obj.batched_distance(torch.tensor(q), torch.tensor(ds), k=12, n_splits=4, cuda=True)
+    assert isinstance(d, torch.Tensor) and d.device.type == "cpu" and i.dtype == torch.int32
+    do, io = oracle.shadow_topk(ds, q, 12, 6)
+    assert_topk_equal(d.numpy(), i.numpy(), do, io)
+
+
+def test_testing_ipynb_self_consistency():
+    """testing.ipynb:62-78 re-expressed for Identity: re-embedding the returned paths and
+    re-computing the distance reproduces the returned distances (their rtol 1e-2; here 1e-6)."""
+    ds, q = make_inputs(32, 4096, 126, 8, seed=4)
+    obj = _obj(ds, 126, 252)
+    d, paths, _ = obj.shadow(q, k=1024)
+    pin = torch.tensor(obj.context.select_in_context(paths))[:, :, 0, :]
+    ds_test = obj.distance(torch.tensor(q), pin)
+    assert torch.allclose(ds_test, torch.tensor(d), rtol=1e-6)
+
+
+@pytest.mark.parametrize("proba,eta,vol", [("softmax", 0.1, False), ("softmax", 0.02, True), ("uniform", None, False)])
+def test_predict_from_paths_matches_oracle(proba, eta, vol):
+    ds, q = make_inputs(256, 2048, 60, 5, seed=8)
+    obj = _obj(ds, 60, 20)
+    d, paths, _ = obj.shadow(q, k=512)
+    Ts = [10, 5, 20]  # unsorted on purpose
+    mean, std = obj.predict_from_paths(d, paths, sb.RealizedVariance(Ts, vol), proba, eta)
+    mo, so = oracle.predict_from_paths(d, paths, 20, Ts, vol, proba, eta)
+    assert mean.shape == (5, 3) and mean.dtype == np.float32
+    assert np.allclose(mean, mo, rtol=1e-6, atol=0)
+    assert np.allclose(std, so, rtol=1e-5, atol=0)
+    # the host plugin path (arbitrary callable, as README.md:77-80) agrees with the fused kernel
+    lam = lambda x: sb.realized_variance(x, Ts=Ts, vol=vol)[:, :, 0, :]  # noqa: E731
+    mh, sh = obj.predict_from_paths(d, paths, lam, proba, eta)
+    assert np.allclose(mh, mo, rtol=2e-6) and np.allclose(sh, so, rtol=1e-4)
+
+
+def test_predict_end_to_end_chunks():
+    ds, q = make_inputs(128, 1024, 40, 6, seed=12)
+    obj = _obj(ds, 40, 20)
+    rv = sb.RealizedVariance([5, 10, 20])
+    p1, s1 = obj.predict(q, k=200, to_predict=rv, eta=0.1, n_context_splits=1)
+    p3, s3 = obj.predict(q, k=200, to_predict=rv, eta=0.1, n_context_splits=3, n_dataset_splits=8, cuda=True)
+    assert p1.shape == (6, 3) and np.array_equal(p1, p3) and np.array_equal(s1, s3)
+    d, paths, _ = obj.shadow(q, k=200)
+    mo, so = oracle.predict_from_paths(d, paths, 20, [5, 10, 20], False, "softmax", 0.1)
+    assert np.allclose(p1, mo, rtol=1e-6) and np.allclose(s1, so, rtol=1e-5)
+
+
+def test_merge_topk_equals_global():
+    ds, q = make_inputs(64, 700, 30, 3, seed=14)
+    k, H = 128, 10
+    rows = torch.tensor(ds[:, 0, :]).cuda()
+    qd = torch.tensor(q[:, 0, :]).cuda()
+    parts_d, parts_i = [], []
+    for s in range(0, 64, 16):
+        d, i, _ = _lib.scan_topk(rows[s:s + 16].contiguous(), 700, qd, H, k, s)
+        parts_d.append(d)
+        parts_i.append(i)
+    d, i = _lib.merge_topk(torch.stack(parts_d), torch.stack(parts_i), 700 - 30 - H + 1)
+    do, io = oracle.shadow_topk(ds, q, k, H)
+    assert_topk_equal(d.cpu().numpy(), i.cpu().numpy(), do, io)
+
+
+def test_full_size_properties_cfg2():
+    """BASELINE configs[1] (R=32768 x T=4096, W=252, k=1024) through size-independent
+    properties: ascending distances, every returned (r,t) re-evaluates to its distance on the
+    oracle, planted near-copies of the query are found at rank 0.., and the k-th distance
+    bounds an oracle-evaluated random sample of windows."""
+    R, T, W, H, k = 32768, 4096, 252, 20, 1024
+    g = torch.Generator().manual_seed(0)
+    ds = torch.randn(R, 1, T, generator=g, dtype=torch.float32) * 0.01
+    g = torch.Generator().manual_seed(1)
+    q = torch.randn(1, 1, W, generator=g, dtype=torch.float32) * 0.01
+    planted = [(31000, 77), (5, 3800), (16384, 0)]
+    for n, (r, t) in enumerate(planted):
+        ds[r, 0, t:t + W] = q[0, 0] * (1.0 + 0.01 * (n + 1))
+    obj = _obj(ds, W, H)
+    d, paths, idx = obj.shadow(q, k=k)
+    assert (np.diff(d[0]) >= 0).all()
+    assert [tuple(v) for v in idx[0, :3]] == planted
+    dsn = ds.numpy()
+    qn = q.numpy()[0, 0]
+    # every winner's distance re-evaluated by the oracle on its own window
+    for j in range(0, k, 7):
+        r, t = idx[0, j]
+        dd = oracle.distances(dsn[r:r + 1, :, t:t + W + H], qn, H)
+        assert dd.shape == (1, 1) and dd[0, 0] == d[0, j]
+        assert np.array_equal(paths[0, j, 0], dsn[r, 0, t:t + W + H])
+    # no window of an oracle-scanned row sample beats the k-th distance without being returned
+    rows = np.arange(0, R, 257)
+    do, io = oracle.shadow_topk(dsn[rows], qn, 64, H)
+    got = {tuple(v) for v in idx[0]}
+    for dist_, (rr, tt) in zip(do[0], io[0]):
+        if dist_ < d[0, -1]:
+            assert (int(rows[rr]), int(tt)) in got
