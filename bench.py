@@ -57,10 +57,10 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.idx = gpu_index
         self.rows = []
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.idx)], capture_output=True, text=True, timeout=5).stdout
@@ -69,10 +69,10 @@ class ClockSampler(threading.Thread):
                     self.rows.append(f)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._halt.wait(0.1)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         sm = sorted(int(float(r[1])) for r in self.rows if r[1].replace(".", "").isdigit())
         mx = [int(float(r[2])) for r in self.rows if r[2].replace(".", "").isdigit()]

@@ -44,9 +44,12 @@ struct QState {
     unsigned int count;          // keys appended to the current buffer (may exceed cap: overflow)
     unsigned int overflow;
     unsigned int cur;            // current ping-pong buffer
-    unsigned int pad;
+    unsigned int ccount;         // filter candidates awaiting the exact re-rank
+    float thr_fast;              // s_thr widened by the exact sequence's own rounding (filter compare)
+    float q2;                    // sum q_j^2 (fp64 accumulated, rounded once)
+    unsigned int pad[6];
 };
-static_assert(sizeof(QState) == 32, "QState layout");
+static_assert(sizeof(QState) == 64, "QState layout");
 
 struct ScanParams {
     const float *ds;
@@ -59,10 +62,14 @@ struct ScanParams {
     int nq;
     QState *st;            // (nq)
     unsigned long long *keys;  // (nq, 2, cap)
+    unsigned int *cand;        // (nq, cap) flat window indices that passed the filter
     unsigned int cap;
     int bulk_ok;           // rows are 16-byte aligned: TMA bulk staging
     int buf_floats;        // floats per staging buffer (multiple of 4)
     int wpad;              // padded query stride in shared memory
+    int epl;               // filter: samples per lane of the squared-prefix pass (odd multiple of 4)
+    int pfx_floats;        // filter: floats of the per-warp prefix buffer
+    float cw;              // filter: slack coefficient (W + 256) * 2^-24
 };
 
 // ------------------------------------------------------------------------------------------
@@ -126,6 +133,8 @@ __global__ void qprep_kernel(const float *__restrict__ q, int W, int nq, QState 
 #pragma unroll
     for (int l = 0; l < 8; ++l) s = __fadd_rn(s, acc[l]);
     for (int j = n8; j < W; ++j) s = __fadd_rn(s, __fmul_rn(x[j], x[j]));
+    double q2 = 0.0;
+    for (int j = 0; j < W; ++j) q2 += (double)x[j] * (double)x[j];
     QState z;
     z.tau_key = ~0ull;
     z.s_thr = __int_as_float(0x7f800000);
@@ -133,7 +142,10 @@ __global__ void qprep_kernel(const float *__restrict__ q, int W, int nq, QState 
     z.count = 0;
     z.overflow = 0;
     z.cur = 0;
-    z.pad = 0;
+    z.ccount = 0;
+    z.thr_fast = __int_as_float(0x7f800000);
+    z.q2 = (float)q2;
+    for (int i = 0; i < 6; ++i) z.pad[i] = 0;
     st[b] = z;
 }
 
@@ -300,6 +312,277 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_exact_kernel(const ScanP
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// filter scan (PSH_MODE_FILTER): one FMA per element instead of sub+mul+add
+// ------------------------------------------------------------------------------------------
+// ||q - y_t||^2 = Q2 + Y2_t - 2 D_t with D_t = sum_j q_j y_{t+j} (one FFMA chain per window) and
+// Y2_t = sum_j y_{t+j}^2 taken from a per-segment prefix sum of squares (one warp scan per
+// task).  The kernel evaluates a rigorous LOWER BOUND of the true squared distance,
+//     LB = Q2 + Y2^ - 2 D^ - cw (Q2 + Ptot),      cw = (W + 256) 2^-24,
+// (D^: |D^-D| <= gamma_W sum|q_j y_j| <= gamma_W (Q2+Y2)/2;  Y2^: difference of two prefix
+// values of depth <= 46 roundings, |Y2^-Y2| <= 96u Ptot;  Q2 rounded once;  <= 16u (Q2+Ptot) for
+// the combination itself;  Ptot = sum of squares of the whole staged segment >= every Y2_t)
+// and appends the window to the query's candidate list iff LB <= thr_fast, where thr_fast is
+// s_thr widened by the exact sequence's own worst-case rounding (select_kernel).  Every window
+// whose EXACT distance beats the threshold therefore passes; the survivors (a few 1e-4 of all
+// windows) are re-evaluated with the reference's exact sequence by rerank_kernel, so the final
+// top-k is bit-identical to PSH_MODE_EXACT.  NaN/Inf bounds pass (decided exactly later).
+template <bool GUARD>
+__device__ __forceinline__ void dot_block(float (&acc)[WPT], float (&ring)[RING], const float *__restrict__ yb,
+                                          const float *__restrict__ qs, int rem) {
+    float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int jj = 0; jj < RING; ++jj) {
+        if (GUARD && jj >= rem) break;
+        if ((jj & 3) == 0) {
+            const float4 v = *reinterpret_cast<const float4 *>(yb + jj + WPT);
+            ring[(jj + WPT + 0) & (RING - 1)] = v.x;
+            ring[(jj + WPT + 1) & (RING - 1)] = v.y;
+            ring[(jj + WPT + 2) & (RING - 1)] = v.z;
+            ring[(jj + WPT + 3) & (RING - 1)] = v.w;
+            q4 = *reinterpret_cast<const float4 *>(qs + jj);
+        }
+        const float qj = (jj & 3) == 0 ? q4.x : (jj & 3) == 1 ? q4.y : (jj & 3) == 2 ? q4.z : q4.w;
+#pragma unroll
+        for (int w = 0; w < WPT; ++w) acc[w] = fmaf(qj, ring[(jj + w) & (RING - 1)], acc[w]);
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS, 2) scan_filter_kernel(const ScanParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *qs_all = reinterpret_cast<float *>(smem_raw);
+    float *bufs = qs_all + (size_t)p.nq * p.wpad;
+    float *pfx_all = bufs + (size_t)SCAN_WARPS * 2 * p.buf_floats;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(pfx_all + (size_t)SCAN_WARPS * p.pfx_floats);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *mybuf = bufs + (size_t)warp * 2 * p.buf_floats;
+    float *pfx = pfx_all + (size_t)warp * p.pfx_floats;  // pfx[4 + i] = sum_{e<=i} y_e^2, pfx[0..3] = 0
+    const uint32_t bar0 = smem_u32(&bars[warp * 2]);
+
+    for (int i = threadIdx.x; i < p.nq * p.wpad; i += SCAN_THREADS) {
+        int b = i / p.wpad, j = i - b * p.wpad;
+        qs_all[i] = j < p.W ? p.queries[(size_t)b * p.W + j] : 0.0f;
+    }
+    if (lane < 4) pfx[lane] = 0.0f;
+    if (p.bulk_ok && lane == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const long long ntasks = (p.i1 - p.i0) * (long long)p.nseg;
+    const long long gw = (long long)blockIdx.x * SCAN_WARPS + warp;
+    const long long nw = (long long)gridDim.x * SCAN_WARPS;
+    const int need = SEG + p.W - 1;
+
+    auto task_src = [&](long long task, long long &row, int &t0, int &nvalid) {
+        long long slot = p.i0 + task / p.nseg;
+        int s = (int)(task - (task / p.nseg) * p.nseg);
+        row = (long long)(((unsigned long long)slot * (unsigned long long)p.perm) % (unsigned long long)p.R);
+        t0 = s * SEG;
+        nvalid = min(need, p.T - t0);
+    };
+    auto issue = [&](long long task, int which) {
+        long long row; int t0, nvalid;
+        task_src(task, row, t0, nvalid);
+        uint32_t bytes = (uint32_t)((nvalid + 3) & ~3) * 4u;
+        uint32_t bar = bar0 + 8u * which;
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(smem_u32(mybuf + (size_t)which * p.buf_floats), p.ds + row * p.row_stride + t0, bytes, bar);
+    };
+
+    uint32_t phase0 = 0, phase1 = 0;
+    if (p.bulk_ok && gw < ntasks && lane == 0) issue(gw, 0);
+
+    int n = 0;
+    for (long long task = gw; task < ntasks; task += nw, ++n) {
+        const int cur = n & 1;
+        long long row; int t0, nvalid;
+        task_src(task, row, t0, nvalid);
+        float *buf = mybuf + (size_t)cur * p.buf_floats;
+        if (p.bulk_ok) {
+            if (task + nw < ntasks && lane == 0) issue(task + nw, cur ^ 1);
+            if (cur == 0) { mbar_wait(bar0, phase0); phase0 ^= 1; }
+            else { mbar_wait(bar0 + 8, phase1); phase1 ^= 1; }
+        } else {
+            const float *src = p.ds + row * p.row_stride + t0;
+            for (int i = lane; i < nvalid; i += 32) buf[i] = __ldg(src + i);
+            __syncwarp();
+        }
+
+        // ---- prefix sums of squares over the staged segment (samples >= nvalid count as 0) ----
+        float ptot;
+        {
+            const int e0 = lane * p.epl;
+            const float *yl = buf + e0;
+            float tot = 0.0f;
+            for (int i = 0; i < p.epl; i += 4) {
+                float4 v = *reinterpret_cast<const float4 *>(yl + i);
+                v.x = e0 + i + 0 < nvalid ? v.x : 0.0f;
+                v.y = e0 + i + 1 < nvalid ? v.y : 0.0f;
+                v.z = e0 + i + 2 < nvalid ? v.z : 0.0f;
+                v.w = e0 + i + 3 < nvalid ? v.w : 0.0f;
+                tot = fmaf(v.x, v.x, tot); tot = fmaf(v.y, v.y, tot);
+                tot = fmaf(v.z, v.z, tot); tot = fmaf(v.w, v.w, tot);
+            }
+            float incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                float v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            ptot = __shfl_sync(FULL, incl, 31);
+            float run = incl - tot;  // exclusive offset of this lane
+            for (int i = 0; i < p.epl; i += 4) {
+                float4 v = *reinterpret_cast<const float4 *>(yl + i);
+                v.x = e0 + i + 0 < nvalid ? v.x : 0.0f;
+                v.y = e0 + i + 1 < nvalid ? v.y : 0.0f;
+                v.z = e0 + i + 2 < nvalid ? v.z : 0.0f;
+                v.w = e0 + i + 3 < nvalid ? v.w : 0.0f;
+                float4 o4;
+                run = fmaf(v.x, v.x, run); o4.x = run;
+                run = fmaf(v.y, v.y, run); o4.y = run;
+                run = fmaf(v.z, v.z, run); o4.z = run;
+                run = fmaf(v.w, v.w, run); o4.w = run;
+                *reinterpret_cast<float4 *>(pfx + 4 + e0 + i) = o4;
+            }
+            __syncwarp();
+        }
+
+        const float *yb = buf + lane * WPT;
+        const int tl = t0 + lane * WPT;
+        const int tloc = lane * WPT;
+        const unsigned int flat0 = (unsigned int)((unsigned long long)row * (unsigned long long)p.Tp + (unsigned long long)tl);
+
+        // Y2 of this lane's windows: pfx[4 + t+W-1] - pfx[4 + t-1]
+        float y2[WPT];
+        {
+            float lo[16];
+            const float4 a = *reinterpret_cast<const float4 *>(pfx + tloc + 0);
+            const float4 c = *reinterpret_cast<const float4 *>(pfx + tloc + 4);
+            const float4 e = *reinterpret_cast<const float4 *>(pfx + tloc + 8);
+            const float4 g = *reinterpret_cast<const float4 *>(pfx + tloc + 12);
+            lo[0] = a.x; lo[1] = a.y; lo[2] = a.z; lo[3] = a.w; lo[4] = c.x; lo[5] = c.y; lo[6] = c.z; lo[7] = c.w;
+            lo[8] = e.x; lo[9] = e.y; lo[10] = e.z; lo[11] = e.w; lo[12] = g.x; lo[13] = g.y; lo[14] = g.z; lo[15] = g.w;
+            const float *hi = pfx + tloc + p.W + 3;
+#pragma unroll
+            for (int w = 0; w < WPT; ++w) y2[w] = hi[w] - lo[w + 3];
+        }
+
+        for (int b = 0; b < p.nq; ++b) {
+            const float *qs = qs_all + (size_t)b * p.wpad;
+            float acc[WPT], ring[RING];
+#pragma unroll
+            for (int w = 0; w < WPT; ++w) acc[w] = 0.0f;
+            {
+                const float4 a = *reinterpret_cast<const float4 *>(yb + 0);
+                const float4 c = *reinterpret_cast<const float4 *>(yb + 4);
+                const float4 e = *reinterpret_cast<const float4 *>(yb + 8);
+                ring[0] = a.x; ring[1] = a.y; ring[2] = a.z; ring[3] = a.w;
+                ring[4] = c.x; ring[5] = c.y; ring[6] = c.z; ring[7] = c.w;
+                ring[8] = e.x; ring[9] = e.y; ring[10] = e.z; ring[11] = e.w;
+                ring[12] = ring[13] = ring[14] = ring[15] = 0.0f;
+            }
+            int j0 = 0;
+#pragma unroll 1
+            for (; j0 + RING <= p.W; j0 += RING) dot_block<false>(acc, ring, yb + j0, qs + j0, RING);
+            if (j0 < p.W) dot_block<true>(acc, ring, yb + j0, qs + j0, p.W - j0);
+
+            // ---- epilogue: LB <= thr_fast  <=>  (Y2^ - 2 D^) + (Q2 - slack - thr_fast) <= 0 ----
+            const float q2 = p.st[b].q2;
+            const float thr = ld_volatile_f32(&p.st[b].thr_fast);
+            const float base = (q2 - p.cw * (q2 + ptot)) - thr;
+            unsigned int mask = 0;
+#pragma unroll
+            for (int w = 0; w < WPT; ++w) {
+                const float v = fmaf(-2.0f, acc[w], y2[w]) + base;
+                if (tl + w < p.Tp && !(v > 0.0f)) mask |= 1u << w;
+            }
+            if (__any_sync(FULL, mask != 0)) {
+                const int cnt = __popc(mask);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int v = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int total = __shfl_sync(FULL, incl, 31);
+                unsigned int basepos = 0;
+                if (lane == 31) basepos = atomicAdd(&p.st[b].ccount, (unsigned int)total);
+                basepos = __shfl_sync(FULL, basepos, 31);
+                unsigned int pos = basepos + (unsigned int)(incl - cnt);
+                unsigned int *dst = p.cand + (size_t)b * p.cap;
+#pragma unroll
+                for (int w = 0; w < WPT; ++w)
+                    if (mask & (1u << w)) {
+                        if (pos < p.cap) dst[pos] = flat0 + w;
+                        ++pos;
+                    }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// exact re-rank of the filter's candidates: one thread per candidate evaluates the reference's
+// sequential sub/mul/add chain on the window, applies the exact thresholds and appends the
+// (distance bits, flat index) key.  grid = (blocks, nq).
+// ------------------------------------------------------------------------------------------
+constexpr int RERANK_THREADS = 128;
+
+__global__ void __launch_bounds__(RERANK_THREADS) rerank_kernel(const float *__restrict__ ds, long long row_stride,
+                                                                 unsigned int Tp, int W,
+                                                                 const float *__restrict__ queries, QState *st_all,
+                                                                 const unsigned int *__restrict__ cand_all,
+                                                                 unsigned long long *keys_all, unsigned int cap) {
+    extern __shared__ __align__(16) float qsh[];
+    const int b = blockIdx.y;
+    QState *st = st_all + b;
+    const unsigned int craw = st->ccount;
+    const unsigned int C = min(craw, cap);
+    if (craw > cap && threadIdx.x == 0 && blockIdx.x == 0) st->overflow = 1;
+    if (blockIdx.x * RERANK_THREADS >= C) return;
+    for (int j = threadIdx.x; j < W; j += RERANK_THREADS) qsh[j] = queries[(size_t)b * W + j];
+    __syncthreads();
+    const float s_thr = st->s_thr, qn = st->qnorm;
+    const unsigned long long tau = st->tau_key;
+    const unsigned int *cand = cand_all + (size_t)b * cap;
+    unsigned long long *dst = keys_all + ((size_t)b * 2 + st->cur) * cap;
+    const int lane = threadIdx.x & 31;
+    const unsigned int Cr = (C + 31u) & ~31u;
+    for (unsigned int i = blockIdx.x * RERANK_THREADS + threadIdx.x; i < Cr; i += gridDim.x * RERANK_THREADS) {
+        bool keep = false;
+        unsigned long long key = 0;
+        if (i < C) {
+            const unsigned int flat = cand[i];
+            const unsigned int r = flat / Tp, t = flat - r * Tp;
+            const float *y = ds + (long long)r * row_stride + t;
+            float s = 0.0f;
+#pragma unroll 4
+            for (int j = 0; j < W; ++j) {
+                const float df = __fsub_rn(qsh[j], __ldg(y + j));
+                s = __fadd_rn(s, __fmul_rn(df, df));
+            }
+            if (s <= s_thr) {
+                key = ((unsigned long long)__float_as_uint(dist_from_s(s, qn)) << 32) | flat;
+                keep = key <= tau;
+            }
+        }
+        const unsigned int bal = __ballot_sync(FULL, keep);
+        if (bal) {
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(&st->count, (unsigned int)__popc(bal));
+            base = __shfl_sync(FULL, base, 0);
+            const unsigned int pos = base + __popc(bal & ((1u << lane) - 1u));
+            if (keep && pos < cap) dst[pos] = key;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // select: keep the k smallest keys of a query's candidate list (MSB-first radix select on the
 // 64-bit key, compaction into the other ping-pong buffer), publish the new thresholds.
@@ -314,7 +597,7 @@ __device__ __forceinline__ void hist_add(unsigned int *hist, unsigned int digit,
 }
 
 __global__ void __launch_bounds__(SEL_THREADS) select_kernel(QState *st_all, unsigned long long *keys_all,
-                                                              unsigned int cap, unsigned int k) {
+                                                              unsigned int cap, unsigned int k, int W) {
     __shared__ unsigned int hist[256];
     __shared__ unsigned long long s_prefix;
     __shared__ unsigned int s_need, s_done, s_out;
@@ -330,7 +613,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(QState *st_all, uns
         s_prefix = 0; s_need = k; s_done = 0; s_out = 0;
     }
     if (M <= k) {  // nothing to drop yet (uniform branch: M, k are block-uniform)
-        if (tid == 0) st->count = M;
+        if (tid == 0) { st->count = M; st->ccount = 0; }
         return;
     }
     __syncthreads();
@@ -423,7 +706,13 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(QState *st_all, uns
         if (tid == 0) {
             st->tau_key = tau;
             st->s_thr = s_thr;
+            // exact s >= S_true (1 - gamma_{W+2}) - W 2^-126  =>  S_true <= thr_fast (rounded up)
+            const double widen = 1.0 + 2.0 * (double)(W + 8) * 5.9604644775390625e-8;
+            st->thr_fast = (s_thr < __int_as_float(0x7f800000))
+                               ? __double2float_ru((double)s_thr * widen + 1e-30)
+                               : s_thr;
             st->count = s_out;
+            st->ccount = 0;
             st->cur = cur ^ 1u;
         }
     }
@@ -654,7 +943,7 @@ struct Plan {
     unsigned int cap;
     long long n0;      // rows of the seeding chunk
     int growth;
-    size_t off_state, off_keys, total;
+    size_t off_state, off_keys, off_cand, total;
 };
 
 constexpr int SEED_FACTOR = 16;  // seeding chunk holds ~16 k windows
@@ -681,7 +970,8 @@ bool make_plan(long long R, long long T, int B, int W, int H, long long k, Plan 
     pl.cap = (unsigned int)cap;
     pl.off_state = 0;
     pl.off_keys = align_up((size_t)B * sizeof(QState), 256);
-    pl.total = pl.off_keys + (size_t)B * 2 * (size_t)pl.cap * sizeof(unsigned long long);
+    pl.off_cand = pl.off_keys + (size_t)B * 2 * (size_t)pl.cap * sizeof(unsigned long long);
+    pl.total = pl.off_cand + align_up((size_t)B * (size_t)pl.cap * sizeof(unsigned int), 256);
     return true;
 }
 
@@ -768,30 +1058,41 @@ size_t psh_scan_workspace_bytes(int64_t R, int64_t T, int B, int W, int H, int64
 
 static int run_scan_group(const float *d_dataset, long long R, long long T, long long row_stride,
                           const float *d_q, int nq, int W, int H, long long k, int row_offset,
-                          const Plan &pl, QState *st, unsigned long long *keys, bool safe,
-                          float *d_out_dist, int *d_out_idx, cudaStream_t stream) {
+                          const Plan &pl, QState *st, unsigned long long *keys, unsigned int *cand, int mode,
+                          bool safe, float *d_out_dist, int *d_out_idx, cudaStream_t stream) {
     (void)H;
     qprep_kernel<<<(nq + 127) / 128, 128, 0, stream>>>(d_q, W, nq, st);
     PSH_LAUNCHED();
 
+    const bool filter = (mode == PSH_MODE_FILTER) && !safe;
     ScanParams p;
     p.ds = d_dataset; p.row_stride = row_stride; p.T = (int)T; p.Tp = (int)pl.Tp; p.W = W;
     p.nseg = (int)((pl.Tp + SEG - 1) / SEG);
     p.R = R; p.perm = perm_stride(R);
-    p.queries = d_q; p.nq = nq; p.st = st; p.keys = keys; p.cap = pl.cap;
+    p.queries = d_q; p.nq = nq; p.st = st; p.keys = keys; p.cand = cand; p.cap = pl.cap;
     p.bulk_ok = ((reinterpret_cast<uintptr_t>(d_dataset) & 15u) == 0 && (row_stride & 3) == 0) ? 1 : 0;
-    p.buf_floats = (int)align_up((size_t)SEG + W - 1 + RING + 4, 4);
+    const int need = SEG + W - 1;
+    int epl4 = ((need + 31) / 32 + 3) / 4;
+    if ((epl4 & 1) == 0) ++epl4;  // odd multiple of 4 floats per lane: conflict-free LDS.128/STS.128
+    p.epl = 4 * epl4;
+    p.pfx_floats = 4 + 32 * p.epl + 4;
+    p.cw = (float)(W + 256) * 5.9604644775390625e-8f;
+    p.buf_floats = (int)align_up((size_t)need + RING + 4, 4);
+    if (p.buf_floats < 32 * p.epl) p.buf_floats = 32 * p.epl;
     p.wpad = (int)align_up((size_t)W + 4, 4);
-    const size_t smem = ((size_t)nq * p.wpad + (size_t)SCAN_WARPS * 2 * p.buf_floats) * sizeof(float)
-                        + (size_t)SCAN_WARPS * 2 * sizeof(unsigned long long);
-    if (smem > 200 * 1024) return PSH_E_UNSUPPORTED;
-    PSH_CUDA(cudaFuncSetAttribute(scan_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
-    if (ctas_per_sm > 2) ctas_per_sm = 2;
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    const size_t smem_exact = ((size_t)nq * p.wpad + (size_t)SCAN_WARPS * 2 * p.buf_floats) * sizeof(float)
+                              + (size_t)SCAN_WARPS * 2 * sizeof(unsigned long long);
+    const size_t smem_filter = smem_exact + (size_t)SCAN_WARPS * p.pfx_floats * sizeof(float);
+    if (smem_filter > 200 * 1024) return PSH_E_UNSUPPORTED;
+    PSH_CUDA(cudaFuncSetAttribute(scan_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_exact));
+    PSH_CUDA(cudaFuncSetAttribute(scan_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_filter));
+    auto ctas_per_sm = [](size_t smem) {
+        int c = (int)((220 * 1024) / (smem + 1024));
+        return c > 2 ? 2 : (c < 1 ? 1 : c);
+    };
 
-    // chunk schedule over permuted row slots: seed chunk, then geometric growth; in safe mode
-    // every chunk fits the candidate buffer even if all of its windows are appended
+    // chunk schedule over permuted row slots: seed chunk (always exact), then geometric growth;
+    // in safe mode every chunk fits the candidate buffer even if all of its windows are appended
     long long done = 0;
     long long safe_rows = ((long long)pl.cap - k) / pl.Tp;
     if (safe_rows < 1) safe_rows = 1;
@@ -801,18 +1102,36 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
         else next = done == 0 ? pl.n0 : done * pl.growth;
         if (next > R) next = R;
         p.i0 = done; p.i1 = next;
+        const bool use_filter = filter && done > 0;
         long long ntasks = (next - done) * p.nseg;
         long long ctas = (ntasks + SCAN_WARPS - 1) / SCAN_WARPS;
-        long long max_ctas = (long long)sm_count() * ctas_per_sm;
+        long long max_ctas = (long long)sm_count() * ctas_per_sm(use_filter ? smem_filter : smem_exact);
         if (ctas > max_ctas) ctas = max_ctas;
-        {
-            ProfScope ps(stream, 0);
-            scan_exact_kernel<<<(unsigned int)ctas, SCAN_THREADS, smem, stream>>>(p);
+        if (use_filter) {
+            {
+                ProfScope ps(stream, 0);
+                scan_filter_kernel<<<(unsigned int)ctas, SCAN_THREADS, smem_filter, stream>>>(p);
+            }
+            PSH_LAUNCHED();
+            unsigned int rb = (pl.cap + RERANK_THREADS - 1) / RERANK_THREADS;
+            unsigned int rb_max = (unsigned int)sm_count() * 8u;
+            if (rb > rb_max) rb = rb_max;
+            {
+                ProfScope ps(stream, 1);
+                rerank_kernel<<<dim3(rb, nq), RERANK_THREADS, (size_t)W * sizeof(float), stream>>>(
+                    d_dataset, row_stride, (unsigned int)pl.Tp, W, d_q, st, cand, keys, pl.cap);
+            }
+            PSH_LAUNCHED();
+        } else {
+            {
+                ProfScope ps(stream, 0);
+                scan_exact_kernel<<<(unsigned int)ctas, SCAN_THREADS, smem_exact, stream>>>(p);
+            }
+            PSH_LAUNCHED();
         }
-        PSH_LAUNCHED();
         {
             ProfScope ps(stream, 1);
-            select_kernel<<<nq, SEL_THREADS, 0, stream>>>(st, keys, pl.cap, (unsigned int)k);
+            select_kernel<<<nq, SEL_THREADS, 0, stream>>>(st, keys, pl.cap, (unsigned int)k, W);
         }
         PSH_LAUNCHED();
         done = next;
@@ -836,8 +1155,8 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
                       int32_t row_offset, int mode,
                       float *d_out_dist, int32_t *d_out_idx,
                       void *d_ws, size_t ws_bytes, void *stream_) {
-    (void)mode;
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (mode != PSH_MODE_EXACT && mode != PSH_MODE_FILTER) return PSH_E_ARG;
     if (!d_dataset || !d_queries || !d_out_dist || !d_out_idx || !d_ws) return PSH_E_ARG;
     if (row_stride < T) return PSH_E_ARG;
     Plan pl;
@@ -852,11 +1171,12 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
     unsigned char *ws = static_cast<unsigned char *>(d_ws);
     QState *st = reinterpret_cast<QState *>(ws + pl.off_state);
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(ws + pl.off_keys);
+    unsigned int *cand = reinterpret_cast<unsigned int *>(ws + pl.off_cand);
 
     for (int g0 = 0; g0 < B; g0 += QG_MAX) {
         int nq = B - g0 < QG_MAX ? B - g0 : QG_MAX;
         int rc = run_scan_group(d_dataset, R, T, row_stride, d_queries + (size_t)g0 * W, nq, W, H, k, row_offset,
-                                pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, false,
+                                pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap, mode, false,
                                 d_out_dist + (size_t)g0 * k, d_out_idx + (size_t)g0 * k * 2, stream);
         if (rc != PSH_OK) return rc;
     }
@@ -870,7 +1190,8 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
         for (int i = 0; i < nq; ++i) ovf = ovf || hst[i].overflow != 0;
         if (ovf) {
             int rc = run_scan_group(d_dataset, R, T, row_stride, d_queries + (size_t)g0 * W, nq, W, H, k, row_offset,
-                                    pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, true,
+                                    pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap, mode,
+                                    true,
                                     d_out_dist + (size_t)g0 * k, d_out_idx + (size_t)g0 * k * 2, stream);
             if (rc != PSH_OK) return rc;
             PSH_CUDA(cudaStreamSynchronize(stream));
