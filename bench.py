@@ -48,7 +48,8 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed regions (B200_PROFILING.md's clocks
+    line), through NVML in-process (10 ms period); falls back to polling nvidia-smi."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -56,33 +57,66 @@ class ClockSampler(threading.Thread):
     def __init__(self, gpu_index: int):
         super().__init__(daemon=True)
         self.idx = gpu_index
-        self.rows = []
+        self.sm, self.mx, self.reasons, self.power = [], [], set(), []
         self._halt = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(int(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+        self.mx.append(int(n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)))
+        try:
+            self.power.append(n.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+        except Exception:
+            pass
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = int(get(self.h))
+        for name, const in (("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                            ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                            ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                            ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap")):
+            if bits & int(getattr(n, const, 0)):
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                              "-i", str(self.idx)], capture_output=True, text=True, timeout=5).stdout
+        f = [x.strip() for x in out.strip().split(",")]
+        if len(f) >= 8:
+            self.sm.append(int(float(f[1])))
+            self.mx.append(int(float(f[2])))
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.idx)], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 8:
-                    self.rows.append(f)
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._halt.wait(0.1)
+            self._halt.wait(0.01 if self.nvml is not None else 0.1)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=6)
-        sm = sorted(int(float(r[1])) for r in self.rows if r[1].replace(".", "").isdigit())
-        mx = [int(float(r[2])) for r in self.rows if r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": max(self.mx) if self.mx else None, "reasons": sorted(self.reasons),
+                "samples": len(sm), "power_w_max": max(self.power) if self.power else None,
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def make_shard(rank: int):

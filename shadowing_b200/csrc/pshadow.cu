@@ -55,7 +55,10 @@ struct ScanParams {
     const float *ds;
     long long row_stride;
     int T, Tp, W, nseg;
+    unsigned int nseg_m, nseg_s;  // multiply-high division by nseg
+    unsigned int ntasks;   // (i1 - i0) * nseg, < 2^32
     long long R;
+    double inv_R;
     long long i0, i1;      // range of permuted row slots scanned by this launch
     long long perm;        // row = (slot * perm) % R, gcd(perm, R) = 1
     const float *queries;  // (nq, W)
@@ -150,15 +153,22 @@ __global__ void qprep_kernel(const float *__restrict__ q, int W, int nq, QState 
 }
 
 // ------------------------------------------------------------------------------------------
-// exact scan
+// the scan kernel (exact and filter flavours share staging, task decode and register tiling)
 // ------------------------------------------------------------------------------------------
-// One block of up to RING reduction steps j = j0 .. j0+RING-1 for the WPT windows of a lane.
-// ring[m & 15] holds sample (j0 + m) of the lane's run; a float4 of new samples and of query
-// values is fetched every 4 steps.  Arithmetic is strictly sub -> mul -> add (never FMA), j
-// ascending: the reference's reduction order, hence its bits.
-template <bool GUARD>
-__device__ __forceinline__ void exact_block(float (&acc)[WPT], float (&ring)[RING], const float *__restrict__ yb,
-                                            const float *__restrict__ qs, int rem) {
+// Work unit ("task") = SEG consecutive windows of one trajectory, owned by one warp:
+//   * lane 0 stages the SEG+W-1 samples the task touches with ONE TMA bulk copy
+//     (cp.async.bulk -> mbarrier complete_tx), double buffered per warp: the copy of the warp's
+//     next task is in flight while the current one is evaluated; no CTA-wide barrier exists in
+//     the steady state;
+//   * each lane owns WPT consecutive windows and slides them through a 16-register ring: one
+//     LDS.128 of samples and one LDS.128 (broadcast) of query values feed 4 reduction steps x
+//     WPT windows of arithmetic;
+//   * exact flavour: acc = fl(acc + fl(fl(q_j - y)^2)), j ascending, never FMA -- the
+//     reference's reduction order (path_distance.py:65 on the conv1d windows), hence its bits;
+//   * filter flavour: one FMA per element, see below.
+template <bool EXACT, bool GUARD>
+__device__ __forceinline__ void step_block(float (&acc)[WPT], float (&ring)[RING], const float *__restrict__ yb,
+                                           const float *__restrict__ qs, int rem) {
     float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int jj = 0; jj < RING; ++jj) {
@@ -174,151 +184,47 @@ __device__ __forceinline__ void exact_block(float (&acc)[WPT], float (&ring)[RIN
         const float qj = (jj & 3) == 0 ? q4.x : (jj & 3) == 1 ? q4.y : (jj & 3) == 2 ? q4.z : q4.w;
 #pragma unroll
         for (int w = 0; w < WPT; ++w) {
-            const float df = __fsub_rn(qj, ring[(jj + w) & (RING - 1)]);
-            acc[w] = __fadd_rn(acc[w], __fmul_rn(df, df));
+            if (EXACT) {
+                const float df = __fsub_rn(qj, ring[(jj + w) & (RING - 1)]);
+                acc[w] = __fadd_rn(acc[w], __fmul_rn(df, df));
+            } else {
+                acc[w] = fmaf(qj, ring[(jj + w) & (RING - 1)], acc[w]);
+            }
         }
     }
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS, 2) scan_exact_kernel(const ScanParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *qs_all = reinterpret_cast<float *>(smem_raw);
-    float *bufs = qs_all + (size_t)p.nq * p.wpad;
-    unsigned long long *bars =
-        reinterpret_cast<unsigned long long *>(bufs + (size_t)SCAN_WARPS * 2 * p.buf_floats);
+// Note on the filter flavour's inner loop (measured, profiles/r01_*): a scalar FFMA reads three
+// registers while the register file serves one even and one odd register per cycle; the query
+// value sits in the operand-reuse cache, but with a sliding ring every accumulator meets every
+// sample slot, so ptxas cannot keep (sample, accumulator) in opposite banks everywhere: ~60 % of
+// the FFMAs take two cycles (66 % FP32-pipe utilisation).  Two alternatives were built and
+// measured slower on B200: a dual-ring layout (samples duplicated with flipped parity; ptxas
+// re-schedules across steps and loses the property) and packed FFMA2 (fma.rn.f32x2; 1.67 ms vs
+// 1.44 ms per query -- three 64-bit operand reads per instruction without reuse).
+struct Task { long long row; int t0; int nvalid; };
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *mybuf = bufs + (size_t)warp * 2 * p.buf_floats;
-    const uint32_t bar0 = smem_u32(&bars[warp * 2]);
-
-    // stage the queries (zero padded to wpad so the float4 fetch of the tail stays in bounds)
-    for (int i = threadIdx.x; i < p.nq * p.wpad; i += SCAN_THREADS) {
-        int b = i / p.wpad, j = i - b * p.wpad;
-        qs_all[i] = j < p.W ? p.queries[(size_t)b * p.W + j] : 0.0f;
-    }
-    if (p.bulk_ok && lane == 0) {
-        mbar_init(bar0, 1);
-        mbar_init(bar0 + 8, 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    const long long ntasks = (p.i1 - p.i0) * (long long)p.nseg;
-    const long long gw = (long long)blockIdx.x * SCAN_WARPS + warp;
-    const long long nw = (long long)gridDim.x * SCAN_WARPS;
-    const int need = SEG + p.W - 1;  // samples a full segment touches
-
-    auto task_src = [&](long long task, long long &row, int &t0, int &nvalid) {
-        long long slot = p.i0 + task / p.nseg;
-        int s = (int)(task - (task / p.nseg) * p.nseg);
-        row = (long long)(((unsigned long long)slot * (unsigned long long)p.perm) % (unsigned long long)p.R);
-        t0 = s * SEG;
-        nvalid = min(need, p.T - t0);
-    };
-    auto issue = [&](long long task, int which) {  // lane 0 only
-        long long row; int t0, nvalid;
-        task_src(task, row, t0, nvalid);
-        uint32_t bytes = (uint32_t)((nvalid + 3) & ~3) * 4u;
-        uint32_t bar = bar0 + 8u * which;
-        mbar_expect_tx(bar, bytes);
-        bulk_g2s(smem_u32(mybuf + (size_t)which * p.buf_floats), p.ds + row * p.row_stride + t0, bytes, bar);
-    };
-
-    uint32_t phase0 = 0, phase1 = 0;
-    if (p.bulk_ok && gw < ntasks && lane == 0) issue(gw, 0);
-
-    int n = 0;
-    for (long long task = gw; task < ntasks; task += nw, ++n) {
-        const int cur = n & 1;
-        long long row; int t0, nvalid;
-        task_src(task, row, t0, nvalid);
-        float *buf = mybuf + (size_t)cur * p.buf_floats;
-        if (p.bulk_ok) {
-            if (task + nw < ntasks && lane == 0) issue(task + nw, cur ^ 1);
-            if (cur == 0) { mbar_wait(bar0, phase0); phase0 ^= 1; }
-            else { mbar_wait(bar0 + 8, phase1); phase1 ^= 1; }
-        } else {
-            const float *src = p.ds + row * p.row_stride + t0;
-            for (int i = lane; i < nvalid; i += 32) buf[i] = __ldg(src + i);
-            __syncwarp();
-        }
-
-        const float *yb = buf + lane * WPT;
-        const int tl = t0 + lane * WPT;  // first window of this lane
-        const unsigned int flat0 = (unsigned int)((unsigned long long)row * (unsigned long long)p.Tp + (unsigned long long)tl);
-
-        for (int b = 0; b < p.nq; ++b) {
-            const float *qs = qs_all + (size_t)b * p.wpad;
-            float acc[WPT], ring[RING];
-#pragma unroll
-            for (int w = 0; w < WPT; ++w) acc[w] = 0.0f;
-            {
-                const float4 a = *reinterpret_cast<const float4 *>(yb + 0);
-                const float4 c = *reinterpret_cast<const float4 *>(yb + 4);
-                const float4 e = *reinterpret_cast<const float4 *>(yb + 8);
-                ring[0] = a.x; ring[1] = a.y; ring[2] = a.z; ring[3] = a.w;
-                ring[4] = c.x; ring[5] = c.y; ring[6] = c.z; ring[7] = c.w;
-                ring[8] = e.x; ring[9] = e.y; ring[10] = e.z; ring[11] = e.w;
-                ring[12] = ring[13] = ring[14] = ring[15] = 0.0f;
-            }
-            int j0 = 0;
-#pragma unroll 1
-            for (; j0 + RING <= p.W; j0 += RING) exact_block<false>(acc, ring, yb + j0, qs + j0, RING);
-            if (j0 < p.W) exact_block<true>(acc, ring, yb + j0, qs + j0, p.W - j0);
-
-            // ---- epilogue: rare candidates go to the per-query key list ----
-            const float s_thr = ld_volatile_f32(&p.st[b].s_thr);
-            unsigned int mask = 0;
-#pragma unroll
-            for (int w = 0; w < WPT; ++w)
-                if (tl + w < p.Tp && acc[w] <= s_thr) mask |= 1u << w;
-            if (__any_sync(FULL, mask != 0)) {
-                const float qn = p.st[b].qnorm;
-                const unsigned long long tau = ld_volatile_u64(&p.st[b].tau_key);
-                unsigned long long key[WPT];
-#pragma unroll
-                for (int w = 0; w < WPT; ++w) {
-                    key[w] = 0;
-                    if (mask & (1u << w)) {
-                        const float d = dist_from_s(acc[w], qn);
-                        key[w] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(flat0 + w);
-                        if (key[w] > tau) mask &= ~(1u << w);
-                    }
-                }
-                const int cnt = __popc(mask);
-                int incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    int v = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                const int total = __shfl_sync(FULL, incl, 31);
-                if (total > 0) {
-                    unsigned int base = 0;
-                    if (lane == 31) base = atomicAdd(&p.st[b].count, (unsigned int)total);
-                    base = __shfl_sync(FULL, base, 31);
-                    unsigned int pos = base + (unsigned int)(incl - cnt);
-                    unsigned long long *dst = p.keys + ((size_t)b * 2 + p.st[b].cur) * p.cap;
-#pragma unroll
-                    for (int w = 0; w < WPT; ++w)
-                        if (mask & (1u << w)) {
-                            if (pos < p.cap) dst[pos] = key[w];
-                            ++pos;
-                        }
-                }
-            }
-        }
-        __syncwarp();  // every lane is done with buf before it is refilled
-    }
+__device__ __forceinline__ Task decode_task(const ScanParams &p, unsigned int task) {
+    // task -> (row slot, segment): division by the launch-invariant nseg via multiply-high
+    const unsigned int sr = (unsigned int)(((unsigned long long)__umulhi(task, p.nseg_m) + task) >> p.nseg_s);
+    const unsigned int seg = task - sr * (unsigned int)p.nseg;
+    // row = (slot * perm) mod R: quotient estimated in fp64 (exact to +-1), remainder fixed up
+    const unsigned long long prod = (unsigned long long)(p.i0 + sr) * (unsigned long long)p.perm;
+    const unsigned long long q = __double2ull_rz(__ull2double_rz(prod) * p.inv_R);
+    long long r = (long long)(prod - q * (unsigned long long)p.R);
+    if (r < 0) r += p.R;
+    else if (r >= p.R) r -= p.R;
+    Task t;
+    t.row = r;
+    t.t0 = (int)seg * SEG;
+    t.nvalid = min(SEG + p.W - 1, p.T - t.t0);
+    return t;
 }
 
-
-// ------------------------------------------------------------------------------------------
-// filter scan (PSH_MODE_FILTER): one FMA per element instead of sub+mul+add
-// ------------------------------------------------------------------------------------------
-// ||q - y_t||^2 = Q2 + Y2_t - 2 D_t with D_t = sum_j q_j y_{t+j} (one FFMA chain per window) and
-// Y2_t = sum_j y_{t+j}^2 taken from a per-segment prefix sum of squares (one warp scan per
-// task).  The kernel evaluates a rigorous LOWER BOUND of the true squared distance,
+// Filter flavour (PSH_MODE_FILTER): ||q - y_t||^2 = Q2 + Y2_t - 2 D_t with D_t = sum_j q_j y_{t+j}
+// (one FFMA chain per window) and Y2_t = sum_j y_{t+j}^2 taken from a per-task prefix sum of
+// squares (one warp scan).  The kernel evaluates a rigorous LOWER BOUND of the true squared
+// distance,
 //     LB = Q2 + Y2^ - 2 D^ - cw (Q2 + Ptot),      cw = (W + 256) 2^-24,
 // (D^: |D^-D| <= gamma_W sum|q_j y_j| <= gamma_W (Q2+Y2)/2;  Y2^: difference of two prefix
 // values of depth <= 46 roundings, |Y2^-Y2| <= 96u Ptot;  Q2 rounded once;  <= 16u (Q2+Ptot) for
@@ -328,44 +234,26 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_exact_kernel(const ScanP
 // whose EXACT distance beats the threshold therefore passes; the survivors (a few 1e-4 of all
 // windows) are re-evaluated with the reference's exact sequence by rerank_kernel, so the final
 // top-k is bit-identical to PSH_MODE_EXACT.  NaN/Inf bounds pass (decided exactly later).
-template <bool GUARD>
-__device__ __forceinline__ void dot_block(float (&acc)[WPT], float (&ring)[RING], const float *__restrict__ yb,
-                                          const float *__restrict__ qs, int rem) {
-    float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int jj = 0; jj < RING; ++jj) {
-        if (GUARD && jj >= rem) break;
-        if ((jj & 3) == 0) {
-            const float4 v = *reinterpret_cast<const float4 *>(yb + jj + WPT);
-            ring[(jj + WPT + 0) & (RING - 1)] = v.x;
-            ring[(jj + WPT + 1) & (RING - 1)] = v.y;
-            ring[(jj + WPT + 2) & (RING - 1)] = v.z;
-            ring[(jj + WPT + 3) & (RING - 1)] = v.w;
-            q4 = *reinterpret_cast<const float4 *>(qs + jj);
-        }
-        const float qj = (jj & 3) == 0 ? q4.x : (jj & 3) == 1 ? q4.y : (jj & 3) == 2 ? q4.z : q4.w;
-#pragma unroll
-        for (int w = 0; w < WPT; ++w) acc[w] = fmaf(qj, ring[(jj + w) & (RING - 1)], acc[w]);
-    }
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS, 2) scan_filter_kernel(const ScanParams p) {
+template <bool EXACT>
+__global__ void __launch_bounds__(SCAN_THREADS, EXACT ? 2 : 3) scan_kernel(const ScanParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *qs_all = reinterpret_cast<float *>(smem_raw);
     float *bufs = qs_all + (size_t)p.nq * p.wpad;
     float *pfx_all = bufs + (size_t)SCAN_WARPS * 2 * p.buf_floats;
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(pfx_all + (size_t)SCAN_WARPS * p.pfx_floats);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(
+        pfx_all + (EXACT ? (size_t)0 : (size_t)SCAN_WARPS * p.pfx_floats));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *mybuf = bufs + (size_t)warp * 2 * p.buf_floats;
     float *pfx = pfx_all + (size_t)warp * p.pfx_floats;  // pfx[4 + i] = sum_{e<=i} y_e^2, pfx[0..3] = 0
     const uint32_t bar0 = smem_u32(&bars[warp * 2]);
 
+    // stage the queries (zero padded to wpad so the float4 fetch of the tail stays in bounds)
     for (int i = threadIdx.x; i < p.nq * p.wpad; i += SCAN_THREADS) {
-        int b = i / p.wpad, j = i - b * p.wpad;
+        const int b = i / p.wpad, j = i - b * p.wpad;
         qs_all[i] = j < p.W ? p.queries[(size_t)b * p.W + j] : 0.0f;
     }
-    if (lane < 4) pfx[lane] = 0.0f;
+    if (!EXACT && lane < 4) pfx[lane] = 0.0f;
     if (p.bulk_ok && lane == 0) {
         mbar_init(bar0, 1);
         mbar_init(bar0 + 8, 1);
@@ -373,75 +261,70 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_filter_kernel(const Scan
     }
     __syncthreads();
 
-    const long long ntasks = (p.i1 - p.i0) * (long long)p.nseg;
-    const long long gw = (long long)blockIdx.x * SCAN_WARPS + warp;
-    const long long nw = (long long)gridDim.x * SCAN_WARPS;
-    const int need = SEG + p.W - 1;
+    const unsigned int ntasks = p.ntasks;
+    const unsigned int gw = blockIdx.x * SCAN_WARPS + warp;
+    const unsigned int nw = gridDim.x * SCAN_WARPS;
+    if (gw >= ntasks) return;
 
-    auto task_src = [&](long long task, long long &row, int &t0, int &nvalid) {
-        long long slot = p.i0 + task / p.nseg;
-        int s = (int)(task - (task / p.nseg) * p.nseg);
-        row = (long long)(((unsigned long long)slot * (unsigned long long)p.perm) % (unsigned long long)p.R);
-        t0 = s * SEG;
-        nvalid = min(need, p.T - t0);
-    };
-    auto issue = [&](long long task, int which) {
-        long long row; int t0, nvalid;
-        task_src(task, row, t0, nvalid);
-        uint32_t bytes = (uint32_t)((nvalid + 3) & ~3) * 4u;
-        uint32_t bar = bar0 + 8u * which;
+    auto issue = [&](const Task &t, int which) {  // lane 0 only
+        const uint32_t bytes = (uint32_t)((t.nvalid + 3) & ~3) * 4u;
+        const uint32_t bar = bar0 + 8u * which;
         mbar_expect_tx(bar, bytes);
-        bulk_g2s(smem_u32(mybuf + (size_t)which * p.buf_floats), p.ds + row * p.row_stride + t0, bytes, bar);
+        bulk_g2s(smem_u32(mybuf + (size_t)which * p.buf_floats), p.ds + t.row * p.row_stride + t.t0, bytes, bar);
     };
 
+    Task tk = decode_task(p, gw);
     uint32_t phase0 = 0, phase1 = 0;
-    if (p.bulk_ok && gw < ntasks && lane == 0) issue(gw, 0);
+    if (p.bulk_ok && lane == 0) issue(tk, 0);
 
     int n = 0;
-    for (long long task = gw; task < ntasks; task += nw, ++n) {
+    for (unsigned int task = gw; task < ntasks; ++n) {
         const int cur = n & 1;
-        long long row; int t0, nvalid;
-        task_src(task, row, t0, nvalid);
+        const unsigned int next = task + nw;
+        const bool have_next = next < ntasks && next > task;
+        Task tn = tk;
+        if (have_next) tn = decode_task(p, next);
         float *buf = mybuf + (size_t)cur * p.buf_floats;
         if (p.bulk_ok) {
-            if (task + nw < ntasks && lane == 0) issue(task + nw, cur ^ 1);
+            if (have_next && lane == 0) issue(tn, cur ^ 1);
             if (cur == 0) { mbar_wait(bar0, phase0); phase0 ^= 1; }
             else { mbar_wait(bar0 + 8, phase1); phase1 ^= 1; }
         } else {
-            const float *src = p.ds + row * p.row_stride + t0;
-            for (int i = lane; i < nvalid; i += 32) buf[i] = __ldg(src + i);
-            __syncwarp();
+            const float *src = p.ds + tk.row * p.row_stride + tk.t0;
+            for (int i = lane; i < tk.nvalid; i += 32) buf[i] = __ldg(src + i);
         }
+        const int t0 = tk.t0;
+        const float *yb = buf + lane * WPT;
+        const int tl = t0 + lane * WPT;  // first window of this lane
+        const unsigned int flat0 =
+            (unsigned int)((unsigned long long)tk.row * (unsigned long long)p.Tp + (unsigned long long)tl);
+        const bool all_valid = t0 + SEG <= p.Tp;
 
-        // ---- prefix sums of squares over the staged segment (samples >= nvalid count as 0) ----
-        float ptot;
-        {
+        float y2[WPT];
+        float ptot = 0.0f;
+        if (!EXACT) {
+            // samples beyond the valid part of the row count as zeros in the prefix sums
+            for (int i = tk.nvalid + lane; i < 32 * p.epl; i += 32) buf[i] = 0.0f;
+            __syncwarp();
+            // ---- inclusive prefix sums of squares over the staged segment ----
             const int e0 = lane * p.epl;
             const float *yl = buf + e0;
             float tot = 0.0f;
             for (int i = 0; i < p.epl; i += 4) {
-                float4 v = *reinterpret_cast<const float4 *>(yl + i);
-                v.x = e0 + i + 0 < nvalid ? v.x : 0.0f;
-                v.y = e0 + i + 1 < nvalid ? v.y : 0.0f;
-                v.z = e0 + i + 2 < nvalid ? v.z : 0.0f;
-                v.w = e0 + i + 3 < nvalid ? v.w : 0.0f;
+                const float4 v = *reinterpret_cast<const float4 *>(yl + i);
                 tot = fmaf(v.x, v.x, tot); tot = fmaf(v.y, v.y, tot);
                 tot = fmaf(v.z, v.z, tot); tot = fmaf(v.w, v.w, tot);
             }
             float incl = tot;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                float v = __shfl_up_sync(FULL, incl, o);
+                const float v = __shfl_up_sync(FULL, incl, o);
                 if (lane >= o) incl += v;
             }
             ptot = __shfl_sync(FULL, incl, 31);
             float run = incl - tot;  // exclusive offset of this lane
             for (int i = 0; i < p.epl; i += 4) {
-                float4 v = *reinterpret_cast<const float4 *>(yl + i);
-                v.x = e0 + i + 0 < nvalid ? v.x : 0.0f;
-                v.y = e0 + i + 1 < nvalid ? v.y : 0.0f;
-                v.z = e0 + i + 2 < nvalid ? v.z : 0.0f;
-                v.w = e0 + i + 3 < nvalid ? v.w : 0.0f;
+                const float4 v = *reinterpret_cast<const float4 *>(yl + i);
                 float4 o4;
                 run = fmaf(v.x, v.x, run); o4.x = run;
                 run = fmaf(v.y, v.y, run); o4.y = run;
@@ -450,16 +333,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_filter_kernel(const Scan
                 *reinterpret_cast<float4 *>(pfx + 4 + e0 + i) = o4;
             }
             __syncwarp();
-        }
-
-        const float *yb = buf + lane * WPT;
-        const int tl = t0 + lane * WPT;
-        const int tloc = lane * WPT;
-        const unsigned int flat0 = (unsigned int)((unsigned long long)row * (unsigned long long)p.Tp + (unsigned long long)tl);
-
-        // Y2 of this lane's windows: pfx[4 + t+W-1] - pfx[4 + t-1]
-        float y2[WPT];
-        {
+            // Y2 of this lane's windows: pfx[4 + t+W-1] - pfx[4 + t-1]
+            const int tloc = lane * WPT;
             float lo[16];
             const float4 a = *reinterpret_cast<const float4 *>(pfx + tloc + 0);
             const float4 c = *reinterpret_cast<const float4 *>(pfx + tloc + 4);
@@ -470,6 +345,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_filter_kernel(const Scan
             const float *hi = pfx + tloc + p.W + 3;
 #pragma unroll
             for (int w = 0; w < WPT; ++w) y2[w] = hi[w] - lo[w + 3];
+        } else {
+            if (!p.bulk_ok) __syncwarp();
         }
 
         for (int b = 0; b < p.nq; ++b) {
@@ -488,89 +365,167 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_filter_kernel(const Scan
             }
             int j0 = 0;
 #pragma unroll 1
-            for (; j0 + RING <= p.W; j0 += RING) dot_block<false>(acc, ring, yb + j0, qs + j0, RING);
-            if (j0 < p.W) dot_block<true>(acc, ring, yb + j0, qs + j0, p.W - j0);
+            for (; j0 + RING <= p.W; j0 += RING) step_block<EXACT, false>(acc, ring, yb + j0, qs + j0, RING);
+            if (j0 < p.W) step_block<EXACT, true>(acc, ring, yb + j0, qs + j0, p.W - j0);
 
-            // ---- epilogue: LB <= thr_fast  <=>  (Y2^ - 2 D^) + (Q2 - slack - thr_fast) <= 0 ----
-            const float q2 = p.st[b].q2;
-            const float thr = ld_volatile_f32(&p.st[b].thr_fast);
-            const float base = (q2 - p.cw * (q2 + ptot)) - thr;
+            // ---- epilogue: rare candidates are appended to the per-query lists ----
             unsigned int mask = 0;
+            if (EXACT) {
+                const float s_thr = ld_volatile_f32(&p.st[b].s_thr);
 #pragma unroll
-            for (int w = 0; w < WPT; ++w) {
-                const float v = fmaf(-2.0f, acc[w], y2[w]) + base;
-                if (tl + w < p.Tp && !(v > 0.0f)) mask |= 1u << w;
+                for (int w = 0; w < WPT; ++w)
+                    if (acc[w] <= s_thr) mask |= 1u << w;
+            } else {
+                // LB <= thr_fast  <=>  (Y2^ - 2 D^) + (Q2 - slack - thr_fast) <= 0
+                const float q2 = p.st[b].q2;
+                const float thr = ld_volatile_f32(&p.st[b].thr_fast);
+                const float base = (q2 - p.cw * (q2 + ptot)) - thr;
+#pragma unroll
+                for (int w = 0; w < WPT; ++w) {
+                    const float v = fmaf(-2.0f, acc[w], y2[w]) + base;
+                    if (!(v > 0.0f)) mask |= 1u << w;
+                }
+            }
+            if (!all_valid) {
+#pragma unroll
+                for (int w = 0; w < WPT; ++w)
+                    if (tl + w >= p.Tp) mask &= ~(1u << w);
             }
             if (__any_sync(FULL, mask != 0)) {
+                unsigned long long key[WPT];
+                if (EXACT) {
+                    const float qn = p.st[b].qnorm;
+                    const unsigned long long tau = ld_volatile_u64(&p.st[b].tau_key);
+#pragma unroll
+                    for (int w = 0; w < WPT; ++w) {
+                        key[w] = 0;
+                        if (mask & (1u << w)) {
+                            const float d = dist_from_s(acc[w], qn);
+                            key[w] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(flat0 + w);
+                            if (key[w] > tau) mask &= ~(1u << w);
+                        }
+                    }
+                }
                 const int cnt = __popc(mask);
                 int incl = cnt;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    int v = __shfl_up_sync(FULL, incl, o);
+                    const int v = __shfl_up_sync(FULL, incl, o);
                     if (lane >= o) incl += v;
                 }
                 const int total = __shfl_sync(FULL, incl, 31);
-                unsigned int basepos = 0;
-                if (lane == 31) basepos = atomicAdd(&p.st[b].ccount, (unsigned int)total);
-                basepos = __shfl_sync(FULL, basepos, 31);
-                unsigned int pos = basepos + (unsigned int)(incl - cnt);
-                unsigned int *dst = p.cand + (size_t)b * p.cap;
+                if (total > 0) {
+                    unsigned int base = 0;
+                    if (lane == 31) base = atomicAdd(EXACT ? &p.st[b].count : &p.st[b].ccount, (unsigned int)total);
+                    base = __shfl_sync(FULL, base, 31);
+                    unsigned int pos = base + (unsigned int)(incl - cnt);
+                    if (EXACT) {
+                        unsigned long long *dst = p.keys + ((size_t)b * 2 + p.st[b].cur) * p.cap;
 #pragma unroll
-                for (int w = 0; w < WPT; ++w)
-                    if (mask & (1u << w)) {
-                        if (pos < p.cap) dst[pos] = flat0 + w;
-                        ++pos;
+                        for (int w = 0; w < WPT; ++w)
+                            if (mask & (1u << w)) {
+                                if (pos < p.cap) dst[pos] = key[w];
+                                ++pos;
+                            }
+                    } else {
+                        unsigned int *dst = p.cand + (size_t)b * p.cap;
+#pragma unroll
+                        for (int w = 0; w < WPT; ++w)
+                            if (mask & (1u << w)) {
+                                if (pos < p.cap) dst[pos] = flat0 + w;
+                                ++pos;
+                            }
                     }
+                }
             }
         }
-        __syncwarp();
+        __syncwarp();  // every lane is done with buf before it is refilled
+        if (!have_next) break;
+        tk = tn;
+        task = next;
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// exact re-rank of the filter's candidates: one thread per candidate evaluates the reference's
-// sequential sub/mul/add chain on the window, applies the exact thresholds and appends the
-// (distance bits, flat index) key.  grid = (blocks, nq).
+// exact re-rank of the filter's candidates.  Each warp takes 32 candidates at a time: their
+// windows are staged into a shared-memory tile with coalesced 4-byte cp.async copies (windows
+// are only 4-byte aligned), then lane c evaluates candidate c with the reference's sequential
+// sub/mul/add chain (tile row stride is odd: conflict-free), applies the exact thresholds and
+// appends the (distance bits, flat index) key.  grid = (blocks, nq).
 // ------------------------------------------------------------------------------------------
-constexpr int RERANK_THREADS = 128;
+constexpr int RR_WARPS = 4;
+constexpr int RR_THREADS = RR_WARPS * 32;
+constexpr int RR_JC = 256;          // reduction steps staged per pass
+constexpr int RR_WP = RR_JC + 1;    // tile row stride (floats)
 
-__global__ void __launch_bounds__(RERANK_THREADS) rerank_kernel(const float *__restrict__ ds, long long row_stride,
-                                                                 unsigned int Tp, int W,
-                                                                 const float *__restrict__ queries, QState *st_all,
-                                                                 const unsigned int *__restrict__ cand_all,
-                                                                 unsigned long long *keys_all, unsigned int cap) {
-    extern __shared__ __align__(16) float qsh[];
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const float *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(RR_THREADS) rerank_kernel(const float *__restrict__ ds, long long row_stride,
+                                                             unsigned int Tp, int W,
+                                                             const float *__restrict__ queries, QState *st_all,
+                                                             const unsigned int *__restrict__ cand_all,
+                                                             unsigned long long *keys_all, unsigned int cap) {
+    extern __shared__ __align__(16) float rr_smem[];
+    const int wq = (W + 3) & ~3;
+    float *qsh = rr_smem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *tile = rr_smem + wq + (size_t)warp * 32 * RR_WP;
+
     const int b = blockIdx.y;
     QState *st = st_all + b;
     const unsigned int craw = st->ccount;
     const unsigned int C = min(craw, cap);
     if (craw > cap && threadIdx.x == 0 && blockIdx.x == 0) st->overflow = 1;
-    if (blockIdx.x * RERANK_THREADS >= C) return;
-    for (int j = threadIdx.x; j < W; j += RERANK_THREADS) qsh[j] = queries[(size_t)b * W + j];
+    const unsigned int groups = (C + 31u) / 32u;
+    if (blockIdx.x * RR_WARPS >= groups) return;
+    for (int j = threadIdx.x; j < W; j += RR_THREADS) qsh[j] = queries[(size_t)b * W + j];
     __syncthreads();
     const float s_thr = st->s_thr, qn = st->qnorm;
     const unsigned long long tau = st->tau_key;
     const unsigned int *cand = cand_all + (size_t)b * cap;
     unsigned long long *dst = keys_all + ((size_t)b * 2 + st->cur) * cap;
-    const int lane = threadIdx.x & 31;
-    const unsigned int Cr = (C + 31u) & ~31u;
-    for (unsigned int i = blockIdx.x * RERANK_THREADS + threadIdx.x; i < Cr; i += gridDim.x * RERANK_THREADS) {
+
+    for (unsigned int g = blockIdx.x * RR_WARPS + warp; g < groups; g += gridDim.x * RR_WARPS) {
+        const unsigned int i = g * 32u + lane;
+        const bool valid = i < C;
+        const unsigned int flat = valid ? cand[i] : 0u;
+        const unsigned int r = flat / Tp, t = flat - r * Tp;
+        const long long off = (long long)r * row_stride + t;
+        const unsigned int vmask = __ballot_sync(FULL, valid);
+        float s = 0.0f;
+        for (int j0 = 0; j0 < W; j0 += RR_JC) {
+            const int jn = min(RR_JC, W - j0);
+            for (int c = 0; c < 32; ++c) {
+                const long long oc = __shfl_sync(FULL, off, c);
+                if (vmask & (1u << c)) {
+                    const float *src = ds + oc + j0;
+                    const uint32_t d0 = smem_u32(tile + c * RR_WP);
+                    for (int j = lane; j < jn; j += 32) cp_async_4(d0 + 4u * j, src + j);
+                }
+            }
+            cp_async_wait_all();
+            __syncwarp();
+            if (valid) {
+                const float *row = tile + lane * RR_WP;
+                const float *qq = qsh + j0;
+#pragma unroll 4
+                for (int j = 0; j < jn; ++j) {
+                    const float df = __fsub_rn(qq[j], row[j]);
+                    s = __fadd_rn(s, __fmul_rn(df, df));
+                }
+            }
+            __syncwarp();
+        }
         bool keep = false;
         unsigned long long key = 0;
-        if (i < C) {
-            const unsigned int flat = cand[i];
-            const unsigned int r = flat / Tp, t = flat - r * Tp;
-            const float *y = ds + (long long)r * row_stride + t;
-            float s = 0.0f;
-#pragma unroll 4
-            for (int j = 0; j < W; ++j) {
-                const float df = __fsub_rn(qsh[j], __ldg(y + j));
-                s = __fadd_rn(s, __fmul_rn(df, df));
-            }
-            if (s <= s_thr) {
-                key = ((unsigned long long)__float_as_uint(dist_from_s(s, qn)) << 32) | flat;
-                keep = key <= tau;
-            }
+        if (valid && s <= s_thr) {
+            key = ((unsigned long long)__float_as_uint(dist_from_s(s, qn)) << 32) | flat;
+            keep = key <= tau;
         }
         const unsigned int bal = __ballot_sync(FULL, keep);
         if (bal) {
@@ -1078,18 +1033,27 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
     p.pfx_floats = 4 + 32 * p.epl + 4;
     p.cw = (float)(W + 256) * 5.9604644775390625e-8f;
     p.buf_floats = (int)align_up((size_t)need + RING + 4, 4);
-    if (p.buf_floats < 32 * p.epl) p.buf_floats = 32 * p.epl;
+    if (p.buf_floats < 32 * p.epl + 4) p.buf_floats = 32 * p.epl + 4;
     p.wpad = (int)align_up((size_t)W + 4, 4);
     const size_t smem_exact = ((size_t)nq * p.wpad + (size_t)SCAN_WARPS * 2 * p.buf_floats) * sizeof(float)
                               + (size_t)SCAN_WARPS * 2 * sizeof(unsigned long long);
     const size_t smem_filter = smem_exact + (size_t)SCAN_WARPS * p.pfx_floats * sizeof(float);
     if (smem_filter > 200 * 1024) return PSH_E_UNSUPPORTED;
-    PSH_CUDA(cudaFuncSetAttribute(scan_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_exact));
-    PSH_CUDA(cudaFuncSetAttribute(scan_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_filter));
-    auto ctas_per_sm = [](size_t smem) {
-        int c = (int)((220 * 1024) / (smem + 1024));
-        return c > 2 ? 2 : (c < 1 ? 1 : c);
+    PSH_CUDA(cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_exact));
+    PSH_CUDA(cudaFuncSetAttribute(scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_filter));
+    const size_t smem_rr = ((size_t)((W + 3) & ~3) + (size_t)RR_WARPS * 32 * RR_WP) * sizeof(float);
+    PSH_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rr));
+    auto ctas_per_sm = [](size_t smem, int lim) {
+        int c = (int)((224 * 1024) / (smem + 1024));
+        return c > lim ? lim : (c < 1 ? 1 : c);
     };
+    {
+        unsigned int sft = 0;
+        while ((1u << sft) < (unsigned int)p.nseg) ++sft;
+        p.nseg_s = sft;
+        p.nseg_m = (unsigned int)((((1ull << 32) * ((1ull << sft) - (unsigned long long)p.nseg)) / (unsigned long long)p.nseg) + 1ull);
+    }
+    p.inv_R = 1.0 / (double)R;
 
     // chunk schedule over permuted row slots: seed chunk (always exact), then geometric growth;
     // in safe mode every chunk fits the candidate buffer even if all of its windows are appended
@@ -1103,29 +1067,30 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
         if (next > R) next = R;
         p.i0 = done; p.i1 = next;
         const bool use_filter = filter && done > 0;
-        long long ntasks = (next - done) * p.nseg;
+        long long ntasks = (next - done) * p.nseg;  // < 2^32: nseg <= Tp and R*Tp < 2^32
+        p.ntasks = (unsigned int)ntasks;
         long long ctas = (ntasks + SCAN_WARPS - 1) / SCAN_WARPS;
-        long long max_ctas = (long long)sm_count() * ctas_per_sm(use_filter ? smem_filter : smem_exact);
+        long long max_ctas = (long long)sm_count() * (use_filter ? ctas_per_sm(smem_filter, 3) : ctas_per_sm(smem_exact, 2));
         if (ctas > max_ctas) ctas = max_ctas;
         if (use_filter) {
             {
                 ProfScope ps(stream, 0);
-                scan_filter_kernel<<<(unsigned int)ctas, SCAN_THREADS, smem_filter, stream>>>(p);
+                scan_kernel<false><<<(unsigned int)ctas, SCAN_THREADS, smem_filter, stream>>>(p);
             }
             PSH_LAUNCHED();
-            unsigned int rb = (pl.cap + RERANK_THREADS - 1) / RERANK_THREADS;
-            unsigned int rb_max = (unsigned int)sm_count() * 8u;
+            unsigned int rb = (pl.cap + RR_THREADS - 1) / RR_THREADS;
+            unsigned int rb_max = (unsigned int)sm_count() * 2u;
             if (rb > rb_max) rb = rb_max;
             {
                 ProfScope ps(stream, 1);
-                rerank_kernel<<<dim3(rb, nq), RERANK_THREADS, (size_t)W * sizeof(float), stream>>>(
+                rerank_kernel<<<dim3(rb, nq), RR_THREADS, smem_rr, stream>>>(
                     d_dataset, row_stride, (unsigned int)pl.Tp, W, d_q, st, cand, keys, pl.cap);
             }
             PSH_LAUNCHED();
         } else {
             {
                 ProfScope ps(stream, 0);
-                scan_exact_kernel<<<(unsigned int)ctas, SCAN_THREADS, smem_exact, stream>>>(p);
+                scan_kernel<true><<<(unsigned int)ctas, SCAN_THREADS, smem_exact, stream>>>(p);
             }
             PSH_LAUNCHED();
         }

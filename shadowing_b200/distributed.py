@@ -50,8 +50,10 @@ def sharded_scan(ps, rows: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int
         i_loc[:, :k_loc] = i
     d_all = torch.empty((world, B, k), dtype=torch.float32, device=rows.device)
     i_all = torch.empty((world, B, k, 2), dtype=torch.int32, device=rows.device)
-    dist.all_gather_into_tensor(d_all, d_loc, group=pg)
-    dist.all_gather_into_tensor(i_all, i_loc, group=pg)
+    # all_gather on views of one buffer: NCCL coalesces it into a single ncclAllGather; gloo
+    # (CPU tests) has no all_gather_into_tensor
+    dist.all_gather(list(d_all.unbind(0)), d_loc, group=pg)
+    dist.all_gather(list(i_all.unbind(0)), i_loc, group=pg)
     return _lib.merge_topk(d_all, i_all, Tp)
 
 
