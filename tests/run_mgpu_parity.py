@@ -1,0 +1,53 @@
+"""Multi-GPU parity (run under torchrun on a GPU box, not collected by pytest):
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/run_mgpu_parity.py
+The ensemble is sharded over N ranks (NCCL); every rank must return exactly the CPU oracle's
+single-process answer (distances, indices, paths) -- SURVEY.md section 8(e)."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def main():
+    from conftest import make_inputs
+    import shadowing_b200 as sb
+    from shadowing_b200.distributed import shard_bounds
+    from oracle import oracle
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ok = True
+    for (R, T, W, H, k, B) in [(1024, 4096, 252, 20, 1024, 2), (37, 700, 20, 5, 300, 3), (3, 600, 16, 4, 900, 1)]:
+        ds, q = make_inputs(R, T, W, B, seed=500 + R)
+        lo, hi = shard_bounds(R, world, rank)
+        obj = sb.PathShadowing(sb.Identity(W), sb.RelativeMSE(), ds[lo:hi], sb.PredictionContext(H), device=dev,
+                               row_offset=lo, process_group=dist.group.WORLD)
+        d, paths, idx = obj.shadow(q, k=k)
+        pred, pstd = obj.predict(q, k=k, to_predict=sb.RealizedVariance([2, 4]), eta=0.1)
+        do, po, io = oracle.shadow(ds, q, k, H)
+        mo, so = oracle.predict_from_paths(do, po, H, [2, 4], False, "softmax", 0.1)
+        good = (np.array_equal(d.view(np.uint32), do.view(np.uint32)) and np.array_equal(idx, io)
+                and np.array_equal(paths, po) and np.allclose(pred, mo, rtol=1e-6) and np.allclose(pstd, so, rtol=1e-5))
+        print(f"rank {rank}/{world} R={R} T={T} W={W} k={k} B={B}: {'OK' if good else 'MISMATCH'}", flush=True)
+        ok = ok and good
+    flag = torch.tensor([0 if ok else 1], device=dev)
+    dist.all_reduce(flag)
+    dist.destroy_process_group()
+    if int(flag.item()) != 0:
+        sys.exit(1)
+    if rank == 0:
+        print("MGPU PARITY OK")
+
+
+if __name__ == "__main__":
+    main()
