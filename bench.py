@@ -267,6 +267,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e = float(t[0]), float(t[1])
 
+    eff_mode = "fft" if args.mode == "auto" else args.mode
     if rank == 0:
         windows_per_step = world * R_PER_GPU * TP
         value = windows_per_step * args.steps / (ms_dev * 1e-3)
@@ -282,7 +283,11 @@ def run_ours(args):
                 traffic = json.loads(tp.read_text()).get("scan_dram_bytes_per_step")
             except Exception:
                 traffic = None
-        flop_per_win = ALG_FLOP_PER_WINDOW if args.mode == "exact" else W
+        eff_mode = "fft" if args.mode == "auto" else args.mode
+        # fp32 lane-ops per window actually issued by the scan flavour (exact: sub+mul+add per
+        # element; filter: one FMA per element; fft: ~1.6 k FP instructions per thread per pair of
+        # trajectories / 7650 windows, counted from SASS)
+        flop_per_win = {"exact": ALG_FLOP_PER_WINDOW, "filter": W, "fft": 27}[eff_mode]
         sm_clk = (clocks.get("sm_mhz") or sm_max) * 1e6
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
         fp32_rate = R_PER_GPU * TP * flop_per_win / (scan_ms_per_step * 1e-3)
@@ -292,7 +297,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "BASELINE configs[1]: R=32768xT=4096 Gaussian dlnx per GPU, W=252, H=20, "
                                    "k=1024, Identity+RelativeMSE, one query date per step",
-                       "rows_per_gpu": R_PER_GPU, "scan_mode": args.mode,
+                       "rows_per_gpu": R_PER_GPU, "scan_mode": eff_mode,
                        "l2": "512 MiB shard per GPU > 126 MB L2 (inputs larger than L2)",
                        "dataset": "resident in HBM (uploaded once at construction)",
                        "parallelism": f"rows sharded x{world}, all-gather + merge of per-GPU top-k"},
@@ -325,7 +330,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="filter", choices=["filter", "exact"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "fft", "filter", "exact"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -34,8 +34,11 @@ enum {
 /* scan modes */
 enum {
     PSH_MODE_EXACT = 0, /* every window evaluated with the reference's exact fp32 sequence    */
-    PSH_MODE_FILTER = 1 /* 1-FMA/element lower-bound filter, exact re-rank of the survivors;  */
-                        /* results identical to PSH_MODE_EXACT by construction                */
+    PSH_MODE_FILTER = 1, /* 1-FMA/element lower-bound filter, exact re-rank of the survivors; */
+                         /* results identical to PSH_MODE_EXACT by construction               */
+    PSH_MODE_FFT = 2     /* lower-bound filter through one inverse FFT per trajectory pair    */
+                         /* (needs psh_fft_prepare aux, T <= 4096; else behaves as FILTER);   */
+                         /* same exact re-rank, results identical to PSH_MODE_EXACT           */
 };
 
 int psh_version(void);
@@ -58,6 +61,7 @@ size_t psh_scan_workspace_bytes(int64_t R, int64_t T, int B, int W, int H, int64
  *   d_out_dist  (B, k) fp32, ascending
  *   d_out_idx   (B, k, 2) int32 [trajectory, offset]; ties ordered by (distance, r*T'+t)
  *   d_ws        scratch of >= psh_scan_workspace_bytes(...) bytes, 256-byte aligned
+ *   d_aux       PSH_MODE_FFT: buffer filled by psh_fft_prepare for this dataset/W/H, else NULL
  *
  * Distances carry the reference's CPU bit pattern: s = sum_j fl(fl(q_j - y_{t+j})^2)
  * accumulated sequentially in fp32 without FMA, sqrt, IEEE divide by ||q|| (8-lane order).
@@ -67,7 +71,21 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
                       const float *d_queries, int B, int W, int H, int64_t k,
                       int32_t row_offset, int mode,
                       float *d_out_dist, int32_t *d_out_idx,
-                      void *d_ws, size_t ws_bytes, void *stream);
+                      void *d_ws, size_t ws_bytes, const void *d_aux, size_t aux_bytes, void *stream);
+
+/*
+ * Dataset-side precomputation for PSH_MODE_FFT (no reference counterpart; the reference
+ * recomputes everything per call).  Fills d_aux (>= psh_fft_aux_bytes, 256-byte aligned) with
+ * the 4096-point spectra of all trajectory pairs, the window energies sum_{j<W} y_{t+j}^2 and
+ * the pair norms.  Valid for this (dataset, W, H) only; T <= 4096 (else PSH_E_UNSUPPORTED / 0).
+ */
+size_t psh_fft_aux_bytes(int64_t R, int64_t T, int W, int H);
+int psh_fft_prepare(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride, int W, int H,
+                    void *d_aux, size_t aux_bytes, void *stream);
+
+/* Test hook: n independent 4096-point complex transforms (dir -1 forward, +1 inverse,
+ * unnormalised) with the library's FFT; d_aux is a prepared aux buffer (twiddles). */
+int psh_debug_fft4096(const void *d_in, void *d_out, int n, int dir, const void *d_aux, void *stream);
 
 /*
  * k-way merge of G per-shard results into the global top-k: replaces the cat + topk +

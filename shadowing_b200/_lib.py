@@ -12,6 +12,8 @@ LIB_PATH = _PKG / "libpshadow.so"
 
 PSH_MODE_EXACT = 0
 PSH_MODE_FILTER = 1
+PSH_MODE_FFT = 2
+FFT_MAX_T = 4096
 
 _lib = None
 
@@ -42,7 +44,13 @@ def lib() -> ctypes.CDLL:
         L.psh_scan_workspace_bytes.restype = sz
         L.psh_scan_workspace_bytes.argtypes = [i64, i64, ci, ci, ci, i64]
         L.psh_scan_topk_f32.restype = ci
-        L.psh_scan_topk_f32.argtypes = [vp, i64, i64, i64, vp, ci, ci, ci, i64, i32, ci, vp, vp, vp, sz, vp]
+        L.psh_scan_topk_f32.argtypes = [vp, i64, i64, i64, vp, ci, ci, ci, i64, i32, ci, vp, vp, vp, sz, vp, sz, vp]
+        L.psh_fft_aux_bytes.restype = sz
+        L.psh_fft_aux_bytes.argtypes = [i64, i64, ci, ci]
+        L.psh_fft_prepare.restype = ci
+        L.psh_fft_prepare.argtypes = [vp, i64, i64, i64, ci, ci, vp, sz, vp]
+        L.psh_debug_fft4096.restype = ci
+        L.psh_debug_fft4096.argtypes = [vp, vp, ci, ci, vp, vp]
         L.psh_merge_topk.restype = ci
         L.psh_merge_topk.argtypes = [vp, vp, ci, ci, i64, i64, vp, vp, vp]
         L.psh_gather_paths.restype = ci
@@ -71,8 +79,33 @@ def launch_count() -> int:
     return int(lib().psh_launch_count())
 
 
+def fft_prepare(ds: torch.Tensor, T: int, W: int, H: int) -> torch.Tensor:
+    """Dataset-side precomputation for PSH_MODE_FFT: spectra of row pairs, window energies, norms."""
+    L = lib()
+    need = L.psh_fft_aux_bytes(ds.shape[0], T, W, H)
+    if need == 0:
+        raise PshadowError(-5, "psh_fft_aux_bytes")
+    aux = torch.empty(need, dtype=torch.uint8, device=ds.device)
+    with torch.cuda.device(ds.device):
+        rc = L.psh_fft_prepare(ds.data_ptr(), ds.shape[0], T, ds.stride(0), W, H, aux.data_ptr(), aux.numel(),
+                               _stream(ds))
+    _check(rc, "psh_fft_prepare")
+    return aux
+
+
+def debug_fft4096(x: torch.Tensor, direction: int, aux: torch.Tensor) -> torch.Tensor:
+    """x (n, 4096) complex64 cuda -> unnormalised DFT (direction -1) / inverse (+1), test hook."""
+    L = lib()
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = L.psh_debug_fft4096(x.data_ptr(), out.data_ptr(), x.shape[0], direction, aux.data_ptr(), _stream(x))
+    _check(rc, "psh_debug_fft4096")
+    return out
+
+
 def scan_topk(ds: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int, row_offset: int = 0,
-              mode: int = PSH_MODE_FILTER, workspace: torch.Tensor | None = None):
+              mode: int = PSH_MODE_FILTER, workspace: torch.Tensor | None = None, aux: torch.Tensor | None = None):
     """ds (R, row_stride) f32 cuda, q (B, W) f32 cuda -> (dist (B,k) f32, idx (B,k,2) i32) cuda."""
     L = lib()
     assert ds.is_cuda and q.is_cuda and ds.dtype == torch.float32 and q.dtype == torch.float32
@@ -90,6 +123,7 @@ def scan_topk(ds: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int, row_off
     with torch.cuda.device(ds.device):
         rc = L.psh_scan_topk_f32(ds.data_ptr(), R, T, row_stride, q.data_ptr(), B, W, H, k, row_offset, mode,
                                  dist.data_ptr(), idx.data_ptr(), workspace.data_ptr(), workspace.numel(),
+                                 aux.data_ptr() if aux is not None else None, aux.numel() if aux is not None else 0,
                                  _stream(ds))
     _check(rc, "psh_scan_topk_f32")
     return dist, idx, workspace

@@ -13,6 +13,7 @@
 // CPU bit pattern (sequential, non-fused fp32), so indices and distances are bit-identical.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <math.h>
 #include <string.h>
 
 #include <atomic>
@@ -47,7 +48,8 @@ struct QState {
     unsigned int ccount;         // filter candidates awaiting the exact re-rank
     float thr_fast;              // s_thr widened by the exact sequence's own rounding (filter compare)
     float q2;                    // sum q_j^2 (fp64 accumulated, rounded once)
-    unsigned int pad[6];
+    float qmax;                  // max_k |FFT(q)_k| (fft flavour), rounded up
+    unsigned int pad[5];
 };
 static_assert(sizeof(QState) == 64, "QState layout");
 
@@ -73,6 +75,9 @@ struct ScanParams {
     int epl;               // filter: samples per lane of the squared-prefix pass (odd multiple of 4)
     int pfx_floats;        // filter: floats of the per-warp prefix buffer
     float cw;              // filter: slack coefficient (W + 256) * 2^-24
+    int pair_mode;         // fft flavour: slots enumerate rows of permuted row PAIRS (2*pair + slot&1)
+    long long npairs;
+    double inv_np;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -116,6 +121,8 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
 // the reference's distance from its squared numerator: sqrt then IEEE divide (path_distance.py:65)
 __device__ __forceinline__ float dist_from_s(float s, float qn) { return __fdiv_rn(__fsqrt_rn(s), qn); }
 
+#include "pshadow_fft.cuh"
+
 // ------------------------------------------------------------------------------------------
 // query preparation: ||q|| in torch's contiguous-reduction order (8 interleaved partial sums,
 // lanes added 0..7, scalar tail), state reset.  path_distance.py:65 `x.norm(dim=-1)`.
@@ -148,7 +155,8 @@ __global__ void qprep_kernel(const float *__restrict__ q, int W, int nq, QState 
     z.ccount = 0;
     z.thr_fast = __int_as_float(0x7f800000);
     z.q2 = (float)q2;
-    for (int i = 0; i < 6; ++i) z.pad[i] = 0;
+    z.qmax = 0.0f;
+    for (int i = 0; i < 5; ++i) z.pad[i] = 0;
     st[b] = z;
 }
 
@@ -202,20 +210,24 @@ __device__ __forceinline__ void step_block(float (&acc)[WPT], float (&ring)[RING
 // measured slower on B200: a dual-ring layout (samples duplicated with flipped parity; ptxas
 // re-schedules across steps and loses the property) and packed FFMA2 (fma.rn.f32x2; 1.67 ms vs
 // 1.44 ms per query -- three 64-bit operand reads per instruction without reuse).
-struct Task { long long row; int t0; int nvalid; };
+struct Task { long long row; int t0; int nvalid; int tp_eff; };
 
 __device__ __forceinline__ Task decode_task(const ScanParams &p, unsigned int task) {
     // task -> (row slot, segment): division by the launch-invariant nseg via multiply-high
     const unsigned int sr = (unsigned int)(((unsigned long long)__umulhi(task, p.nseg_m) + task) >> p.nseg_s);
     const unsigned int seg = task - sr * (unsigned int)p.nseg;
     // row = (slot * perm) mod R: quotient estimated in fp64 (exact to +-1), remainder fixed up
-    const unsigned long long prod = (unsigned long long)(p.i0 + sr) * (unsigned long long)p.perm;
-    const unsigned long long q = __double2ull_rz(__ull2double_rz(prod) * p.inv_R);
-    long long r = (long long)(prod - q * (unsigned long long)p.R);
-    if (r < 0) r += p.R;
-    else if (r >= p.R) r -= p.R;
+    const unsigned long long slot = (unsigned long long)(p.i0 + sr);
+    const unsigned long long modn = p.pair_mode ? (unsigned long long)p.npairs : (unsigned long long)p.R;
+    const unsigned long long prod = (p.pair_mode ? (slot >> 1) : slot) * (unsigned long long)p.perm;
+    const unsigned long long q = __double2ull_rz(__ull2double_rz(prod) * (p.pair_mode ? p.inv_np : p.inv_R));
+    long long r = (long long)(prod - q * modn);
+    if (r < 0) r += (long long)modn;
+    else if (r >= (long long)modn) r -= (long long)modn;
+    if (p.pair_mode) r = 2 * r + (long long)(slot & 1ull);
     Task t;
-    t.row = r;
+    t.tp_eff = r < p.R ? p.Tp : 0;  // the phantom partner of the last row of an odd ensemble
+    t.row = r < p.R ? r : p.R - 1;
     t.t0 = (int)seg * SEG;
     t.nvalid = min(SEG + p.W - 1, p.T - t.t0);
     return t;
@@ -298,7 +310,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, EXACT ? 2 : 3) scan_kernel(const
         const int tl = t0 + lane * WPT;  // first window of this lane
         const unsigned int flat0 =
             (unsigned int)((unsigned long long)tk.row * (unsigned long long)p.Tp + (unsigned long long)tl);
-        const bool all_valid = t0 + SEG <= p.Tp;
+        const bool all_valid = t0 + SEG <= tk.tp_eff;
 
         float y2[WPT];
         float ptot = 0.0f;
@@ -389,7 +401,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, EXACT ? 2 : 3) scan_kernel(const
             if (!all_valid) {
 #pragma unroll
                 for (int w = 0; w < WPT; ++w)
-                    if (tl + w >= p.Tp) mask &= ~(1u << w);
+                    if (tl + w >= tk.tp_eff) mask &= ~(1u << w);
             }
             if (__any_sync(FULL, mask != 0)) {
                 unsigned long long key[WPT];
@@ -443,6 +455,233 @@ __global__ void __launch_bounds__(SCAN_THREADS, EXACT ? 2 : 3) scan_kernel(const
         if (!have_next) break;
         tk = tn;
         task = next;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// FFT flavour: preparation kernels, query spectrum, scan
+// ------------------------------------------------------------------------------------------
+struct FftAux {            // device pointers into the caller's aux buffer
+    float2 *tw32;          // exp(+2 pi i m / 4096), m < 4096
+    double2 *tw64;
+    float *ynorm;          // (npairs) sqrt(|y_a|^2 + |y_b|^2), rounded up
+    float2 *Z;             // (npairs, 4096) spectra of y_a + i y_b
+    float *Y2;             // (R, y2_stride) window energies sum_{j<W} y_{t+j}^2
+    long long npairs;
+    int y2_stride;
+    size_t total;
+};
+
+inline bool fft_aux_layout(long long R, long long T, int W, int H, unsigned char *base, FftAux &a) {
+    if (R <= 0 || T <= 0 || T > fftx::N || W <= 0 || H < 0 || T - W - H + 1 <= 0) return false;
+    const long long Tp = T - W - H + 1;
+    a.npairs = (R + 1) / 2;
+    a.y2_stride = (int)((Tp + 3) / 4 * 4);
+    size_t off = 0;
+    a.tw32 = reinterpret_cast<float2 *>(base + off); off += sizeof(float2) * fftx::N;
+    a.tw64 = reinterpret_cast<double2 *>(base + off); off += sizeof(double2) * fftx::N;
+    a.ynorm = reinterpret_cast<float *>(base + off); off += (sizeof(float) * (size_t)a.npairs + 255) / 256 * 256;
+    a.Z = reinterpret_cast<float2 *>(base + off); off += sizeof(float2) * fftx::N * (size_t)a.npairs;
+    a.Y2 = reinterpret_cast<float *>(base + off); off += (sizeof(float) * (size_t)R * (size_t)a.y2_stride + 255) / 256 * 256;
+    a.total = off;
+    return true;
+}
+
+// debug / test entry: batched 4096-point transform of n independent signals
+__global__ void __launch_bounds__(fftx::THREADS) fft_debug_kernel(const float2 *__restrict__ in, float2 *out,
+                                                                  const float2 *__restrict__ tw, int dir) {
+    __shared__ float2 ex[fftx::EX_FLOAT2];
+    const int tid = threadIdx.x;
+    const float2 *x = in + (size_t)blockIdx.x * fftx::N;
+    float2 v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = x[tid + 256 * i];
+    if (dir > 0) fftx::fft4096<1>(v, ex, tw, tid);
+    else fftx::fft4096<-1>(v, ex, tw, tid);
+    float2 *y = out + (size_t)blockIdx.x * fftx::N;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) y[tid + 256 * c] = v[c];
+}
+
+// spectra of row pairs + pair norms: one CTA per pair
+__global__ void __launch_bounds__(fftx::THREADS) fft_prep_spectra_kernel(const float *__restrict__ ds, long long R, int T,
+                                                                         long long row_stride, FftAux a) {
+    __shared__ float2 ex[fftx::EX_FLOAT2];
+    __shared__ double red[fftx::THREADS / 32];
+    const int tid = threadIdx.x;
+    const long long pair = blockIdx.x;
+    const long long ra = 2 * pair, rb = ra + 1;
+    const float *ya = ds + ra * row_stride;
+    const float *yb = ds + (rb < R ? rb : ra) * row_stride;
+    float2 v[16];
+    double e = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int n = tid + 256 * i;
+        const float xa = n < T ? ya[n] : 0.0f;
+        const float xb = (n < T && rb < R) ? yb[n] : 0.0f;
+        v[i] = make_float2(xa, xb);
+        e += (double)xa * (double)xa + (double)xb * (double)xb;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(FULL, e, o);
+    if ((tid & 31) == 0) red[tid >> 5] = e;
+    fftx::fft4096<-1>(v, ex, a.tw32, tid);  // (its barriers also order the writes to red)
+    float2 *z = a.Z + (size_t)pair * fftx::N;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) z[tid + 256 * c] = v[c];
+    if (tid == 0) {
+        double s = 0.0;
+        for (int i = 0; i < fftx::THREADS / 32; ++i) s += red[i];
+        a.ynorm[pair] = __double2float_ru(sqrt(s) * (1.0 + 1e-7));
+    }
+}
+
+// window energies Y2[r][t] = sum_{j<W} y_{t+j}^2 from an fp64 prefix sum, rounded once: one CTA per row
+__global__ void __launch_bounds__(fftx::THREADS) fft_prep_y2_kernel(const float *__restrict__ ds, int T,
+                                                                    long long row_stride, int W, int Tp, FftAux a) {
+    __shared__ double pfx[fftx::N + 1];
+    __shared__ double wsum[fftx::THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *y = ds + (long long)blockIdx.x * row_stride;
+    double loc[16];
+    double run = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int n = 16 * tid + i;
+        const double x = n < T ? (double)y[n] : 0.0;
+        run += x * x;
+        loc[i] = run;
+    }
+    double incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double u = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    double off = incl - run;
+    for (int w = 0; w < warp; ++w) off += wsum[w];
+    if (tid == 0) pfx[0] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pfx[16 * tid + i + 1] = off + loc[i];
+    __syncthreads();
+    float *o = a.Y2 + (size_t)blockIdx.x * a.y2_stride;
+    for (int t = tid; t < a.y2_stride; t += fftx::THREADS) o[t] = t < Tp ? (float)(pfx[t + W] - pfx[t]) : 0.0f;
+}
+
+// conj(FFT_4096(q padded))/4096 per query (direct fp64 DFT on the exact twiddle table) + max |Q_k|
+__global__ void __launch_bounds__(fftx::THREADS) qfft_kernel(const float *__restrict__ q, int W,
+                                                             const double2 *__restrict__ tw64, float2 *Qc, QState *st) {
+    extern __shared__ double qd[];
+    __shared__ double red[fftx::THREADS / 32];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    for (int j = tid; j < W; j += fftx::THREADS) qd[j] = (double)q[(size_t)b * W + j];
+    __syncthreads();
+    double mx = 0.0;
+    for (int k = tid; k < fftx::N; k += fftx::THREADS) {
+        double re = 0.0, im = 0.0;
+        for (int j = 0; j < W; ++j) {
+            const double2 w = tw64[(j * k) & (fftx::N - 1)];  // exp(+i theta): Q_k = sum q_j exp(-i theta)
+            re += qd[j] * w.x;
+            im -= qd[j] * w.y;
+        }
+        mx = fmax(mx, re * re + im * im);
+        Qc[(size_t)b * fftx::N + k] = make_float2((float)(re / fftx::N), (float)(-im / fftx::N));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 1; i < fftx::THREADS / 32; ++i) mx = fmax(mx, red[i]);
+        st[b].qmax = __double2float_ru(sqrt(mx) * (1.0 + 1e-7));
+    }
+}
+
+struct FftScanParams {
+    const float2 *Z;
+    const float *Y2;
+    const float *ynorm;
+    const float2 *tw;
+    const float2 *Qc;  // (nq, 4096)
+    int Tp, y2_stride, nq;
+    long long npairs, R;
+    long long i0, i1;  // pair slots of this launch
+    long long perm;
+    double inv_np;
+    QState *st;
+    unsigned int *cand;
+    unsigned int cap;
+    float cf_u;        // CF * 2^-24: |c^_t - c_t| <= cf_u * Qmax * ynorm  (CF = 512, theory ~165)
+};
+
+// One CTA per row pair: Z * conj(Q)/N -> inverse FFT -> (D_a[t], D_b[t]) for t = tid + 256 c.
+// Lower bound LB = Q2 + Y2 - 2 D^ - slack,
+//   slack = 2 cf_u Qmax ynorm + 8u (Q2 + ynorm^2)   (FFT error; Y2, Q2 roundings and the combination)
+__global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftScanParams p) {
+    __shared__ float2 ex[fftx::EX_FLOAT2];
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (long long slot = p.i0 + blockIdx.x; slot < p.i1; slot += gridDim.x) {
+        const unsigned long long prod = (unsigned long long)slot * (unsigned long long)p.perm;
+        const unsigned long long qq = __double2ull_rz(__ull2double_rz(prod) * p.inv_np);
+        long long pair = (long long)(prod - qq * (unsigned long long)p.npairs);
+        if (pair < 0) pair += p.npairs;
+        else if (pair >= p.npairs) pair -= p.npairs;
+        const float2 *Zp = p.Z + (size_t)pair * fftx::N;
+        const long long ra = 2 * pair, rb = ra + 1;
+        const bool has_b = rb < p.R;
+        const float yn = p.ynorm[pair];
+        const float *y2a = p.Y2 + (size_t)ra * p.y2_stride;
+        const float *y2b = p.Y2 + (size_t)(has_b ? rb : ra) * p.y2_stride;
+        for (int b = 0; b < p.nq; ++b) {
+            const float2 *Qb = p.Qc + (size_t)b * fftx::N;
+            float2 v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fftx::cmul(__ldg(Zp + tid + 256 * i), __ldg(Qb + tid + 256 * i));
+            fftx::fft4096<1>(v, ex, p.tw, tid);
+            const float q2 = p.st[b].q2, qmax = p.st[b].qmax;
+            const float thr = ld_volatile_f32(&p.st[b].thr_fast);
+            const float slack = (2.0f * p.cf_u * qmax * yn + 4.76837158203125e-7f * (q2 + yn * yn)) * 1.0001f;
+            const float base = (q2 - slack) - thr;
+            unsigned int mask = 0;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const int t = tid + 256 * c;
+                if (t < p.Tp) {
+                    const float va = fmaf(-2.0f, v[c].x, __ldg(y2a + t)) + base;
+                    if (!(va > 0.0f)) mask |= 1u << c;
+                    if (has_b) {
+                        const float vb = fmaf(-2.0f, v[c].y, __ldg(y2b + t)) + base;
+                        if (!(vb > 0.0f)) mask |= 1u << (16 + c);
+                    }
+                }
+            }
+            if (__any_sync(FULL, mask != 0)) {
+                const int cnt = __popc(mask);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += u;
+                }
+                const int total = __shfl_sync(FULL, incl, 31);
+                unsigned int basepos = 0;
+                if (lane == 31) basepos = atomicAdd(&p.st[b].ccount, (unsigned int)total);
+                basepos = __shfl_sync(FULL, basepos, 31);
+                unsigned int pos = basepos + (unsigned int)(incl - cnt);
+                unsigned int *dst = p.cand + (size_t)b * p.cap;
+                const unsigned int fa = (unsigned int)((unsigned long long)ra * (unsigned long long)p.Tp);
+                const unsigned int fb = (unsigned int)((unsigned long long)rb * (unsigned long long)p.Tp);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    if (mask & (1u << c)) { if (pos < p.cap) dst[pos] = fa + (unsigned int)(tid + 256 * c); ++pos; }
+                    if (mask & (1u << (16 + c))) { if (pos < p.cap) dst[pos] = fb + (unsigned int)(tid + 256 * c); ++pos; }
+                }
+            }
+            __syncthreads();  // ex is reused by the next transform
+        }
     }
 }
 
@@ -898,7 +1137,7 @@ struct Plan {
     unsigned int cap;
     long long n0;      // rows of the seeding chunk
     int growth;
-    size_t off_state, off_keys, off_cand, total;
+    size_t off_state, off_keys, off_cand, off_qspec, total;
 };
 
 constexpr int SEED_FACTOR = 16;  // seeding chunk holds ~16 k windows
@@ -926,7 +1165,8 @@ bool make_plan(long long R, long long T, int B, int W, int H, long long k, Plan 
     pl.off_state = 0;
     pl.off_keys = align_up((size_t)B * sizeof(QState), 256);
     pl.off_cand = pl.off_keys + (size_t)B * 2 * (size_t)pl.cap * sizeof(unsigned long long);
-    pl.total = pl.off_cand + align_up((size_t)B * (size_t)pl.cap * sizeof(unsigned int), 256);
+    pl.off_qspec = pl.off_cand + align_up((size_t)B * (size_t)pl.cap * sizeof(unsigned int), 256);
+    pl.total = pl.off_qspec + (size_t)B * fftx::N * sizeof(float2);  // query spectra (fft flavour)
     return true;
 }
 
@@ -1011,15 +1251,65 @@ size_t psh_scan_workspace_bytes(int64_t R, int64_t T, int B, int W, int H, int64
     return pl.total;
 }
 
+size_t psh_fft_aux_bytes(int64_t R, int64_t T, int W, int H) {
+    FftAux a;
+    if (!fft_aux_layout(R, T, W, H, nullptr, a)) return 0;
+    return a.total;
+}
+
+int psh_fft_prepare(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride, int W, int H,
+                    void *d_aux, size_t aux_bytes, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!d_dataset || !d_aux || row_stride < T) return PSH_E_ARG;
+    FftAux a;
+    if (!fft_aux_layout(R, T, W, H, static_cast<unsigned char *>(d_aux), a)) return T > fftx::N ? PSH_E_UNSUPPORTED : PSH_E_ARG;
+    if (aux_bytes < a.total || (reinterpret_cast<uintptr_t>(d_aux) & 255u)) return PSH_E_WORKSPACE;
+    // twiddle tables: exp(+2 pi i m / 4096) in fp64, rounded once for the fp32 copy
+    static std::vector<double2> h64;
+    static std::vector<float2> h32;
+    if (h64.empty()) {
+        h64.resize(fftx::N); h32.resize(fftx::N);
+        for (int m = 0; m < fftx::N; ++m) {
+            // exact symmetries from the first octant keep the table accurate to the last bit
+            const double ang = 6.283185307179586476925286766559 * (double)m / (double)fftx::N;
+            h64[m].x = cos(ang); h64[m].y = sin(ang);
+            h32[m].x = (float)h64[m].x; h32[m].y = (float)h64[m].y;
+        }
+    }
+    PSH_CUDA(cudaMemcpyAsync(a.tw64, h64.data(), sizeof(double2) * fftx::N, cudaMemcpyHostToDevice, stream));
+    PSH_CUDA(cudaMemcpyAsync(a.tw32, h32.data(), sizeof(float2) * fftx::N, cudaMemcpyHostToDevice, stream));
+    fft_prep_spectra_kernel<<<(unsigned int)a.npairs, fftx::THREADS, 0, stream>>>(d_dataset, R, (int)T, row_stride, a);
+    PSH_LAUNCHED();
+    fft_prep_y2_kernel<<<(unsigned int)R, fftx::THREADS, 0, stream>>>(d_dataset, (int)T, row_stride, W,
+                                                                     (int)(T - W - H + 1), a);
+    PSH_LAUNCHED();
+    return PSH_OK;
+}
+
+int psh_debug_fft4096(const void *d_in, void *d_out, int n, int dir, const void *d_aux, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!d_in || !d_out || !d_aux || n <= 0) return PSH_E_ARG;
+    fft_debug_kernel<<<n, fftx::THREADS, 0, stream>>>(static_cast<const float2 *>(d_in), static_cast<float2 *>(d_out),
+                                                      static_cast<const float2 *>(d_aux), dir);
+    PSH_LAUNCHED();
+    return PSH_OK;
+}
+
 static int run_scan_group(const float *d_dataset, long long R, long long T, long long row_stride,
                           const float *d_q, int nq, int W, int H, long long k, int row_offset,
-                          const Plan &pl, QState *st, unsigned long long *keys, unsigned int *cand, int mode,
-                          bool safe, float *d_out_dist, int *d_out_idx, cudaStream_t stream) {
+                          const Plan &pl, QState *st, unsigned long long *keys, unsigned int *cand, float2 *qspec,
+                          const FftAux *aux, int mode, bool safe, float *d_out_dist, int *d_out_idx,
+                          cudaStream_t stream) {
     (void)H;
     qprep_kernel<<<(nq + 127) / 128, 128, 0, stream>>>(d_q, W, nq, st);
     PSH_LAUNCHED();
 
-    const bool filter = (mode == PSH_MODE_FILTER) && !safe;
+    const bool use_fft = (mode == PSH_MODE_FFT) && !safe && aux != nullptr;
+    const bool filter = (mode == PSH_MODE_FILTER || (mode == PSH_MODE_FFT && !use_fft)) && !safe;
+    if (use_fft) {
+        qfft_kernel<<<nq, fftx::THREADS, (size_t)W * sizeof(double), stream>>>(d_q, W, aux->tw64, qspec, st);
+        PSH_LAUNCHED();
+    }
     ScanParams p;
     p.ds = d_dataset; p.row_stride = row_stride; p.T = (int)T; p.Tp = (int)pl.Tp; p.W = W;
     p.nseg = (int)((pl.Tp + SEG - 1) / SEG);
@@ -1054,30 +1344,62 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
         p.nseg_m = (unsigned int)((((1ull << 32) * ((1ull << sft) - (unsigned long long)p.nseg)) / (unsigned long long)p.nseg) + 1ull);
     }
     p.inv_R = 1.0 / (double)R;
+    p.pair_mode = use_fft ? 1 : 0;
+    p.npairs = (R + 1) / 2;
+    p.inv_np = 1.0 / (double)p.npairs;
+    if (use_fft) p.perm = perm_stride(p.npairs);
+    FftScanParams fp;
+    if (use_fft) {
+        fp.Z = aux->Z; fp.Y2 = aux->Y2; fp.ynorm = aux->ynorm; fp.tw = aux->tw32; fp.Qc = qspec;
+        fp.Tp = (int)pl.Tp; fp.y2_stride = aux->y2_stride; fp.nq = nq;
+        fp.npairs = p.npairs; fp.R = R; fp.perm = p.perm; fp.inv_np = p.inv_np;
+        fp.st = st; fp.cand = cand; fp.cap = pl.cap;
+        fp.cf_u = 512.0f * 5.9604644775390625e-8f;
+    }
 
-    // chunk schedule over permuted row slots: seed chunk (always exact), then geometric growth;
-    // in safe mode every chunk fits the candidate buffer even if all of its windows are appended
+    // chunk schedule over permuted slots (rows, or row pairs in the fft flavour): seed chunk
+    // (always exact), then geometric growth; in safe mode every chunk fits the candidate buffer
+    // even if all of its windows are appended
+    const long long unit = use_fft ? 2 : 1;                 // rows per slot
+    const long long nslots = use_fft ? p.npairs : R;
     long long done = 0;
-    long long safe_rows = ((long long)pl.cap - k) / pl.Tp;
-    if (safe_rows < 1) safe_rows = 1;
-    while (done < R) {
+    long long safe_slots = ((long long)pl.cap - k) / (pl.Tp * unit);
+    if (safe_slots < 1) safe_slots = 1;
+    const long long seed_slots = (pl.n0 + unit - 1) / unit;
+    while (done < nslots) {
         long long next;
-        if (safe) next = done + safe_rows;
-        else next = done == 0 ? pl.n0 : done * pl.growth;
-        if (next > R) next = R;
-        p.i0 = done; p.i1 = next;
-        const bool use_filter = filter && done > 0;
-        long long ntasks = (next - done) * p.nseg;  // < 2^32: nseg <= Tp and R*Tp < 2^32
-        p.ntasks = (unsigned int)ntasks;
-        long long ctas = (ntasks + SCAN_WARPS - 1) / SCAN_WARPS;
-        long long max_ctas = (long long)sm_count() * (use_filter ? ctas_per_sm(smem_filter, 3) : ctas_per_sm(smem_exact, 2));
-        if (ctas > max_ctas) ctas = max_ctas;
-        if (use_filter) {
+        if (safe) next = done + safe_slots;
+        else next = done == 0 ? seed_slots : done * pl.growth;
+        if (next > nslots) next = nslots;
+        const bool first = done == 0;
+        if (use_fft && !first) {
+            fp.i0 = done; fp.i1 = next;
+            long long ctas = next - done;
+            const long long max_ctas = (long long)sm_count() * 2;
+            if (ctas > max_ctas) ctas = max_ctas;
             {
                 ProfScope ps(stream, 0);
-                scan_kernel<false><<<(unsigned int)ctas, SCAN_THREADS, smem_filter, stream>>>(p);
+                fft_scan_kernel<<<(unsigned int)ctas, fftx::THREADS, 0, stream>>>(fp);
             }
             PSH_LAUNCHED();
+        } else {
+            p.i0 = done * unit; p.i1 = next * unit;
+            const bool use_filter = filter && !first;
+            long long ntasks = (p.i1 - p.i0) * p.nseg;  // < 2^32: nseg <= Tp and R*Tp < 2^32
+            p.ntasks = (unsigned int)ntasks;
+            long long ctas = (ntasks + SCAN_WARPS - 1) / SCAN_WARPS;
+            long long max_ctas = (long long)sm_count() * (use_filter ? ctas_per_sm(smem_filter, 3) : ctas_per_sm(smem_exact, 2));
+            if (ctas > max_ctas) ctas = max_ctas;
+            if (use_filter) {
+                ProfScope ps(stream, 0);
+                scan_kernel<false><<<(unsigned int)ctas, SCAN_THREADS, smem_filter, stream>>>(p);
+            } else {
+                ProfScope ps(stream, 0);
+                scan_kernel<true><<<(unsigned int)ctas, SCAN_THREADS, smem_exact, stream>>>(p);
+            }
+            PSH_LAUNCHED();
+        }
+        if (!first && (use_fft || filter)) {
             unsigned int rb = (pl.cap + RR_THREADS - 1) / RR_THREADS;
             unsigned int rb_max = (unsigned int)sm_count() * 2u;
             if (rb > rb_max) rb = rb_max;
@@ -1085,12 +1407,6 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
                 ProfScope ps(stream, 1);
                 rerank_kernel<<<dim3(rb, nq), RR_THREADS, smem_rr, stream>>>(
                     d_dataset, row_stride, (unsigned int)pl.Tp, W, d_q, st, cand, keys, pl.cap);
-            }
-            PSH_LAUNCHED();
-        } else {
-            {
-                ProfScope ps(stream, 0);
-                scan_kernel<true><<<(unsigned int)ctas, SCAN_THREADS, smem_exact, stream>>>(p);
             }
             PSH_LAUNCHED();
         }
@@ -1119,9 +1435,9 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
                       const float *d_queries, int B, int W, int H, int64_t k,
                       int32_t row_offset, int mode,
                       float *d_out_dist, int32_t *d_out_idx,
-                      void *d_ws, size_t ws_bytes, void *stream_) {
+                      void *d_ws, size_t ws_bytes, const void *d_aux, size_t aux_bytes, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (mode != PSH_MODE_EXACT && mode != PSH_MODE_FILTER) return PSH_E_ARG;
+    if (mode != PSH_MODE_EXACT && mode != PSH_MODE_FILTER && mode != PSH_MODE_FFT) return PSH_E_ARG;
     if (!d_dataset || !d_queries || !d_out_dist || !d_out_idx || !d_ws) return PSH_E_ARG;
     if (row_stride < T) return PSH_E_ARG;
     Plan pl;
@@ -1137,11 +1453,20 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
     QState *st = reinterpret_cast<QState *>(ws + pl.off_state);
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(ws + pl.off_keys);
     unsigned int *cand = reinterpret_cast<unsigned int *>(ws + pl.off_cand);
+    float2 *qspec = reinterpret_cast<float2 *>(ws + pl.off_qspec);
+    FftAux aux;
+    const FftAux *auxp = nullptr;
+    if (mode == PSH_MODE_FFT && d_aux != nullptr) {
+        if (!fft_aux_layout(R, T, W, H, const_cast<unsigned char *>(static_cast<const unsigned char *>(d_aux)), aux) ||
+            aux_bytes < aux.total || (reinterpret_cast<uintptr_t>(d_aux) & 255u))
+            return PSH_E_WORKSPACE;
+        auxp = &aux;
+    }
 
     for (int g0 = 0; g0 < B; g0 += QG_MAX) {
         int nq = B - g0 < QG_MAX ? B - g0 : QG_MAX;
         int rc = run_scan_group(d_dataset, R, T, row_stride, d_queries + (size_t)g0 * W, nq, W, H, k, row_offset,
-                                pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap, mode, false,
+                                pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap, qspec + (size_t)g0 * fftx::N, auxp, mode, false,
                                 d_out_dist + (size_t)g0 * k, d_out_idx + (size_t)g0 * k * 2, stream);
         if (rc != PSH_OK) return rc;
     }
@@ -1155,7 +1480,7 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
         for (int i = 0; i < nq; ++i) ovf = ovf || hst[i].overflow != 0;
         if (ovf) {
             int rc = run_scan_group(d_dataset, R, T, row_stride, d_queries + (size_t)g0 * W, nq, W, H, k, row_offset,
-                                    pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap, mode,
+                                    pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap, qspec + (size_t)g0 * fftx::N, auxp, mode,
                                     true,
                                     d_out_dist + (size_t)g0 * k, d_out_idx + (size_t)g0 * k * 2, stream);
             if (rc != PSH_OK) return rc;

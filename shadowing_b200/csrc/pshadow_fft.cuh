@@ -1,0 +1,108 @@
+// pshadow_fft.cuh -- FFT flavour of the filter scan (PSH_MODE_FFT), included by pshadow.cu.
+//
+// The cross term D_t = sum_j q_j y_{t+j} of ||q - y_t||^2 = Q2 + Y2_t - 2 D_t is a correlation:
+// for a whole trajectory it costs O(log N) per window through the FFT instead of W FMAs.  Two
+// trajectories share one complex transform (z = y_a + i y_b; q is real, so the correlation of z
+// with q is corr(y_a) + i corr(y_b)).  What is W- and query-independent is computed once per
+// dataset (psh_fft_prepare): the spectra Z = FFT_4096(z) of all row pairs, the window energies
+// Y2[r][t] (fp64 prefix sums, rounded once) and the pair norms.  Per query the scan then streams
+// Z and Y2 once (2 x the raw bytes), multiplies by conj(FFT(q))/N, runs ONE inverse 4096-point
+// FFT per row pair in registers/shared memory and tests the same rigorous lower bound as the
+// FMA filter; survivors go through the exact re-rank, so results stay bit-identical.
+//
+// FFT: N = 4096 = 16 x 16 x 16, 256 threads, 16 complex values per thread, three radix-16
+// passes in registers with two padded shared-memory exchanges.  Input index n = tid + 256 i,
+// output index k = tid + 256 c: both coalesced, no bit-reversal pass.
+#pragma once
+
+namespace fftx {
+
+constexpr int N = 4096;
+constexpr int THREADS = 256;
+constexpr int EX_STRIDE = 257;                    // padded row of the exchange buffer (float2)
+constexpr int EX_FLOAT2 = 16 * EX_STRIDE;
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+// multiply by exp(DIR * i * angle) given w = exp(+i * angle)
+template <int DIR>
+__device__ __forceinline__ float2 cmul_dir(float2 a, float2 w) {
+    return DIR > 0 ? cmul(a, w) : cmul(a, make_float2(w.x, -w.y));
+}
+
+// 4-point DFT, in place, natural order; DIR = -1 forward (e^{-2 pi i nk/4}), +1 inverse
+template <int DIR>
+__device__ __forceinline__ void fft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3) {
+    const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = csub(a1, a3);
+    const float2 it3 = DIR > 0 ? make_float2(-t3.y, t3.x) : make_float2(t3.y, -t3.x);  // (DIR i) t3
+    a0 = cadd(t0, t2);
+    a2 = csub(t0, t2);
+    a1 = cadd(t1, it3);
+    a3 = csub(t1, it3);
+}
+
+// 16-point DFT of v[0..15] (natural order in, natural order out), all indices compile-time
+template <int DIR>
+__device__ __forceinline__ void fft16(float2 (&v)[16]) {
+    // step 1: for each n1, 4-point DFT over n2 of x[n1 + 4 n2] -> y[n1][k2] kept at v[n1 + 4 k2]
+#pragma unroll
+    for (int n1 = 0; n1 < 4; ++n1) fft4<DIR>(v[n1], v[n1 + 4], v[n1 + 8], v[n1 + 12]);
+    // step 2: twiddles w16^(n1 k2)
+    const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, r = 0.70710678118654752f;
+    const float d = (float)DIR;
+    v[1 + 4 * 1] = cmul(v[1 + 4 * 1], make_float2(c1, d * s1));    // w^1
+    v[2 + 4 * 1] = cmul(v[2 + 4 * 1], make_float2(r, d * r));      // w^2
+    v[3 + 4 * 1] = cmul(v[3 + 4 * 1], make_float2(s1, d * c1));    // w^3
+    v[1 + 4 * 2] = cmul(v[1 + 4 * 2], make_float2(r, d * r));      // w^2
+    {                                                              // w^4 = DIR i
+        const float2 t = v[2 + 4 * 2];
+        v[2 + 4 * 2] = DIR > 0 ? make_float2(-t.y, t.x) : make_float2(t.y, -t.x);
+    }
+    v[3 + 4 * 2] = cmul(v[3 + 4 * 2], make_float2(-r, d * r));     // w^6
+    v[1 + 4 * 3] = cmul(v[1 + 4 * 3], make_float2(s1, d * c1));    // w^3
+    v[2 + 4 * 3] = cmul(v[2 + 4 * 3], make_float2(-r, d * r));     // w^6
+    v[3 + 4 * 3] = cmul(v[3 + 4 * 3], make_float2(-c1, -d * s1));  // w^9
+    // step 3: for each k2, 4-point DFT over n1 -> X[4 k1 + k2] lands at v[k1 + 4 k2]
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) fft4<DIR>(v[4 * k2], v[4 * k2 + 1], v[4 * k2 + 2], v[4 * k2 + 3]);
+    // natural order: X[4 k1 + k2] = v[k1 + 4 k2]  (a register renaming under full unrolling)
+    float2 w[16];
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1)
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) w[4 * k1 + k2] = v[k1 + 4 * k2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = w[i];
+}
+
+// 4096-point transform by one CTA of 256 threads.  In: v[i] = x[tid + 256 i].  Out: v[c] =
+// X[tid + 256 c].  tw[m] = exp(+2 pi i m / 4096).  `ex` is EX_FLOAT2 float2 of shared memory;
+// the caller must __syncthreads() before ex is touched again.
+template <int DIR>
+__device__ __forceinline__ void fft4096(float2 (&v)[16], float2 *ex, const float2 *__restrict__ tw, int tid) {
+    fft16<DIR>(v);  // over i -> a
+#pragma unroll
+    for (int a = 1; a < 16; ++a) v[a] = cmul_dir<DIR>(v[a], __ldg(tw + a * tid));
+#pragma unroll
+    for (int a = 0; a < 16; ++a) ex[a * EX_STRIDE + tid] = v[a];
+    __syncthreads();
+    const int a2 = tid >> 4, t1 = tid & 15;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = ex[a2 * EX_STRIDE + t1 + 16 * i];
+    fft16<DIR>(v);  // over tau2 -> b
+#pragma unroll
+    for (int b = 1; b < 16; ++b) v[b] = cmul_dir<DIR>(v[b], __ldg(tw + 16 * b * t1));
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < 16; ++b) ex[a2 * EX_STRIDE + b * 16 + t1] = v[b];
+    __syncthreads();
+    const int a = tid & 15, bb = tid >> 4;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) v[t] = ex[a * EX_STRIDE + bb * 16 + t];
+    fft16<DIR>(v);  // over tau1 -> c
+}
+
+}  // namespace fftx

@@ -45,7 +45,8 @@ def sharded_scan(ps, rows: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int
     i_loc[..., 0] = _PAD_ROW
     i_loc[..., 1] = 0
     if k_loc > 0:
-        d, i, ps._workspace = _lib.scan_topk(rows, T, q, H, k_loc, ps._row_offset, ps._mode, ps._workspace)
+        mode, aux = ps._mode_and_aux(rows, T, W, H)
+        d, i, ps._workspace = _lib.scan_topk(rows, T, q, H, k_loc, ps._row_offset, mode, ps._workspace, aux)
         d_loc[:, :k_loc] = d
         i_loc[:, :k_loc] = i
     d_all = torch.empty((world, B, k), dtype=torch.float32, device=rows.device)

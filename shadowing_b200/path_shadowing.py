@@ -98,7 +98,7 @@ class PathShadowing:
         device: torch.device | str | None = None,
         row_offset: int = 0,
         process_group=None,
-        scan_mode: str = "filter",
+        scan_mode: str = "auto",
     ):
         if isinstance(dataset, (str, Path)):
             dataset = _load_npy_dir(Path(dataset))
@@ -112,11 +112,17 @@ class PathShadowing:
         self._device = torch.device(device) if device is not None else None
         self._row_offset = int(row_offset)
         self._pg = process_group
-        if scan_mode not in ("filter", "exact"):
-            raise ValueError("scan_mode must be 'filter' or 'exact'")
-        self._mode = _lib.PSH_MODE_FILTER if scan_mode == "filter" else _lib.PSH_MODE_EXACT
+        if scan_mode not in ("auto", "fft", "filter", "exact"):
+            raise ValueError("scan_mode must be 'auto', 'fft', 'filter' or 'exact'")
+        # every mode returns bit-identical results; they differ in how candidates are filtered:
+        #   exact  -- every window with the reference's sub/mul/add sequence
+        #   filter -- 1 FMA per element lower bound, exact re-rank of survivors
+        #   fft    -- lower bound through one inverse FFT per trajectory pair (T <= 4096)
+        #   auto   -- fft when the context is long enough to pay for it, else filter
+        self._scan_mode = scan_mode
         self._resident = None  # (key, device rows (R, row_stride), T)
         self._workspace = None
+        self._fft_aux = None   # (key, aux buffer) for (resident rows, W, H)
 
     # ------------------------------------------------------------------ device residency
     def _dev(self) -> torch.device:
@@ -161,7 +167,21 @@ class PathShadowing:
             rows, T = self._rows_to_device(ds, self._dev())
             self._resident = (key, rows, T)
             self._workspace = None
+            self._fft_aux = None
         return self._resident[1], self._resident[2]
+
+    def _mode_and_aux(self, rows: torch.Tensor, T: int, W: int, H: int):
+        mode = self._scan_mode
+        if mode == "auto":
+            mode = "fft" if (T <= _lib.FFT_MAX_T and W >= 64 and T >= 1024) else "filter"
+        if mode == "exact":
+            return _lib.PSH_MODE_EXACT, None
+        if mode == "filter" or T > _lib.FFT_MAX_T:
+            return _lib.PSH_MODE_FILTER, None
+        key = (rows.data_ptr(), tuple(rows.shape), T, W, H)
+        if self._fft_aux is None or self._fft_aux[0] != key:
+            self._fft_aux = (key, _lib.fft_prepare(rows, T, W, H))
+        return _lib.PSH_MODE_FFT, self._fft_aux[1]
 
     # ------------------------------------------------------------------ scan
     def _scan_device(self, x: torch.Tensor, rows: torch.Tensor, T: int, k: int):
@@ -182,8 +202,9 @@ class PathShadowing:
                 raise RuntimeError(f"context ({W}) + horizon ({H}) longer than the trajectories ({T})")
             if k > n_windows:
                 raise RuntimeError(f"selected index k out of range: k={k} > {n_windows} windows")
-            dist, idx, self._workspace = _lib.scan_topk(rows, T, q, H, k, self._row_offset, self._mode,
-                                                        self._workspace)
+            mode, aux = self._mode_and_aux(rows, T, W, H)
+            dist, idx, self._workspace = _lib.scan_topk(rows, T, q, H, k, self._row_offset, mode,
+                                                        self._workspace, aux)
             return dist, idx
         from .distributed import sharded_scan
         return sharded_scan(self, rows, T, q, H, k)

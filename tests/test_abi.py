@@ -35,7 +35,9 @@ def test_version_errors_and_workspace_sizing():
     assert L.psh_scan_workspace_bytes(10, 100, 1, 90, 20, 4) == 0   # W + H > T
     assert L.psh_scan_workspace_bytes(0, 100, 1, 10, 0, 4) == 0
     # null pointers are rejected before any device work
-    assert L.psh_scan_topk_f32(None, 1, 100, 100, None, 1, 10, 0, 1, 0, 0, None, None, None, 0, None) == -1
+    assert L.psh_scan_topk_f32(None, 1, 100, 100, None, 1, 10, 0, 1, 0, 0, None, None, None, 0, None, 0, None) == -1
+    assert L.psh_fft_aux_bytes(32768, 4096, 252, 20) > 2 * 32768 * 4096 * 4 // 2
+    assert L.psh_fft_aux_bytes(8, 8192, 252, 20) == 0   # T > 4096: fft flavour unsupported
     assert L.psh_gather_paths(None, 1, 1, 1, None, 1, 0, 1, None, None) == -1
     assert L.psh_merge_topk(None, None, 1, 1, 1, 1, None, None, None) == -1
 

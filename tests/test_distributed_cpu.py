@@ -18,7 +18,7 @@ ROOT = Path(__file__).resolve().parents[1]
 def _standins():
     from oracle import oracle
 
-    def scan_topk(rows, T, q, H, k, row_offset=0, mode=1, workspace=None):
+    def scan_topk(rows, T, q, H, k, row_offset=0, mode=1, workspace=None, aux=None):
         d, i = oracle.shadow_topk(rows[:, :T].numpy(), q.numpy(), k, H, row_offset=row_offset)
         return torch.from_numpy(d), torch.from_numpy(i), workspace
 
@@ -65,7 +65,7 @@ def _worker(rank, world, port, R, T, W, H, k, B, tmp):
         ds, q = make_inputs(R, T, W, B, seed=77)
         lo, hi = distributed.shard_bounds(R, world, rank)
         obj = sb.PathShadowing(sb.Identity(W), sb.RelativeMSE(), ds[lo:hi], sb.PredictionContext(H),
-                               device="cpu", row_offset=lo, process_group=dist.group.WORLD)
+                               device="cpu", row_offset=lo, process_group=dist.group.WORLD, scan_mode="filter")
         d, paths, idx = obj.shadow(q, k=k)
         np.savez(Path(tmp) / f"rank{rank}.npz", d=d, paths=paths, idx=idx)
     finally:

@@ -21,7 +21,7 @@ def _obj(ds, W, H, **kw):
     return sb.PathShadowing(sb.Identity(W), sb.RelativeMSE(), ds, sb.PredictionContext(H), **kw)
 
 
-@pytest.mark.parametrize("mode", ["exact", "filter"])
+@pytest.mark.parametrize("mode", ["exact", "filter", "fft"])
 def test_golden_shadow_bit_exact(golden, mode):
     obj = _obj(golden["dataset"], golden["W"], golden["H"], scan_mode=mode)
     d, paths, idx = obj.shadow(golden["x_context"], k=golden["k"], n_splits=golden["n_splits"], cuda=True)
@@ -32,7 +32,7 @@ def test_golden_shadow_bit_exact(golden, mode):
     assert np.array_equal(paths, golden["paths"])
 
 
-@pytest.mark.parametrize("mode", ["exact", "filter"])
+@pytest.mark.parametrize("mode", ["exact", "filter", "fft"])
 @pytest.mark.parametrize("R,T,W,H,k,B", [
     (512, 4096, 252, 20, 1024, 2),    # north-star window/k on a subsample of rows
     (300, 1000, 100, 0, 77, 3),       # no horizon, odd sizes
@@ -71,10 +71,40 @@ def test_unaligned_rows_take_the_plain_load_path():
     ds, q = make_inputs(33, 1001, 50, 2, seed=21)
     rows = torch.tensor(ds[:, 0, :]).cuda()  # stride 1001
     qd = torch.tensor(q[:, 0, :]).cuda()
-    for mode in (_lib.PSH_MODE_EXACT, _lib.PSH_MODE_FILTER):
-        d, idx, _ = _lib.scan_topk(rows, 1001, qd, 7, 300, 0, mode)
+    for mode in (_lib.PSH_MODE_EXACT, _lib.PSH_MODE_FILTER, _lib.PSH_MODE_FFT):
+        aux = _lib.fft_prepare(rows, 1001, 50, 7) if mode == _lib.PSH_MODE_FFT else None
+        d, idx, _ = _lib.scan_topk(rows, 1001, qd, 7, 300, 0, mode, None, aux)
         do, io = oracle.shadow_topk(ds, q, 300, 7)
         assert_topk_equal(d.cpu().numpy(), idx.cpu().numpy(), do, io)
+
+
+def test_fft4096_matches_numpy_and_error_budget():
+    """The library's 4096-point FFT against numpy (fp64), both directions, and the constant the
+    lower bound relies on: |c^_t - c_t| <= CF u Qmax ynorm with CF = 512 (observed: a few units)."""
+    rng = np.random.default_rng(0)
+    ds = (rng.standard_normal((6, 4096)) * 0.01).astype(np.float32)
+    rows = torch.tensor(ds).cuda()
+    aux = _lib.fft_prepare(rows, 4096, 252, 20)
+    z = (rng.standard_normal((5, 4096)) + 1j * rng.standard_normal((5, 4096))).astype(np.complex64)
+    zd = torch.tensor(z).cuda()
+    for direction, ref in ((-1, np.fft.fft(z.astype(np.complex128), axis=1)),
+                           (1, np.fft.ifft(z.astype(np.complex128), axis=1) * 4096)):
+        out = _lib.debug_fft4096(zd, direction, aux).cpu().numpy()
+        err = np.linalg.norm(out - ref, axis=1) / np.linalg.norm(ref, axis=1)
+        assert err.max() < 40 * 2.0 ** -24, err      # theory: ~80 u worst case, ~3 u typical
+    # full pipeline: forward (library), pointwise conj(Q)/N, inverse (library) vs fp64 correlation
+    q = (rng.standard_normal(252) * 0.01).astype(np.float32)
+    pair = (ds[0] + 1j * ds[1]).astype(np.complex64)[None]
+    Z = _lib.debug_fft4096(torch.tensor(pair).cuda(), -1, aux)
+    Q = np.fft.fft(np.pad(q.astype(np.float64), (0, 4096 - 252)))
+    Qc = torch.tensor((np.conj(Q) / 4096).astype(np.complex64)).cuda()
+    c = _lib.debug_fft4096(Z * Qc[None], 1, aux).cpu().numpy()[0]
+    Tp = 4096 - 252 + 1
+    ca = np.array([np.dot(q.astype(np.float64), ds[0, t:t + 252].astype(np.float64)) for t in range(Tp)])
+    cb = np.array([np.dot(q.astype(np.float64), ds[1, t:t + 252].astype(np.float64)) for t in range(Tp)])
+    err = max(np.abs(c.real[:Tp] - ca).max(), np.abs(c.imag[:Tp] - cb).max())
+    bound_unit = 2.0 ** -24 * np.abs(Q).max() * np.sqrt((ds[0].astype(np.float64) ** 2).sum() + (ds[1].astype(np.float64) ** 2).sum())
+    assert err < 16 * bound_unit, (err / bound_unit)   # CF = 512 leaves >= 32x head-room
 
 
 def _perm_stride(R):
@@ -86,7 +116,7 @@ def _perm_stride(R):
     return p % R or 1
 
 
-@pytest.mark.parametrize("mode", ["exact", "filter"])
+@pytest.mark.parametrize("mode", ["exact", "filter", "fft"])
 def test_adversarial_order_overflows_then_recovers(mode):
     """Seed rows far, every other row near: the candidate buffer overflows and the scan must
     re-run in its safe schedule and still return the exact answer."""
