@@ -620,26 +620,81 @@ struct FftScanParams {
 // One CTA per row pair: Z * conj(Q)/N -> inverse FFT -> (D_a[t], D_b[t]) for t = tid + 256 c.
 // Lower bound LB = Q2 + Y2 - 2 D^ - slack,
 //   slack = 2 cf_u Qmax ynorm + 8u (Q2 + ynorm^2)   (FFT error; Y2, Q2 roundings and the combination)
+// Staging: the pair's spectrum (32 KiB) and its two window-energy rows arrive by TMA bulk copies
+// issued one pair ahead -- the spectrum buffer is free as soon as it has been multiplied into
+// registers, the energy buffer as soon as the epilogue has read it -- so HBM latency hides
+// behind the transform of the current pair.  With a single query its spectrum stays in
+// registers (16 values per thread, a function of tid only).
+__device__ __forceinline__ long long fft_pair_of_slot(const FftScanParams &p, long long slot) {
+    const unsigned long long prod = (unsigned long long)slot * (unsigned long long)p.perm;
+    const unsigned long long qq = __double2ull_rz(__ull2double_rz(prod) * p.inv_np);
+    long long pair = (long long)(prod - qq * (unsigned long long)p.npairs);
+    if (pair < 0) pair += p.npairs;
+    else if (pair >= p.npairs) pair -= p.npairs;
+    return pair;
+}
+
+template <bool SINGLEQ>
 __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftScanParams p) {
-    __shared__ float2 ex[fftx::EX_FLOAT2];
+    extern __shared__ __align__(128) unsigned char fsm[];
+    float2 *Zs = reinterpret_cast<float2 *>(fsm);
+    float *Y2s = reinterpret_cast<float *>(fsm + sizeof(float2) * fftx::N);
+    float2 *ex = reinterpret_cast<float2 *>(fsm + sizeof(float2) * fftx::N + sizeof(float) * 2 * p.y2_stride);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(ex + fftx::EX_FLOAT2);
     const int tid = threadIdx.x, lane = tid & 31;
-    for (long long slot = p.i0 + blockIdx.x; slot < p.i1; slot += gridDim.x) {
-        const unsigned long long prod = (unsigned long long)slot * (unsigned long long)p.perm;
-        const unsigned long long qq = __double2ull_rz(__ull2double_rz(prod) * p.inv_np);
-        long long pair = (long long)(prod - qq * (unsigned long long)p.npairs);
-        if (pair < 0) pair += p.npairs;
-        else if (pair >= p.npairs) pair -= p.npairs;
-        const float2 *Zp = p.Z + (size_t)pair * fftx::N;
+    const uint32_t barZ = smem_u32(&bars[0]), barY = smem_u32(&bars[1]);
+    if (tid == 0) {
+        mbar_init(barZ, 1);
+        mbar_init(barY, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue_z = [&](long long pair) {  // thread 0
+        mbar_expect_tx(barZ, (uint32_t)(sizeof(float2) * fftx::N));
+        bulk_g2s(smem_u32(Zs), p.Z + (size_t)pair * fftx::N, (uint32_t)(sizeof(float2) * fftx::N), barZ);
+    };
+    auto issue_y = [&](long long pair) {  // thread 0
+        const long long ra = 2 * pair, rb = (ra + 1 < p.R) ? ra + 1 : ra;
+        const uint32_t bytes = (uint32_t)(sizeof(float) * p.y2_stride);
+        mbar_expect_tx(barY, 2 * bytes);
+        bulk_g2s(smem_u32(Y2s), p.Y2 + (size_t)ra * p.y2_stride, bytes, barY);
+        bulk_g2s(smem_u32(Y2s + p.y2_stride), p.Y2 + (size_t)rb * p.y2_stride, bytes, barY);
+    };
+
+    long long slot = p.i0 + blockIdx.x;
+    if (slot >= p.i1) return;
+    long long pair = fft_pair_of_slot(p, slot);
+    if (tid == 0) { issue_z(pair); issue_y(pair); }
+
+    float2 qreg[16];
+    if (SINGLEQ) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) qreg[i] = __ldg(p.Qc + tid + 256 * i);
+    }
+    uint32_t phZ = 0, phY = 0;
+    for (; slot < p.i1; slot += gridDim.x) {
+        const long long nslot = slot + gridDim.x;
+        const long long npair = nslot < p.i1 ? fft_pair_of_slot(p, nslot) : -1;
         const long long ra = 2 * pair, rb = ra + 1;
         const bool has_b = rb < p.R;
         const float yn = p.ynorm[pair];
-        const float *y2a = p.Y2 + (size_t)ra * p.y2_stride;
-        const float *y2b = p.Y2 + (size_t)(has_b ? rb : ra) * p.y2_stride;
+        mbar_wait(barZ, phZ); phZ ^= 1;
+        mbar_wait(barY, phY); phY ^= 1;  // (landed long ago except for the very first pair)
         for (int b = 0; b < p.nq; ++b) {
-            const float2 *Qb = p.Qc + (size_t)b * fftx::N;
             float2 v[16];
+            if (SINGLEQ) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fftx::cmul(__ldg(Zp + tid + 256 * i), __ldg(Qb + tid + 256 * i));
+                for (int i = 0; i < 16; ++i) v[i] = fftx::cmul(Zs[tid + 256 * i], qreg[i]);
+            } else {
+                const float2 *Qb = p.Qc + (size_t)b * fftx::N;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fftx::cmul(Zs[tid + 256 * i], __ldg(Qb + tid + 256 * i));
+            }
+            if (b == p.nq - 1) {
+                __syncthreads();  // every thread has taken its part of the spectrum
+                if (tid == 0 && npair >= 0) issue_z(npair);
+            }
             fftx::fft4096<1>(v, ex, p.tw, tid);
             const float q2 = p.st[b].q2, qmax = p.st[b].qmax;
             const float thr = ld_volatile_f32(&p.st[b].thr_fast);
@@ -650,12 +705,10 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
             for (int c = 0; c < 16; ++c) {
                 const int t = tid + 256 * c;
                 if (t < p.Tp) {
-                    const float va = fmaf(-2.0f, v[c].x, __ldg(y2a + t)) + base;
+                    const float va = fmaf(-2.0f, v[c].x, Y2s[t]) + base;
                     if (!(va > 0.0f)) mask |= 1u << c;
-                    if (has_b) {
-                        const float vb = fmaf(-2.0f, v[c].y, __ldg(y2b + t)) + base;
-                        if (!(vb > 0.0f)) mask |= 1u << (16 + c);
-                    }
+                    const float vb = fmaf(-2.0f, v[c].y, Y2s[p.y2_stride + t]) + base;
+                    if (has_b && !(vb > 0.0f)) mask |= 1u << (16 + c);
                 }
             }
             if (__any_sync(FULL, mask != 0)) {
@@ -680,8 +733,10 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
                     if (mask & (1u << (16 + c))) { if (pos < p.cap) dst[pos] = fb + (unsigned int)(tid + 256 * c); ++pos; }
                 }
             }
-            __syncthreads();  // ex is reused by the next transform
+            __syncthreads();  // ex (and, after the last query, the energy rows) may be overwritten
         }
+        if (tid == 0 && npair >= 0) issue_y(npair);
+        pair = npair;
     }
 }
 
@@ -1356,6 +1411,13 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
         fp.st = st; fp.cand = cand; fp.cap = pl.cap;
         fp.cf_u = 512.0f * 5.9604644775390625e-8f;
     }
+    const size_t smem_fft = use_fft ? sizeof(float2) * fftx::N + sizeof(float) * 2 * (size_t)aux->y2_stride
+                                          + sizeof(float2) * fftx::EX_FLOAT2 + 16
+                                    : 0;
+    if (use_fft) {
+        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+    }
 
     // chunk schedule over permuted slots (rows, or row pairs in the fft flavour): seed chunk
     // (always exact), then geometric growth; in safe mode every chunk fits the candidate buffer
@@ -1379,7 +1441,8 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
             if (ctas > max_ctas) ctas = max_ctas;
             {
                 ProfScope ps(stream, 0);
-                fft_scan_kernel<<<(unsigned int)ctas, fftx::THREADS, 0, stream>>>(fp);
+                if (nq == 1) fft_scan_kernel<true><<<(unsigned int)ctas, fftx::THREADS, smem_fft, stream>>>(fp);
+                else fft_scan_kernel<false><<<(unsigned int)ctas, fftx::THREADS, smem_fft, stream>>>(fp);
             }
             PSH_LAUNCHED();
         } else {
