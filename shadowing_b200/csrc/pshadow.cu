@@ -127,37 +127,39 @@ __device__ __forceinline__ float dist_from_s(float s, float qn) { return __fdiv_
 // query preparation: ||q|| in torch's contiguous-reduction order (8 interleaved partial sums,
 // lanes added 0..7, scalar tail), state reset.  path_distance.py:65 `x.norm(dim=-1)`.
 // ------------------------------------------------------------------------------------------
-__global__ void qprep_kernel(const float *__restrict__ q, int W, int nq, QState *st) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) qprep_kernel(const float *__restrict__ q, int W, int nq, QState *st) {
+    // one warp per query; lanes 0..7 own torch's 8 interleaved partial sums
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (b >= nq) return;
     const float *x = q + (size_t)b * W;
-    float acc[8];
-#pragma unroll
-    for (int l = 0; l < 8; ++l) acc[l] = 0.0f;
-    int n8 = (W / 8) * 8;
-    for (int j = 0; j < n8; j += 8) {
-#pragma unroll
-        for (int l = 0; l < 8; ++l) acc[l] = __fadd_rn(acc[l], __fmul_rn(x[j + l], x[j + l]));
-    }
+    const int n8 = (W / 8) * 8;
+    float acc = 0.0f;
+    if (lane < 8)
+        for (int j = lane; j < n8; j += 8) acc = __fadd_rn(acc, __fmul_rn(x[j], x[j]));
     float s = 0.0f;
 #pragma unroll
-    for (int l = 0; l < 8; ++l) s = __fadd_rn(s, acc[l]);
-    for (int j = n8; j < W; ++j) s = __fadd_rn(s, __fmul_rn(x[j], x[j]));
+    for (int l = 0; l < 8; ++l) s = __fadd_rn(s, __shfl_sync(FULL, acc, l));
+    for (int j = n8; j < W; ++j) s = __fadd_rn(s, __fmul_rn(x[j], x[j]));  // scalar tail (all lanes alike)
     double q2 = 0.0;
-    for (int j = 0; j < W; ++j) q2 += (double)x[j] * (double)x[j];
-    QState z;
-    z.tau_key = ~0ull;
-    z.s_thr = __int_as_float(0x7f800000);
-    z.qnorm = __fsqrt_rn(s);
-    z.count = 0;
-    z.overflow = 0;
-    z.cur = 0;
-    z.ccount = 0;
-    z.thr_fast = __int_as_float(0x7f800000);
-    z.q2 = (float)q2;
-    z.qmax = 0.0f;
-    for (int i = 0; i < 5; ++i) z.pad[i] = 0;
-    st[b] = z;
+    for (int j = lane; j < W; j += 32) q2 += (double)x[j] * (double)x[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q2 += __shfl_xor_sync(FULL, q2, o);
+    if (lane == 0) {
+        QState z;
+        z.tau_key = ~0ull;
+        z.s_thr = __int_as_float(0x7f800000);
+        z.qnorm = __fsqrt_rn(s);
+        z.count = 0;
+        z.overflow = 0;
+        z.cur = 0;
+        z.ccount = 0;
+        z.thr_fast = __int_as_float(0x7f800000);
+        z.q2 = (float)q2;
+        z.qmax = 0.0f;
+        for (int i = 0; i < 5; ++i) z.pad[i] = 0;
+        st[b] = z;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -571,32 +573,33 @@ __global__ void __launch_bounds__(fftx::THREADS) fft_prep_y2_kernel(const float 
     for (int t = tid; t < a.y2_stride; t += fftx::THREADS) o[t] = t < Tp ? (float)(pfx[t + W] - pfx[t]) : 0.0f;
 }
 
-// conj(FFT_4096(q padded))/4096 per query (direct fp64 DFT on the exact twiddle table) + max |Q_k|
+// conj(FFT_4096(q padded))/4096 per query (direct fp64 DFT on the exact twiddle table) and
+// max_k |Q_k|.  grid = (4096/256, nq): one frequency per thread.
 __global__ void __launch_bounds__(fftx::THREADS) qfft_kernel(const float *__restrict__ q, int W,
                                                              const double2 *__restrict__ tw64, float2 *Qc, QState *st) {
     extern __shared__ double qd[];
     __shared__ double red[fftx::THREADS / 32];
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.y, tid = threadIdx.x;
     for (int j = tid; j < W; j += fftx::THREADS) qd[j] = (double)q[(size_t)b * W + j];
     __syncthreads();
-    double mx = 0.0;
-    for (int k = tid; k < fftx::N; k += fftx::THREADS) {
-        double re = 0.0, im = 0.0;
-        for (int j = 0; j < W; ++j) {
-            const double2 w = tw64[(j * k) & (fftx::N - 1)];  // exp(+i theta): Q_k = sum q_j exp(-i theta)
-            re += qd[j] * w.x;
-            im -= qd[j] * w.y;
-        }
-        mx = fmax(mx, re * re + im * im);
-        Qc[(size_t)b * fftx::N + k] = make_float2((float)(re / fftx::N), (float)(-im / fftx::N));
+    const int k = blockIdx.x * fftx::THREADS + tid;
+    double re = 0.0, im = 0.0;
+#pragma unroll 4
+    for (int j = 0; j < W; ++j) {
+        const double2 w = __ldg(tw64 + ((j * k) & (fftx::N - 1)));  // exp(+i theta): Q_k = sum q_j exp(-i theta)
+        re += qd[j] * w.x;
+        im -= qd[j] * w.y;
     }
+    Qc[(size_t)b * fftx::N + k] = make_float2((float)(re / fftx::N), (float)(-im / fftx::N));
+    double mx = re * re + im * im;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
     if ((tid & 31) == 0) red[tid >> 5] = mx;
     __syncthreads();
     if (tid == 0) {
         for (int i = 1; i < fftx::THREADS / 32; ++i) mx = fmax(mx, red[i]);
-        st[b].qmax = __double2float_ru(sqrt(mx) * (1.0 + 1e-7));
+        const float m = __double2float_ru(sqrt(mx) * (1.0 + 1e-7));
+        atomicMax(reinterpret_cast<unsigned int *>(&st[b].qmax), __float_as_uint(m));  // positive floats order as uints
     }
 }
 
@@ -833,141 +836,6 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(const float *__restr
 }
 
 // ------------------------------------------------------------------------------------------
-// select: keep the k smallest keys of a query's candidate list (MSB-first radix select on the
-// 64-bit key, compaction into the other ping-pong buffer), publish the new thresholds.
-// Replaces torch.topk + cat + topk (path_shadowing.py:165,170-173).
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void hist_add(unsigned int *hist, unsigned int digit, bool active) {
-    // warp-aggregated shared-memory histogram increment
-    unsigned int act = __ballot_sync(FULL, active);
-    if (!active) return;
-    unsigned int peers = __match_any_sync(act, digit);
-    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned int)__popc(peers));
-}
-
-__global__ void __launch_bounds__(SEL_THREADS) select_kernel(QState *st_all, unsigned long long *keys_all,
-                                                              unsigned int cap, unsigned int k, int W) {
-    __shared__ unsigned int hist[256];
-    __shared__ unsigned long long s_prefix;
-    __shared__ unsigned int s_need, s_done, s_out;
-    QState *st = st_all + blockIdx.x;
-    const unsigned int cnt_raw = st->count;
-    const unsigned int M = min(cnt_raw, cap);
-    const unsigned int cur = st->cur;
-    const unsigned long long *src = keys_all + ((size_t)blockIdx.x * 2 + cur) * cap;
-    unsigned long long *dst = keys_all + ((size_t)blockIdx.x * 2 + (cur ^ 1)) * cap;
-    const int tid = threadIdx.x;
-    if (tid == 0) {
-        if (cnt_raw > cap) st->overflow = 1;
-        s_prefix = 0; s_need = k; s_done = 0; s_out = 0;
-    }
-    if (M <= k) {  // nothing to drop yet (uniform branch: M, k are block-uniform)
-        if (tid == 0) { st->count = M; st->ccount = 0; }
-        return;
-    }
-    __syncthreads();
-    unsigned long long tau = ~0ull;
-    for (int pass = 0; pass < 8; ++pass) {
-        const int shift = 56 - 8 * pass;
-        for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
-        __syncthreads();
-        const unsigned long long prefix = s_prefix;
-        const unsigned int Mr = (M + 31u) & ~31u;
-        for (unsigned int i = tid; i < Mr; i += SEL_THREADS) {
-            bool act = i < M;
-            unsigned long long key = act ? src[i] : 0ull;
-            if (pass > 0) act = act && ((key >> (shift + 8)) == (prefix >> (shift + 8)));
-            hist_add(hist, (unsigned int)(key >> shift) & 255u, act);
-        }
-        __syncthreads();
-        if (tid < 32) {  // warp 0: locate the bin holding the need-th smallest key
-            unsigned int need = s_need;
-            unsigned int loc[8], sum = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { loc[i] = hist[tid * 8 + i]; sum += loc[i]; }
-            unsigned int incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                unsigned int v = __shfl_up_sync(FULL, incl, o);
-                if (tid >= o) incl += v;
-            }
-            unsigned int excl = incl - sum;
-            if (excl < need && need <= incl) {  // exactly one lane
-                unsigned int c = excl;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (c < need && need <= c + loc[i]) {
-                        s_prefix = prefix | ((unsigned long long)(tid * 8 + i) << shift);
-                        s_need = need - c;
-                        s_done = (loc[i] == need - c) ? 1u : 0u;
-                    }
-                    c += loc[i];
-                }
-            }
-        }
-        __syncthreads();
-        if (s_done || pass == 7) {
-            tau = s_prefix | (shift ? ((1ull << shift) - 1ull) : 0ull);
-            break;
-        }
-    }
-    // compaction: exactly k keys are <= tau
-    for (unsigned int i = tid; i < ((M + 31u) & ~31u); i += SEL_THREADS) {
-        bool keep = false;
-        unsigned long long key = 0;
-        if (i < M) { key = src[i]; keep = key <= tau; }
-        unsigned int bal = __ballot_sync(FULL, keep);
-        if (bal) {
-            unsigned int base = 0;
-            if ((tid & 31) == 0) base = atomicAdd(&s_out, (unsigned int)__popc(bal));
-            base = __shfl_sync(FULL, base, 0);
-            if (keep) dst[base + __popc(bal & ((1u << (tid & 31)) - 1u))] = key;
-        }
-    }
-    __syncthreads();
-    if (tid < 32) {
-        // s_thr: the largest float s with dist_from_s(s) <= tau's distance (monotone map)
-        const float qn = st->qnorm;
-        const float taud = __uint_as_float((unsigned int)(tau >> 32));
-        float s_thr;
-        if (!(taud < __int_as_float(0x7f800000)) || !(qn > 0.0f)) {
-            s_thr = __int_as_float(0x7f800000);
-        } else {
-            const float est = __fmul_rn(__fmul_rn(taud, qn), __fmul_rn(taud, qn));
-            unsigned int eb = __float_as_uint(est);
-            // probe est-16 .. est+15 ulps in parallel, fall back to bisection outside that band
-            unsigned int lo_b = eb > 16u ? eb - 16u : 0u;
-            unsigned int cand = min(lo_b + (unsigned int)tid, 0x7f800000u);
-            bool ok = dist_from_s(__uint_as_float(cand), qn) <= taud;
-            unsigned int okm = __ballot_sync(FULL, ok);
-            if (okm != 0u && okm != FULL) {
-                int hi = 31 - __clz(okm);  // monotone: ok lanes form a prefix
-                s_thr = __uint_as_float(min(lo_b + (unsigned int)hi, 0x7f800000u));
-            } else {
-                unsigned int lo = 0u, hi = 0x7f800000u;  // invariant: f(lo) ok (s=0 -> d=0), answer in [lo,hi]
-                while (lo < hi) {
-                    unsigned int mid = lo + (hi - lo + 1u) / 2u;
-                    if (dist_from_s(__uint_as_float(mid), qn) <= taud) lo = mid; else hi = mid - 1u;
-                }
-                s_thr = __uint_as_float(lo);
-            }
-        }
-        if (tid == 0) {
-            st->tau_key = tau;
-            st->s_thr = s_thr;
-            // exact s >= S_true (1 - gamma_{W+2}) - W 2^-126  =>  S_true <= thr_fast (rounded up)
-            const double widen = 1.0 + 2.0 * (double)(W + 8) * 5.9604644775390625e-8;
-            st->thr_fast = (s_thr < __int_as_float(0x7f800000))
-                               ? __double2float_ru((double)s_thr * widen + 1e-30)
-                               : s_thr;
-            st->count = s_out;
-            st->ccount = 0;
-            st->cur = cur ^ 1u;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // bitonic sort of n (power of two) 64-bit keys by one CTA; data in shared or global memory
 // ------------------------------------------------------------------------------------------
 __device__ void bitonic_sort_cta(unsigned long long *a, unsigned int n) {
@@ -984,6 +852,253 @@ __device__ void bitonic_sort_cta(unsigned long long *a, unsigned int n) {
         }
     }
     __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// select: keep the k smallest keys of a query's candidate list, publish the new thresholds and,
+// after the last chunk, order the k keys and decode them into the outputs.
+// Replaces torch.topk + cat + topk (path_shadowing.py:165,170-173).  One CTA per query.
+//   fast path   : min/max of the distance bits -> 2048 linear bins over that range -> the bin
+//                 holding the k-th key -> keys below it are kept, keys inside it (a handful) are
+//                 sorted in shared memory and the smallest ones complete the k  (3 passes)
+//   generic path: MSB-first radix select on the full 64-bit key (8-bit digits), used when the
+//                 fast path degenerates (all distances equal, or a huge tie group at the k-th)
+// ------------------------------------------------------------------------------------------
+constexpr int SEL_BINS = 2048;
+constexpr int SEL_LIST = 4096;  // boundary-bin keys / fused final sort capacity (keys)
+
+__device__ __forceinline__ void hist_add(unsigned int *hist, unsigned int digit, bool active) {
+    // warp-aggregated shared-memory histogram increment
+    unsigned int act = __ballot_sync(FULL, active);
+    if (!active) return;
+    unsigned int peers = __match_any_sync(act, digit);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned int)__popc(peers));
+}
+
+// generic path; returns tau (exactly k keys of src are <= tau) and compacts them into dst
+__device__ unsigned long long select_generic(const unsigned long long *src, unsigned long long *dst, unsigned int M,
+                                             unsigned int k, unsigned int *hist, unsigned long long *s_prefix,
+                                             unsigned int *s_need, unsigned int *s_done, unsigned int *s_out) {
+    const int tid = threadIdx.x;
+    if (tid == 0) { *s_prefix = 0; *s_need = k; *s_done = 0; *s_out = 0; }
+    __syncthreads();
+    unsigned long long tau = ~0ull;
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 56 - 8 * pass;
+        for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
+        __syncthreads();
+        const unsigned long long prefix = *s_prefix;
+        const unsigned int Mr = (M + 31u) & ~31u;
+        for (unsigned int i = tid; i < Mr; i += SEL_THREADS) {
+            bool act = i < M;
+            unsigned long long key = act ? src[i] : 0ull;
+            if (pass > 0) act = act && ((key >> (shift + 8)) == (prefix >> (shift + 8)));
+            hist_add(hist, (unsigned int)(key >> shift) & 255u, act);
+        }
+        __syncthreads();
+        if (tid < 32) {  // warp 0: locate the bin holding the need-th smallest key
+            unsigned int need = *s_need;
+            unsigned int loc[8], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { loc[i] = hist[tid * 8 + i]; sum += loc[i]; }
+            unsigned int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned int v = __shfl_up_sync(FULL, incl, o);
+                if (tid >= o) incl += v;
+            }
+            unsigned int excl = incl - sum;
+            if (excl < need && need <= incl) {  // exactly one lane
+                unsigned int cc = excl;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (cc < need && need <= cc + loc[i]) {
+                        *s_prefix = prefix | ((unsigned long long)(tid * 8 + i) << shift);
+                        *s_need = need - cc;
+                        *s_done = (loc[i] == need - cc) ? 1u : 0u;
+                    }
+                    cc += loc[i];
+                }
+            }
+        }
+        __syncthreads();
+        if (*s_done || pass == 7) {
+            tau = *s_prefix | (shift ? ((1ull << shift) - 1ull) : 0ull);
+            break;
+        }
+    }
+    for (unsigned int i = tid; i < ((M + 31u) & ~31u); i += SEL_THREADS) {
+        bool keep = false;
+        unsigned long long key = 0;
+        if (i < M) { key = src[i]; keep = key <= tau; }
+        unsigned int bal = __ballot_sync(FULL, keep);
+        if (bal) {
+            unsigned int base = 0;
+            if ((tid & 31) == 0) base = atomicAdd(s_out, (unsigned int)__popc(bal));
+            base = __shfl_sync(FULL, base, 0);
+            if (keep) dst[base + __popc(bal & ((1u << (tid & 31)) - 1u))] = key;
+        }
+    }
+    __syncthreads();
+    return tau;
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) select_kernel(QState *st_all, unsigned long long *keys_all,
+                                                              unsigned int cap, unsigned int k, int W, int final_sort,
+                                                              unsigned int Tp, int row_offset, float *out_d,
+                                                              int *out_idx) {
+    __shared__ unsigned int hist[SEL_BINS];
+    __shared__ unsigned long long list[SEL_LIST];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned int s_need, s_done, s_out, s_min, s_max, s_bin, s_below, s_nlist, s_fast;
+    QState *st = st_all + blockIdx.x;
+    const unsigned int cnt_raw = st->count;
+    const unsigned int M = min(cnt_raw, cap);
+    const unsigned int cur = st->cur;
+    const unsigned long long *src = keys_all + ((size_t)blockIdx.x * 2 + cur) * cap;
+    unsigned long long *dst = keys_all + ((size_t)blockIdx.x * 2 + (cur ^ 1)) * cap;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) {
+        if (cnt_raw > cap) st->overflow = 1;
+        s_min = 0xffffffffu; s_max = 0u; s_out = 0; s_nlist = 0; s_fast = 0;
+    }
+    const unsigned long long *kept = src;  // where the k (or M <= k) surviving keys live
+    unsigned int nkept = M;
+    if (M > k) {  // uniform branch
+        for (int i = tid; i < SEL_BINS; i += SEL_THREADS) hist[i] = 0;
+        __syncthreads();
+        // pass 1: range of the distance bits
+        unsigned int mn = 0xffffffffu, mx = 0u;
+        for (unsigned int i = tid; i < M; i += SEL_THREADS) {
+            const unsigned int db = (unsigned int)(src[i] >> 32);
+            mn = min(mn, db); mx = max(mx, db);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = min(mn, __shfl_xor_sync(FULL, mn, o));
+            mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+        }
+        if (lane == 0) { atomicMin(&s_min, mn); atomicMax(&s_max, mx); }
+        __syncthreads();
+        const unsigned int lo = s_min, range = s_max - s_min;
+        unsigned int shift = 0;
+        while ((range >> shift) >= (unsigned int)SEL_BINS) ++shift;
+        bool fast = range > 0;
+        if (fast) {
+            // pass 2: histogram
+            for (unsigned int i = tid; i < M; i += SEL_THREADS)
+                atomicAdd(&hist[((unsigned int)(src[i] >> 32) - lo) >> shift], 1u);
+            __syncthreads();
+            if (tid < 32) {  // the bin holding the k-th key
+                unsigned int sum = 0;
+                for (int i = 0; i < SEL_BINS / 32; ++i) sum += hist[tid * (SEL_BINS / 32) + i];
+                unsigned int incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    unsigned int v = __shfl_up_sync(FULL, incl, o);
+                    if (tid >= o) incl += v;
+                }
+                unsigned int excl = incl - sum;
+                if (excl < k && k <= incl) {
+                    unsigned int cc = excl;
+                    for (int i = 0; i < SEL_BINS / 32; ++i) {
+                        const unsigned int h = hist[tid * (SEL_BINS / 32) + i];
+                        if (cc < k && k <= cc + h) { s_bin = tid * (SEL_BINS / 32) + i; s_below = cc; s_fast = h <= (unsigned int)SEL_LIST; }
+                        cc += h;
+                    }
+                }
+            }
+            __syncthreads();
+            fast = s_fast != 0;
+        }
+        unsigned long long tau;
+        if (fast) {
+            // pass 3: keys below the boundary bin are kept, keys inside it go to the list
+            const unsigned int kb = s_bin;
+            for (unsigned int i = tid; i < ((M + 31u) & ~31u); i += SEL_THREADS) {
+                unsigned long long key = 0;
+                unsigned int bin = 0xffffffffu;
+                if (i < M) { key = src[i]; bin = ((unsigned int)(key >> 32) - lo) >> shift; }
+                const bool keep = bin < kb;
+                if (bin == kb) list[atomicAdd(&s_nlist, 1u)] = key;
+                const unsigned int bal = __ballot_sync(FULL, keep);
+                if (bal) {
+                    unsigned int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_out, (unsigned int)__popc(bal));
+                    base = __shfl_sync(FULL, base, 0);
+                    if (keep) dst[base + __popc(bal & ((1u << lane) - 1u))] = key;
+                }
+            }
+            __syncthreads();
+            const unsigned int nl = s_nlist, need = k - s_below;  // 1 <= need <= nl
+            unsigned int np2 = 1; while (np2 < nl) np2 <<= 1;
+            for (unsigned int i = nl + tid; i < np2; i += SEL_THREADS) list[i] = ~0ull;
+            bitonic_sort_cta(list, np2);
+            tau = list[need - 1];
+            for (unsigned int i = tid; i < need; i += SEL_THREADS) dst[s_below + i] = list[i];
+            __syncthreads();
+            if (tid == 0) s_out = k;
+        } else {
+            tau = select_generic(src, dst, M, k, hist, &s_prefix, &s_need, &s_done, &s_out);
+        }
+        kept = dst;
+        nkept = k;
+        if (tid < 32) {
+            // s_thr: the largest float s with dist_from_s(s) <= tau's distance (monotone map)
+            const float qn = st->qnorm;
+            const float taud = __uint_as_float((unsigned int)(tau >> 32));
+            float s_thr;
+            if (!(taud < __int_as_float(0x7f800000)) || !(qn > 0.0f)) {
+                s_thr = __int_as_float(0x7f800000);
+            } else {
+                const float est = __fmul_rn(__fmul_rn(taud, qn), __fmul_rn(taud, qn));
+                unsigned int eb = __float_as_uint(est);
+                // probe est-16 .. est+15 ulps in parallel, fall back to bisection outside that band
+                unsigned int lo_b = eb > 16u ? eb - 16u : 0u;
+                unsigned int cand = min(lo_b + (unsigned int)tid, 0x7f800000u);
+                bool ok = dist_from_s(__uint_as_float(cand), qn) <= taud;
+                unsigned int okm = __ballot_sync(FULL, ok);
+                if (okm != 0u && okm != FULL) {
+                    int hi = 31 - __clz(okm);  // monotone: ok lanes form a prefix
+                    s_thr = __uint_as_float(min(lo_b + (unsigned int)hi, 0x7f800000u));
+                } else {
+                    unsigned int l2 = 0u, h2 = 0x7f800000u;  // invariant: f(l2) ok (s=0 -> d=0), answer in [l2,h2]
+                    while (l2 < h2) {
+                        unsigned int mid = l2 + (h2 - l2 + 1u) / 2u;
+                        if (dist_from_s(__uint_as_float(mid), qn) <= taud) l2 = mid; else h2 = mid - 1u;
+                    }
+                    s_thr = __uint_as_float(l2);
+                }
+            }
+            if (tid == 0) {
+                st->tau_key = tau;
+                st->s_thr = s_thr;
+                // exact s >= S_true (1 - gamma_{W+2}) - W 2^-126  =>  S_true <= thr_fast (rounded up)
+                const double widen = 1.0 + 2.0 * (double)(W + 8) * 5.9604644775390625e-8;
+                st->thr_fast = (s_thr < __int_as_float(0x7f800000))
+                                   ? __double2float_ru((double)s_thr * widen + 1e-30)
+                                   : s_thr;
+                st->count = k;
+                st->ccount = 0;
+                st->cur = cur ^ 1u;
+            }
+        }
+    } else {
+        if (tid == 0) { st->count = M; st->ccount = 0; }
+    }
+    if (!final_sort) return;
+    // fused finalisation (k <= SEL_LIST): order the surviving keys, decode (r, t)
+    __syncthreads();
+    unsigned int np2 = 1; while (np2 < k) np2 <<= 1;
+    for (unsigned int i = tid; i < np2; i += SEL_THREADS) list[i] = i < nkept ? kept[i] : ~0ull;
+    bitonic_sort_cta(list, np2);
+    for (unsigned int i = tid; i < k; i += SEL_THREADS) {
+        const unsigned long long key = list[i];
+        const unsigned int flat = (unsigned int)key;
+        out_d[(size_t)blockIdx.x * k + i] = __uint_as_float((unsigned int)(key >> 32));
+        out_idx[((size_t)blockIdx.x * k + i) * 2 + 0] = (int)(flat / Tp) + row_offset;
+        out_idx[((size_t)blockIdx.x * k + i) * 2 + 1] = (int)(flat % Tp);
+    }
 }
 
 // final ordering of a query's k keys and decoding into (distance, [trajectory, offset])
@@ -1356,13 +1471,14 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
                           const FftAux *aux, int mode, bool safe, float *d_out_dist, int *d_out_idx,
                           cudaStream_t stream) {
     (void)H;
-    qprep_kernel<<<(nq + 127) / 128, 128, 0, stream>>>(d_q, W, nq, st);
+    qprep_kernel<<<(nq + 3) / 4, 128, 0, stream>>>(d_q, W, nq, st);
     PSH_LAUNCHED();
 
     const bool use_fft = (mode == PSH_MODE_FFT) && !safe && aux != nullptr;
     const bool filter = (mode == PSH_MODE_FILTER || (mode == PSH_MODE_FFT && !use_fft)) && !safe;
     if (use_fft) {
-        qfft_kernel<<<nq, fftx::THREADS, (size_t)W * sizeof(double), stream>>>(d_q, W, aux->tw64, qspec, st);
+        qfft_kernel<<<dim3(fftx::N / fftx::THREADS, nq), fftx::THREADS, (size_t)W * sizeof(double), stream>>>(
+            d_q, W, aux->tw64, qspec, st);
         PSH_LAUNCHED();
     }
     ScanParams p;
@@ -1422,6 +1538,7 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
     // chunk schedule over permuted slots (rows, or row pairs in the fft flavour): seed chunk
     // (always exact), then geometric growth; in safe mode every chunk fits the candidate buffer
     // even if all of its windows are appended
+    const bool fuse_final = k <= SEL_LIST;                  // last select also sorts and decodes
     const long long unit = use_fft ? 2 : 1;                 // rows per slot
     const long long nslots = use_fft ? p.npairs : R;
     long long done = 0;
@@ -1475,11 +1592,14 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
         }
         {
             ProfScope ps(stream, 1);
-            select_kernel<<<nq, SEL_THREADS, 0, stream>>>(st, keys, pl.cap, (unsigned int)k, W);
+            const int fin = (fuse_final && next == nslots) ? 1 : 0;
+            select_kernel<<<nq, SEL_THREADS, 0, stream>>>(st, keys, pl.cap, (unsigned int)k, W, fin,
+                                                          (unsigned int)pl.Tp, row_offset, d_out_dist, d_out_idx);
         }
         PSH_LAUNCHED();
         done = next;
     }
+    if (fuse_final) return PSH_OK;
     unsigned int npow2 = 1; while (npow2 < (unsigned int)k) npow2 <<= 1;
     int use_smem = npow2 <= SORT_SMEM_MAX ? 1 : 0;
     size_t fsmem = use_smem ? (size_t)npow2 * sizeof(unsigned long long) : 0;
