@@ -478,7 +478,8 @@ inline bool fft_aux_layout(long long R, long long T, int W, int H, unsigned char
     if (R <= 0 || T <= 0 || T > fftx::N || W <= 0 || H < 0 || T - W - H + 1 <= 0) return false;
     const long long Tp = T - W - H + 1;
     a.npairs = (R + 1) / 2;
-    a.y2_stride = (int)((Tp + 3) / 4 * 4);
+    (void)Tp;
+    a.y2_stride = fftx::N;  // padded with +inf beyond T' so the scan epilogue needs no range checks
     size_t off = 0;
     a.tw32 = reinterpret_cast<float2 *>(base + off); off += sizeof(float2) * fftx::N;
     a.tw64 = reinterpret_cast<double2 *>(base + off); off += sizeof(double2) * fftx::N;
@@ -570,7 +571,8 @@ __global__ void __launch_bounds__(fftx::THREADS) fft_prep_y2_kernel(const float 
     for (int i = 0; i < 16; ++i) pfx[16 * tid + i + 1] = off + loc[i];
     __syncthreads();
     float *o = a.Y2 + (size_t)blockIdx.x * a.y2_stride;
-    for (int t = tid; t < a.y2_stride; t += fftx::THREADS) o[t] = t < Tp ? (float)(pfx[t + W] - pfx[t]) : 0.0f;
+    for (int t = tid; t < a.y2_stride; t += fftx::THREADS)
+        o[t] = t < Tp ? (float)(pfx[t + W] - pfx[t]) : __int_as_float(0x7f800000);
 }
 
 // conj(FFT_4096(q padded))/4096 per query (direct fp64 DFT on the exact twiddle table) and
@@ -675,6 +677,8 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
 #pragma unroll
         for (int i = 0; i < 16; ++i) qreg[i] = __ldg(p.Qc + tid + 256 * i);
     }
+    // thresholds only move between launches
+    const float q2_0 = p.st[0].q2, qmax_0 = p.st[0].qmax, thr_0 = ld_volatile_f32(&p.st[0].thr_fast);
     uint32_t phZ = 0, phY = 0;
     for (; slot < p.i1; slot += gridDim.x) {
         const long long nslot = slot + gridDim.x;
@@ -683,7 +687,6 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
         const bool has_b = rb < p.R;
         const float yn = p.ynorm[pair];
         mbar_wait(barZ, phZ); phZ ^= 1;
-        mbar_wait(barY, phY); phY ^= 1;  // (landed long ago except for the very first pair)
         for (int b = 0; b < p.nq; ++b) {
             float2 v[16];
             if (SINGLEQ) {
@@ -699,21 +702,22 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
                 if (tid == 0 && npair >= 0) issue_z(npair);
             }
             fftx::fft4096<1>(v, ex, p.tw, tid);
-            const float q2 = p.st[b].q2, qmax = p.st[b].qmax;
-            const float thr = ld_volatile_f32(&p.st[b].thr_fast);
+            if (b == 0) { mbar_wait(barY, phY); phY ^= 1; }  // the pair's window energies have landed
+            const float q2 = SINGLEQ ? q2_0 : p.st[b].q2, qmax = SINGLEQ ? qmax_0 : p.st[b].qmax;
+            const float thr = SINGLEQ ? thr_0 : ld_volatile_f32(&p.st[b].thr_fast);
             const float slack = (2.0f * p.cf_u * qmax * yn + 4.76837158203125e-7f * (q2 + yn * yn)) * 1.0001f;
             const float base = (q2 - slack) - thr;
             unsigned int mask = 0;
+            // rows are padded to 4096 entries with +inf: windows t >= T' can never pass
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
                 const int t = tid + 256 * c;
-                if (t < p.Tp) {
-                    const float va = fmaf(-2.0f, v[c].x, Y2s[t]) + base;
-                    if (!(va > 0.0f)) mask |= 1u << c;
-                    const float vb = fmaf(-2.0f, v[c].y, Y2s[p.y2_stride + t]) + base;
-                    if (has_b && !(vb > 0.0f)) mask |= 1u << (16 + c);
-                }
+                const float va = fmaf(-2.0f, v[c].x, Y2s[t]) + base;
+                if (!(va > 0.0f)) mask |= 1u << c;
+                const float vb = fmaf(-2.0f, v[c].y, Y2s[fftx::N + t]) + base;
+                if (!(vb > 0.0f)) mask |= 1u << (16 + c);
             }
+            if (!has_b) mask &= 0xffffu;
             if (__any_sync(FULL, mask != 0)) {
                 const int cnt = __popc(mask);
                 int incl = cnt;
@@ -1311,7 +1315,7 @@ struct Plan {
 };
 
 constexpr int SEED_FACTOR = 16;  // seeding chunk holds ~16 k windows
-constexpr int GROWTH = 16;       // each later chunk multiplies the scanned prefix by this
+constexpr int GROWTH = 20;       // each later chunk multiplies the scanned prefix by at most this
 constexpr int CAP_SLACK = 4;     // candidate buffer: 4x the expected appends of a chunk
 
 bool make_plan(long long R, long long T, int B, int W, int H, long long k, Plan &pl) {
@@ -1545,13 +1549,23 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
     long long safe_slots = ((long long)pl.cap - k) / (pl.Tp * unit);
     if (safe_slots < 1) safe_slots = 1;
     const long long seed_slots = (pl.n0 + unit - 1) / unit;
+    // evenly geometric rounds after the seed: ratio = (nslots/seed)^(1/rounds) <= growth
+    double ratio = (double)pl.growth;
+    if (nslots > seed_slots) {
+        const double span = (double)nslots / (double)seed_slots;
+        const int rounds = (int)ceil(log(span) / log((double)pl.growth) - 1e-9);
+        ratio = pow(span, 1.0 / (double)(rounds > 0 ? rounds : 1)) * (1.0 + 1e-9);
+    }
     while (done < nslots) {
         long long next;
         if (safe) next = done + safe_slots;
-        else next = done == 0 ? seed_slots : done * pl.growth;
+        else next = done == 0 ? seed_slots : (long long)ceil((double)done * ratio);
+        if (next <= done) next = done + 1;
         if (next > nslots) next = nslots;
         const bool first = done == 0;
-        if (use_fft && !first) {
+        // small rounds are cheaper on the exact kernel (no re-rank, fills the GPU with fewer rows)
+        const bool exact_round = first || safe || (!use_fft && !filter) || (use_fft && (next - done) < 64);
+        if (use_fft && !exact_round) {
             fp.i0 = done; fp.i1 = next;
             long long ctas = next - done;
             const long long max_ctas = (long long)sm_count() * 2;
@@ -1564,7 +1578,7 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
             PSH_LAUNCHED();
         } else {
             p.i0 = done * unit; p.i1 = next * unit;
-            const bool use_filter = filter && !first;
+            const bool use_filter = filter && !exact_round;
             long long ntasks = (p.i1 - p.i0) * p.nseg;  // < 2^32: nseg <= Tp and R*Tp < 2^32
             p.ntasks = (unsigned int)ntasks;
             long long ctas = (ntasks + SCAN_WARPS - 1) / SCAN_WARPS;
@@ -1579,7 +1593,7 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
             }
             PSH_LAUNCHED();
         }
-        if (!first && (use_fft || filter)) {
+        if (!exact_round) {
             unsigned int rb = (pl.cap + RR_THREADS - 1) / RR_THREADS;
             unsigned int rb_max = (unsigned int)sm_count() * 2u;
             if (rb > rb_max) rb = rb_max;
