@@ -95,6 +95,10 @@ int psh_debug_fft4096(const void *d_in, void *d_out, int n, int dir, const void 
  */
 int psh_merge_topk(const float *d_dist_parts, const int32_t *d_idx_parts, int G, int B,
                    int64_t k, int64_t Tp, float *d_out_dist, int32_t *d_out_idx, void *stream);
+/* Same merge on packed records (G, B, k, 3) int32 = [distance bits, trajectory, offset]: the
+ * layout one ncclAllGather of the per-rank results produces. */
+int psh_merge_topk_packed(const int32_t *d_rec_parts, int G, int B, int64_t k, int64_t Tp,
+                          float *d_out_dist, int32_t *d_out_idx, void *stream);
 
 /*
  * Gather the winning paths with their out-context: replaces path_shadowing.py:210-216.

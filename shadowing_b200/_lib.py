@@ -53,6 +53,8 @@ def lib() -> ctypes.CDLL:
         L.psh_debug_fft4096.argtypes = [vp, vp, ci, ci, vp, vp]
         L.psh_merge_topk.restype = ci
         L.psh_merge_topk.argtypes = [vp, vp, ci, ci, i64, i64, vp, vp, vp]
+        L.psh_merge_topk_packed.restype = ci
+        L.psh_merge_topk_packed.argtypes = [vp, ci, ci, i64, i64, vp, vp, vp]
         L.psh_gather_paths.restype = ci
         L.psh_gather_paths.argtypes = [vp, i64, i64, i64, vp, i64, i32, ci, vp, vp]
         L.psh_rv_aggregate.restype = ci
@@ -141,6 +143,20 @@ def merge_topk(dist_parts: torch.Tensor, idx_parts: torch.Tensor, Tp: int):
         rc = L.psh_merge_topk(dist_parts.data_ptr(), idx_parts.data_ptr(), G, B, k, Tp, dist.data_ptr(),
                               idx.data_ptr(), _stream(dist_parts))
     _check(rc, "psh_merge_topk")
+    return dist, idx
+
+
+def merge_topk_packed(rec_parts: torch.Tensor, Tp: int):
+    """(G,B,k,3) i32 [distance bits, r, t] -> merged (B,k) f32, (B,k,2) i32."""
+    L = lib()
+    G, B, k, _ = rec_parts.shape
+    rec_parts = rec_parts.contiguous()
+    dist = torch.empty((B, k), dtype=torch.float32, device=rec_parts.device)
+    idx = torch.empty((B, k, 2), dtype=torch.int32, device=rec_parts.device)
+    with torch.cuda.device(rec_parts.device):
+        rc = L.psh_merge_topk_packed(rec_parts.data_ptr(), G, B, k, Tp, dist.data_ptr(), idx.data_ptr(),
+                                     _stream(rec_parts))
+    _check(rc, "psh_merge_topk_packed")
     return dist, idx
 
 

@@ -499,8 +499,10 @@ __global__ void __launch_bounds__(fftx::THREADS) fft_debug_kernel(const float2 *
     float2 v[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = x[tid + 256 * i];
-    if (dir > 0) fftx::fft4096<1>(v, ex, tw, tid);
-    else fftx::fft4096<-1>(v, ex, tw, tid);
+    const fftx::TwSeeds seeds = fftx::load_seeds(tw, tid);
+    if (dir > 0) fftx::fft4096<1, true>(v, ex, tw, tid, seeds);
+    else if (dir < -1) fftx::fft4096<1, false>(v, ex, tw, tid, seeds);   // dir = -2 / +2: seed-twiddle flavour
+    else fftx::fft4096<-1, true>(v, ex, tw, tid, seeds);
     float2 *y = out + (size_t)blockIdx.x * fftx::N;
 #pragma unroll
     for (int c = 0; c < 16; ++c) y[tid + 256 * c] = v[c];
@@ -529,7 +531,7 @@ __global__ void __launch_bounds__(fftx::THREADS) fft_prep_spectra_kernel(const f
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(FULL, e, o);
     if ((tid & 31) == 0) red[tid >> 5] = e;
-    fftx::fft4096<-1>(v, ex, a.tw32, tid);  // (its barriers also order the writes to red)
+    fftx::fft4096<-1, true>(v, ex, a.tw32, tid, fftx::load_seeds(a.tw32, tid));  // (its barriers also order the writes to red)
     float2 *z = a.Z + (size_t)pair * fftx::N;
 #pragma unroll
     for (int c = 0; c < 16; ++c) z[tid + 256 * c] = v[c];
@@ -677,6 +679,7 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
 #pragma unroll
         for (int i = 0; i < 16; ++i) qreg[i] = __ldg(p.Qc + tid + 256 * i);
     }
+    const fftx::TwSeeds seeds = fftx::load_seeds(p.tw, tid);
     // thresholds only move between launches
     const float q2_0 = p.st[0].q2, qmax_0 = p.st[0].qmax, thr_0 = ld_volatile_f32(&p.st[0].thr_fast);
     uint32_t phZ = 0, phY = 0;
@@ -701,7 +704,7 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
                 __syncthreads();  // every thread has taken its part of the spectrum
                 if (tid == 0 && npair >= 0) issue_z(npair);
             }
-            fftx::fft4096<1>(v, ex, p.tw, tid);
+            fftx::fft4096<1, false>(v, ex, p.tw, tid, seeds);
             if (b == 0) { mbar_wait(barY, phY); phY ^= 1; }  // the pair's window energies have landed
             const float q2 = SINGLEQ ? q2_0 : p.st[b].q2, qmax = SINGLEQ ? qmax_0 : p.st[b].qmax;
             const float thr = SINGLEQ ? thr_0 : ld_volatile_f32(&p.st[b].thr_fast);
@@ -1133,7 +1136,10 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const QState *st_
 // sort key is (dbits << 32 | slot) with slot = g*k+i and ties in distance are re-ordered by the
 // global flat index in a final pass over equal-distance runs.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SEL_THREADS) merge_kernel(const float *d_parts, const int *i_parts, int G, int B,
+// Record j of shard g, query b: distance at d_parts[rec * dstride], indices at i_parts[rec * istride + {0,1}],
+// rec = (g*B + b)*k + j  (separate arrays: dstride 1, istride 2; packed [dbits, r, t] records: 3, 3).
+__global__ void __launch_bounds__(SEL_THREADS) merge_kernel(const float *d_parts, const int *i_parts, int dstride,
+                                                             int istride, int G, int B,
                                                              unsigned int k, unsigned long long Tp, unsigned int npow2,
                                                              unsigned long long *scratch, int use_smem,
                                                              float *out_d, int *out_idx) {
@@ -1146,7 +1152,7 @@ __global__ void __launch_bounds__(SEL_THREADS) merge_kernel(const float *d_parts
         unsigned long long key = ~0ull;
         if (i < n) {
             unsigned int g = i / k, j = i - g * k;
-            float d = d_parts[((size_t)g * B + b) * k + j];
+            float d = d_parts[(((size_t)g * B + b) * k + j) * dstride];
             key = ((unsigned long long)__float_as_uint(d) << 32) | i;
         }
         a[i] = key;
@@ -1166,13 +1172,13 @@ __global__ void __launch_bounds__(SEL_THREADS) merge_kernel(const float *d_parts
             for (unsigned int c = lo; c <= hi; ++c) {
                 unsigned int sc = (unsigned int)a[c];
                 unsigned int gc = sc / k, jc = sc - gc * k;
-                const int *ic = i_parts + (((size_t)gc * B + b) * k + jc) * 2;
+                const int *ic = i_parts + (((size_t)gc * B + b) * k + jc) * istride;
                 unsigned long long fc = (unsigned long long)ic[0] * Tp + (unsigned long long)ic[1];
                 unsigned int rank = 0;
                 for (unsigned int e = lo; e <= hi; ++e) {
                     unsigned int se = (unsigned int)a[e];
                     unsigned int ge = se / k, je = se - ge * k;
-                    const int *ie = i_parts + (((size_t)ge * B + b) * k + je) * 2;
+                    const int *ie = i_parts + (((size_t)ge * B + b) * k + je) * istride;
                     unsigned long long fe = (unsigned long long)ie[0] * Tp + (unsigned long long)ie[1];
                     rank += (fe < fc) ? 1u : 0u;
                 }
@@ -1180,7 +1186,7 @@ __global__ void __launch_bounds__(SEL_THREADS) merge_kernel(const float *d_parts
             }
         }
         unsigned int g = slot / k, j = slot - g * k;
-        const int *src = i_parts + (((size_t)g * B + b) * k + j) * 2;
+        const int *src = i_parts + (((size_t)g * B + b) * k + j) * istride;
         out_d[(size_t)b * k + i] = __uint_as_float(db);
         out_idx[((size_t)b * k + i) * 2 + 0] = src[0];
         out_idx[((size_t)b * k + i) * 2 + 1] = src[1];
@@ -1687,11 +1693,9 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
     return PSH_OK;
 }
 
-int psh_merge_topk(const float *d_dist_parts, const int32_t *d_idx_parts, int G, int B,
-                   int64_t k, int64_t Tp, float *d_out_dist, int32_t *d_out_idx, void *stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    if (!d_dist_parts || !d_idx_parts || !d_out_dist || !d_out_idx || G <= 0 || B <= 0 || k <= 0 || Tp <= 0)
-        return PSH_E_ARG;
+static int merge_impl(const float *d_parts, const int *i_parts, int dstride, int istride, int G, int B, int64_t k,
+                      int64_t Tp, float *d_out_dist, int32_t *d_out_idx, cudaStream_t stream) {
+    if (!d_parts || !i_parts || !d_out_dist || !d_out_idx || G <= 0 || B <= 0 || k <= 0 || Tp <= 0) return PSH_E_ARG;
     unsigned long long n = (unsigned long long)G * (unsigned long long)k;
     if (n > 0x7fffffffull) return PSH_E_TOO_LARGE;
     unsigned int npow2 = 1; while (npow2 < n) npow2 <<= 1;
@@ -1701,12 +1705,24 @@ int psh_merge_topk(const float *d_dist_parts, const int32_t *d_idx_parts, int G,
     if (!use_smem) PSH_CUDA(cudaMallocAsync(&scratch, (size_t)B * npow2 * sizeof(unsigned long long), stream));
     if (smem > 48 * 1024)
         PSH_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    merge_kernel<<<B, SEL_THREADS, smem, stream>>>(d_dist_parts, d_idx_parts, G, B, (unsigned int)k,
+    merge_kernel<<<B, SEL_THREADS, smem, stream>>>(d_parts, i_parts, dstride, istride, G, B, (unsigned int)k,
                                                    (unsigned long long)Tp, npow2, scratch, use_smem, d_out_dist,
                                                    d_out_idx);
     PSH_LAUNCHED();
     if (scratch) PSH_CUDA(cudaFreeAsync(scratch, stream));
     return PSH_OK;
+}
+
+int psh_merge_topk(const float *d_dist_parts, const int32_t *d_idx_parts, int G, int B,
+                   int64_t k, int64_t Tp, float *d_out_dist, int32_t *d_out_idx, void *stream_) {
+    return merge_impl(d_dist_parts, d_idx_parts, 1, 2, G, B, k, Tp, d_out_dist, d_out_idx, (cudaStream_t)stream_);
+}
+
+int psh_merge_topk_packed(const int32_t *d_rec_parts, int G, int B, int64_t k, int64_t Tp,
+                          float *d_out_dist, int32_t *d_out_idx, void *stream_) {
+    if (!d_rec_parts) return PSH_E_ARG;
+    return merge_impl(reinterpret_cast<const float *>(d_rec_parts), d_rec_parts + 1, 3, 3, G, B, k, Tp, d_out_dist,
+                      d_out_idx, (cudaStream_t)stream_);
 }
 
 int psh_gather_paths(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride,

@@ -78,14 +78,57 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = w[i];
 }
 
+// powers w^1 .. w^15 of a unit complex number from w^1 and w^4 (both table-exact): every power
+// is a product of at most three table values, so its error stays below ~17 u (a table value: u)
+__device__ __forceinline__ void unit_powers(float2 w1, float2 w4, float2 (&w)[16]) {
+    w[1] = w1;
+    w[2] = cmul(w1, w1);
+    w[3] = cmul(w[2], w1);
+    w[4] = w4;
+    w[5] = cmul(w4, w1);
+    w[6] = cmul(w4, w[2]);
+    w[7] = cmul(w4, w[3]);
+    w[8] = cmul(w4, w4);
+    w[9] = cmul(w[8], w1);
+    w[10] = cmul(w[8], w[2]);
+    w[11] = cmul(w[8], w[3]);
+    w[12] = cmul(w[8], w4);
+    w[13] = cmul(w[12], w1);
+    w[14] = cmul(w[12], w[2]);
+    w[15] = cmul(w[12], w[3]);
+}
+
+// loop-invariant twiddle seeds of a thread: pass A uses powers of exp(2 pi i tid/4096), pass B
+// powers of exp(2 pi i (tid&15)/256)
+struct TwSeeds { float2 a1, a4, b1, b4; };
+__device__ __forceinline__ TwSeeds load_seeds(const float2 *__restrict__ tw, int tid) {
+    TwSeeds s;
+    const int t1 = tid & 15;
+    s.a1 = __ldg(tw + tid);
+    s.a4 = __ldg(tw + 4 * tid);
+    s.b1 = __ldg(tw + 16 * t1);
+    s.b4 = __ldg(tw + 64 * t1);
+    return s;
+}
+
 // 4096-point transform by one CTA of 256 threads.  In: v[i] = x[tid + 256 i].  Out: v[c] =
 // X[tid + 256 c].  tw[m] = exp(+2 pi i m / 4096).  `ex` is EX_FLOAT2 float2 of shared memory;
 // the caller must __syncthreads() before ex is touched again.
-template <int DIR>
-__device__ __forceinline__ void fft4096(float2 (&v)[16], float2 *ex, const float2 *__restrict__ tw, int tid) {
+// TABLE = true : every inter-pass twiddle is read from the table (accuracy: dataset spectra)
+// TABLE = false: twiddles are rebuilt from four register-resident seeds (no loads in the loop)
+template <int DIR, bool TABLE>
+__device__ __forceinline__ void fft4096(float2 (&v)[16], float2 *ex, const float2 *__restrict__ tw, int tid,
+                                        const TwSeeds &seeds) {
     fft16<DIR>(v);  // over i -> a
+    if (TABLE) {
 #pragma unroll
-    for (int a = 1; a < 16; ++a) v[a] = cmul_dir<DIR>(v[a], __ldg(tw + a * tid));
+        for (int a = 1; a < 16; ++a) v[a] = cmul_dir<DIR>(v[a], __ldg(tw + a * tid));
+    } else {
+        float2 w[16];
+        unit_powers(seeds.a1, seeds.a4, w);
+#pragma unroll
+        for (int a = 1; a < 16; ++a) v[a] = cmul_dir<DIR>(v[a], w[a]);
+    }
 #pragma unroll
     for (int a = 0; a < 16; ++a) ex[a * EX_STRIDE + tid] = v[a];
     __syncthreads();
@@ -93,8 +136,15 @@ __device__ __forceinline__ void fft4096(float2 (&v)[16], float2 *ex, const float
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = ex[a2 * EX_STRIDE + t1 + 16 * i];
     fft16<DIR>(v);  // over tau2 -> b
+    if (TABLE) {
 #pragma unroll
-    for (int b = 1; b < 16; ++b) v[b] = cmul_dir<DIR>(v[b], __ldg(tw + 16 * b * t1));
+        for (int b = 1; b < 16; ++b) v[b] = cmul_dir<DIR>(v[b], __ldg(tw + 16 * b * t1));
+    } else {
+        float2 w[16];
+        unit_powers(seeds.b1, seeds.b4, w);
+#pragma unroll
+        for (int b = 1; b < 16; ++b) v[b] = cmul_dir<DIR>(v[b], w[b]);
+    }
     __syncthreads();
 #pragma unroll
     for (int b = 0; b < 16; ++b) ex[a2 * EX_STRIDE + b * 16 + t1] = v[b];

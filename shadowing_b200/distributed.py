@@ -35,27 +35,34 @@ def sharded_scan(ps, rows: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int
     if Tp <= 0:
         raise RuntimeError(f"context ({W}) + horizon ({H}) longer than the trajectories ({T})")
     n_local = rows.shape[0] * Tp
-    tot = torch.tensor([n_local], dtype=torch.int64, device=rows.device)
-    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=pg)
-    if k > int(tot.item()):
-        raise RuntimeError(f"selected index k out of range: k={k} > {int(tot.item())} windows")
+    # total number of windows over all ranks: one collective per (shard, W, H), then cached
+    key = (rows.data_ptr(), rows.shape[0], Tp)
+    cache = getattr(ps, "_total_windows", None)
+    if cache is None or cache[0] != key:
+        tot = torch.tensor([n_local], dtype=torch.int64, device=rows.device)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=pg)
+        cache = (key, int(tot.item()))
+        ps._total_windows = cache
+    if k > cache[1]:
+        raise RuntimeError(f"selected index k out of range: k={k} > {cache[1]} windows")
     k_loc = min(k, n_local)
-    d_loc = torch.full((B, k), _INF, dtype=torch.float32, device=rows.device)
-    i_loc = torch.empty((B, k, 2), dtype=torch.int32, device=rows.device)
-    i_loc[..., 0] = _PAD_ROW
-    i_loc[..., 1] = 0
+    # packed records [distance bits, trajectory, offset]: ONE collective carries everything
+    rec = torch.empty((B, k, 3), dtype=torch.int32, device=rows.device)
+    if k_loc < k:  # a shard with fewer than k windows pads with +inf records that sort last
+        rec[..., 0] = 0x7F800000
+        rec[..., 1] = _PAD_ROW
+        rec[..., 2] = 0
     if k_loc > 0:
         mode, aux = ps._mode_and_aux(rows, T, W, H)
         d, i, ps._workspace = _lib.scan_topk(rows, T, q, H, k_loc, ps._row_offset, mode, ps._workspace, aux)
-        d_loc[:, :k_loc] = d
-        i_loc[:, :k_loc] = i
-    d_all = torch.empty((world, B, k), dtype=torch.float32, device=rows.device)
-    i_all = torch.empty((world, B, k, 2), dtype=torch.int32, device=rows.device)
-    # all_gather on views of one buffer: NCCL coalesces it into a single ncclAllGather; gloo
-    # (CPU tests) has no all_gather_into_tensor
-    dist.all_gather(list(d_all.unbind(0)), d_loc, group=pg)
-    dist.all_gather(list(i_all.unbind(0)), i_loc, group=pg)
-    return _lib.merge_topk(d_all, i_all, Tp)
+        rec[:, :k_loc, 0] = d.view(torch.int32)
+        rec[:, :k_loc, 1:] = i
+    rec_all = torch.empty((world, B, k, 3), dtype=torch.int32, device=rows.device)
+    if rows.is_cuda:
+        dist.all_gather_into_tensor(rec_all, rec, group=pg)          # one ncclAllGather, B*k*12 bytes per rank
+        return _lib.merge_topk_packed(rec_all, Tp)
+    dist.all_gather(list(rec_all.unbind(0)), rec, group=pg)          # gloo (CPU tests) has no *_into_tensor
+    return _lib.merge_topk(rec_all[..., 0].contiguous().view(torch.float32), rec_all[..., 1:].contiguous(), Tp)
 
 
 def sharded_gather(ps, rows: torch.Tensor, T: int, idx: torch.Tensor, L: int) -> torch.Tensor:

@@ -250,7 +250,14 @@ class PathShadowing:
         """
         del n_splits, cuda
         dist, paths, idx = self.shadow_device(x_context, k)
-        return _numpy(dist), _numpy(paths), _numpy(idx)
+        if not dist.is_cuda:
+            return _numpy(dist), _numpy(paths), _numpy(idx)
+        # async copies into pinned staging (torch's caching host allocator), one sync
+        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (dist, paths, idx)]
+        for h, t in zip(host, (dist, paths, idx)):
+            h.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(dist.device).synchronize()
+        return host[0].numpy(), host[1].numpy(), host[2].numpy()
 
     # ------------------------------------------------------------------ aggregation
     @staticmethod

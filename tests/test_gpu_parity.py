@@ -87,18 +87,21 @@ def test_fft4096_matches_numpy_and_error_budget():
     aux = _lib.fft_prepare(rows, 4096, 252, 20)
     z = (rng.standard_normal((5, 4096)) + 1j * rng.standard_normal((5, 4096))).astype(np.complex64)
     zd = torch.tensor(z).cuda()
+    # direction -1: forward, table twiddles (dataset spectra); +1: inverse, table twiddles;
+    # -2: inverse with twiddles rebuilt from register-resident seeds (the scan's flavour)
     for direction, ref in ((-1, np.fft.fft(z.astype(np.complex128), axis=1)),
-                           (1, np.fft.ifft(z.astype(np.complex128), axis=1) * 4096)):
+                           (1, np.fft.ifft(z.astype(np.complex128), axis=1) * 4096),
+                           (-2, np.fft.ifft(z.astype(np.complex128), axis=1) * 4096)):
         out = _lib.debug_fft4096(zd, direction, aux).cpu().numpy()
         err = np.linalg.norm(out - ref, axis=1) / np.linalg.norm(ref, axis=1)
-        assert err.max() < 40 * 2.0 ** -24, err      # theory: ~80 u worst case, ~3 u typical
+        assert err.max() < 40 * 2.0 ** -24, (direction, err)   # theory: ~80-120 u worst case, few u typical
     # full pipeline: forward (library), pointwise conj(Q)/N, inverse (library) vs fp64 correlation
     q = (rng.standard_normal(252) * 0.01).astype(np.float32)
     pair = (ds[0] + 1j * ds[1]).astype(np.complex64)[None]
     Z = _lib.debug_fft4096(torch.tensor(pair).cuda(), -1, aux)
     Q = np.fft.fft(np.pad(q.astype(np.float64), (0, 4096 - 252)))
     Qc = torch.tensor((np.conj(Q) / 4096).astype(np.complex64)).cuda()
-    c = _lib.debug_fft4096(Z * Qc[None], 1, aux).cpu().numpy()[0]
+    c = _lib.debug_fft4096(Z * Qc[None], -2, aux).cpu().numpy()[0]
     Tp = 4096 - 252 + 1
     ca = np.array([np.dot(q.astype(np.float64), ds[0, t:t + 252].astype(np.float64)) for t in range(Tp)])
     cb = np.array([np.dot(q.astype(np.float64), ds[1, t:t + 252].astype(np.float64)) for t in range(Tp)])
@@ -235,6 +238,10 @@ def test_merge_topk_equals_global():
     d, i = _lib.merge_topk(torch.stack(parts_d), torch.stack(parts_i), 700 - 30 - H + 1)
     do, io = oracle.shadow_topk(ds, q, k, H)
     assert_topk_equal(d.cpu().numpy(), i.cpu().numpy(), do, io)
+    # packed records [distance bits, r, t], the layout of the single all-gather
+    rec = torch.cat([torch.stack(parts_d).view(torch.int32).unsqueeze(-1), torch.stack(parts_i)], dim=-1)
+    d2, i2 = _lib.merge_topk_packed(rec, 700 - 30 - H + 1)
+    assert torch.equal(d, d2) and torch.equal(i, i2)
 
 
 def test_full_size_properties_cfg2():
