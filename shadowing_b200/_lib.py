@@ -107,7 +107,8 @@ def debug_fft4096(x: torch.Tensor, direction: int, aux: torch.Tensor) -> torch.T
 
 
 def scan_topk(ds: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int, row_offset: int = 0,
-              mode: int = PSH_MODE_FILTER, workspace: torch.Tensor | None = None, aux: torch.Tensor | None = None):
+              mode: int = PSH_MODE_FILTER, workspace: torch.Tensor | None = None, aux: torch.Tensor | None = None,
+              out: tuple[torch.Tensor, torch.Tensor] | None = None):
     """ds (R, row_stride) f32 cuda, q (B, W) f32 cuda -> (dist (B,k) f32, idx (B,k,2) i32) cuda."""
     L = lib()
     assert ds.is_cuda and q.is_cuda and ds.dtype == torch.float32 and q.dtype == torch.float32
@@ -120,8 +121,11 @@ def scan_topk(ds: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int, row_off
         need = 256
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty(need, dtype=torch.uint8, device=ds.device)
-    dist = torch.empty((B, k), dtype=torch.float32, device=ds.device)
-    idx = torch.empty((B, k, 2), dtype=torch.int32, device=ds.device)
+    if out is not None:
+        dist, idx = out
+    else:
+        dist = torch.empty((B, k), dtype=torch.float32, device=ds.device)
+        idx = torch.empty((B, k, 2), dtype=torch.int32, device=ds.device)
     with torch.cuda.device(ds.device):
         rc = L.psh_scan_topk_f32(ds.data_ptr(), R, T, row_stride, q.data_ptr(), B, W, H, k, row_offset, mode,
                                  dist.data_ptr(), idx.data_ptr(), workspace.data_ptr(), workspace.numel(),
@@ -160,12 +164,14 @@ def merge_topk_packed(rec_parts: torch.Tensor, Tp: int):
     return dist, idx
 
 
-def gather_paths(ds: torch.Tensor, T: int, idx: torch.Tensor, L_out: int, row_offset: int = 0) -> torch.Tensor:
+def gather_paths(ds: torch.Tensor, T: int, idx: torch.Tensor, L_out: int, row_offset: int = 0,
+                 out: torch.Tensor | None = None) -> torch.Tensor:
     """idx (B,k,2) i32 -> paths (B,k,1,L) f32 (rows outside this shard are zeros)."""
     L = lib()
     B, k, _ = idx.shape
     idx = idx.contiguous()
-    out = torch.empty((B, k, 1, L_out), dtype=torch.float32, device=ds.device)
+    if out is None:
+        out = torch.empty((B, k, 1, L_out), dtype=torch.float32, device=ds.device)
     with torch.cuda.device(ds.device):
         rc = L.psh_gather_paths(ds.data_ptr(), ds.shape[0], T, ds.stride(0), idx.data_ptr(), B * k, row_offset,
                                 L_out, out.data_ptr(), _stream(ds))

@@ -123,6 +123,7 @@ class PathShadowing:
         self._resident = None  # (key, device rows (R, row_stride), T)
         self._workspace = None
         self._fft_aux = None   # (key, aux buffer) for (resident rows, W, H)
+        self._staging = None   # pinned host buffers for the results of shadow()
 
     # ------------------------------------------------------------------ device residency
     def _dev(self) -> torch.device:
@@ -184,7 +185,7 @@ class PathShadowing:
         return _lib.PSH_MODE_FFT, self._fft_aux[1]
 
     # ------------------------------------------------------------------ scan
-    def _scan_device(self, x: torch.Tensor, rows: torch.Tensor, T: int, k: int):
+    def _scan_device(self, x: torch.Tensor, rows: torch.Tensor, T: int, k: int, out=None):
         """x (B, 1, W) -> device (dist (B,k), idx (B,k,2)); all-reduced across the process group
         when the ensemble is sharded."""
         self._check_plugins()
@@ -204,7 +205,7 @@ class PathShadowing:
                 raise RuntimeError(f"selected index k out of range: k={k} > {n_windows} windows")
             mode, aux = self._mode_and_aux(rows, T, W, H)
             dist, idx, self._workspace = _lib.scan_topk(rows, T, q, H, k, self._row_offset, mode,
-                                                        self._workspace, aux)
+                                                        self._workspace, aux, out)
             return dist, idx
         from .distributed import sharded_scan
         return sharded_scan(self, rows, T, q, H, k)
@@ -222,17 +223,23 @@ class PathShadowing:
         dist, idx = self._scan_device(_torch(_dim_array(x)), rows, T, k)
         return dist.cpu(), idx.cpu()
 
-    def shadow_device(self, x_context: ArrayType, k: int = 1):
+    def shadow_device(self, x_context: ArrayType, k: int = 1, _packed: torch.Tensor | None = None):
         """`shadow` without the device->host copy: (dist (B,k), paths (B,k,1,W+H), idx (B,k,2))
         as CUDA tensors (used by `predict` to keep the whole pipeline on the GPU)."""
         if self.embedding.kernel.shape[-1] != 0 and self.embedding.kernel.shape[-1] != x_context.shape[-1]:
             raise Exception("The embedding kernel should be of the same size as the context.")
         x = _torch(_dim_array(x_context))
         rows, T = self._resident_rows()
-        dist, idx = self._scan_device(x, rows, T, k)
         L = x.shape[-1] + self.context.get_out_times()
+        out = out_paths = None
+        if _packed is not None and self._pg is None:  # views of one device buffer: [dist | idx | paths]
+            B = x.shape[0]
+            nd, ni = B * k, B * k * 2
+            out = (_packed[:nd].view(torch.float32).view(B, k), _packed[nd:nd + ni].view(B, k, 2))
+            out_paths = _packed[nd + ni:nd + ni + B * k * L].view(torch.float32).view(B, k, 1, L)
+        dist, idx = self._scan_device(x, rows, T, k, out)
         if self._pg is None:
-            paths = _lib.gather_paths(rows, T, idx, L, self._row_offset)
+            paths = _lib.gather_paths(rows, T, idx, L, self._row_offset, out_paths)
         else:
             from .distributed import sharded_gather
             paths = sharded_gather(self, rows, T, idx, L)
@@ -249,15 +256,26 @@ class PathShadowing:
         :return: numpy (distances (B,k) f32 ascending, paths (B,k,C,W+H) f32, indices (B,k,2) i32)
         """
         del n_splits, cuda
-        dist, paths, idx = self.shadow_device(x_context, k)
-        if not dist.is_cuda:
+        if self._pg is not None or not torch.cuda.is_available():
+            dist, paths, idx = self.shadow_device(x_context, k)
             return _numpy(dist), _numpy(paths), _numpy(idx)
-        # async copies into pinned staging (torch's caching host allocator), one sync
-        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (dist, paths, idx)]
-        for h, t in zip(host, (dist, paths, idx)):
-            h.copy_(t, non_blocking=True)
-        torch.cuda.current_stream(dist.device).synchronize()
-        return host[0].numpy(), host[1].numpy(), host[2].numpy()
+        # results land in ONE device buffer [dist | idx | paths] (4-byte words) that is copied to
+        # persistent pinned staging with a single async copy + one sync
+        shp = _dim_array(x_context).shape
+        B, L = shp[0], shp[-1] + self.context.get_out_times()
+        words = B * k * (3 + L)
+        if self._staging is None or self._staging[0].numel() != words:
+            self._staging = (torch.empty(words, dtype=torch.int32, device=self._dev()),
+                             torch.empty(words, dtype=torch.int32, pin_memory=True))
+        dev_buf, host_buf = self._staging
+        self.shadow_device(x_context, k, _packed=dev_buf)
+        host_buf.copy_(dev_buf, non_blocking=True)
+        torch.cuda.current_stream(dev_buf.device).synchronize()
+        flat = host_buf.numpy().copy()
+        nd, ni = B * k, B * k * 2
+        return (flat[:nd].view(np.float32).reshape(B, k),
+                flat[nd + ni:].view(np.float32).reshape(B, k, 1, L),
+                flat[nd:nd + ni].reshape(B, k, 2))
 
     # ------------------------------------------------------------------ aggregation
     @staticmethod
