@@ -873,6 +873,7 @@ __device__ void bitonic_sort_cta(unsigned long long *a, unsigned int n) {
 // ------------------------------------------------------------------------------------------
 constexpr int SEL_BINS = 2048;
 constexpr int SEL_LIST = 4096;  // boundary-bin keys / fused final sort capacity (keys)
+constexpr int SEL_KPT = 24;     // keys per thread cached in registers (24 k keys per query)
 
 __device__ __forceinline__ void hist_add(unsigned int *hist, unsigned int digit, bool active) {
     // warp-aggregated shared-memory histogram increment
@@ -973,10 +974,25 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(QState *st_all, uns
     unsigned int nkept = M;
     if (M > k) {  // uniform branch
         for (int i = tid; i < SEL_BINS; i += SEL_THREADS) hist[i] = 0;
+        // the first SEL_KPT*1024 keys are read from global memory ONCE (independent loads, one
+        // latency) and kept in registers for all three passes; longer lists re-read the tail
+        unsigned long long kreg[SEL_KPT];
+#pragma unroll
+        for (int r = 0; r < SEL_KPT; ++r) {
+            const unsigned int i = tid + r * SEL_THREADS;
+            kreg[r] = i < M ? src[i] : ~0ull;
+        }
         __syncthreads();
         // pass 1: range of the distance bits
         unsigned int mn = 0xffffffffu, mx = 0u;
-        for (unsigned int i = tid; i < M; i += SEL_THREADS) {
+#pragma unroll
+        for (int r = 0; r < SEL_KPT; ++r) {
+            if (tid + r * SEL_THREADS < M) {
+                const unsigned int db = (unsigned int)(kreg[r] >> 32);
+                mn = min(mn, db); mx = max(mx, db);
+            }
+        }
+        for (unsigned int i = tid + SEL_KPT * SEL_THREADS; i < M; i += SEL_THREADS) {
             const unsigned int db = (unsigned int)(src[i] >> 32);
             mn = min(mn, db); mx = max(mx, db);
         }
@@ -993,7 +1009,10 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(QState *st_all, uns
         bool fast = range > 0;
         if (fast) {
             // pass 2: histogram
-            for (unsigned int i = tid; i < M; i += SEL_THREADS)
+#pragma unroll
+            for (int r = 0; r < SEL_KPT; ++r)
+                if (tid + r * SEL_THREADS < M) atomicAdd(&hist[((unsigned int)(kreg[r] >> 32) - lo) >> shift], 1u);
+            for (unsigned int i = tid + SEL_KPT * SEL_THREADS; i < M; i += SEL_THREADS)
                 atomicAdd(&hist[((unsigned int)(src[i] >> 32) - lo) >> shift], 1u);
             __syncthreads();
             if (tid < 32) {  // the bin holding the k-th key
@@ -1022,7 +1041,25 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(QState *st_all, uns
         if (fast) {
             // pass 3: keys below the boundary bin are kept, keys inside it go to the list
             const unsigned int kb = s_bin;
-            for (unsigned int i = tid; i < ((M + 31u) & ~31u); i += SEL_THREADS) {
+            const unsigned int Mr = (M + 31u) & ~31u;
+#pragma unroll
+            for (int r = 0; r < SEL_KPT; ++r) {
+                const unsigned int i = tid + r * SEL_THREADS;
+                if (i - lane < Mr) {  // warp-uniform
+                    const unsigned long long key = kreg[r];
+                    const unsigned int bin = i < M ? (((unsigned int)(key >> 32) - lo) >> shift) : 0xffffffffu;
+                    const bool keep = bin < kb;
+                    if (bin == kb) list[atomicAdd(&s_nlist, 1u)] = key;
+                    const unsigned int bal = __ballot_sync(FULL, keep);
+                    if (bal) {
+                        unsigned int base = 0;
+                        if (lane == 0) base = atomicAdd(&s_out, (unsigned int)__popc(bal));
+                        base = __shfl_sync(FULL, base, 0);
+                        if (keep) dst[base + __popc(bal & ((1u << lane) - 1u))] = key;
+                    }
+                }
+            }
+            for (unsigned int i = tid + SEL_KPT * SEL_THREADS; i < Mr; i += SEL_THREADS) {
                 unsigned long long key = 0;
                 unsigned int bin = 0xffffffffu;
                 if (i < M) { key = src[i]; bin = ((unsigned int)(key >> 32) - lo) >> shift; }
