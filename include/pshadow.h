@@ -59,7 +59,9 @@ size_t psh_scan_workspace_bytes(int64_t R, int64_t T, int B, int W, int H, int64
  *   k           neighbours kept per query
  *   row_offset  added to the returned trajectory index (rank's first global row when sharded)
  *   d_out_dist  (B, k) fp32, ascending
- *   d_out_idx   (B, k, 2) int32 [trajectory, offset]; ties ordered by (distance, r*T'+t)
+ *   d_out_idx   (B, k, 2) int32 [trajectory, offset]; ties ordered by (distance, r*T'+t).
+ *               NULL: d_out_dist receives packed (B, k, 3) int32 records [distance bits,
+ *               trajectory, offset] instead (the payload of the multi-GPU all-gather)
  *   d_ws        scratch of >= psh_scan_workspace_bytes(...) bytes, 256-byte aligned
  *   d_aux       PSH_MODE_FFT: buffer filled by psh_fft_prepare for this dataset/W/H, else NULL
  *

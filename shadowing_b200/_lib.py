@@ -81,6 +81,24 @@ def launch_count() -> int:
     return int(lib().psh_launch_count())
 
 
+def scan_topk_packed(ds: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int, row_offset: int, mode: int,
+                     workspace: torch.Tensor | None, aux: torch.Tensor | None, rec: torch.Tensor):
+    """Same scan, results as packed (B,k,3) int32 records [distance bits, r, t] written to `rec`."""
+    L = lib()
+    R, row_stride = ds.shape[0], ds.stride(0)
+    B, W = q.shape
+    need = L.psh_scan_workspace_bytes(R, T, B, W, H, k) or 256
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=ds.device)
+    with torch.cuda.device(ds.device):
+        rc = L.psh_scan_topk_f32(ds.data_ptr(), R, T, row_stride, q.data_ptr(), B, W, H, k, row_offset, mode,
+                                 rec.data_ptr(), None, workspace.data_ptr(), workspace.numel(),
+                                 aux.data_ptr() if aux is not None else None, aux.numel() if aux is not None else 0,
+                                 _stream(ds))
+    _check(rc, "psh_scan_topk_f32")
+    return workspace
+
+
 def fft_prepare(ds: torch.Tensor, T: int, W: int, H: int) -> torch.Tensor:
     """Dataset-side precomputation for PSH_MODE_FFT: spectra of row pairs, window energies, norms."""
     L = lib()

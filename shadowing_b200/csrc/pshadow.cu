@@ -871,6 +871,19 @@ __device__ void bitonic_sort_cta(unsigned long long *a, unsigned int n) {
 //   generic path: MSB-first radix select on the full 64-bit key (8-bit digits), used when the
 //                 fast path degenerates (all distances equal, or a huge tie group at the k-th)
 // ------------------------------------------------------------------------------------------
+// results: separate (B,k) distances + (B,k,2) indices, or -- when out_idx is NULL -- packed
+// (B,k,3) int32 records [distance bits, trajectory, offset] in out_d (the all-gather payload)
+__device__ __forceinline__ void write_result(float *out_d, int *out_idx, size_t pos, unsigned int dbits, int r, int t) {
+    if (out_idx != nullptr) {
+        out_d[pos] = __uint_as_float(dbits);
+        out_idx[pos * 2 + 0] = r;
+        out_idx[pos * 2 + 1] = t;
+    } else {
+        int *rec = reinterpret_cast<int *>(out_d) + pos * 3;
+        rec[0] = (int)dbits; rec[1] = r; rec[2] = t;
+    }
+}
+
 constexpr int SEL_BINS = 2048;
 constexpr int SEL_LIST = 4096;  // boundary-bin keys / fused final sort capacity (keys)
 constexpr int SEL_KPT = 24;     // keys per thread cached in registers (24 k keys per query)
@@ -1139,9 +1152,8 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(QState *st_all, uns
     for (unsigned int i = tid; i < k; i += SEL_THREADS) {
         const unsigned long long key = list[i];
         const unsigned int flat = (unsigned int)key;
-        out_d[(size_t)blockIdx.x * k + i] = __uint_as_float((unsigned int)(key >> 32));
-        out_idx[((size_t)blockIdx.x * k + i) * 2 + 0] = (int)(flat / Tp) + row_offset;
-        out_idx[((size_t)blockIdx.x * k + i) * 2 + 1] = (int)(flat % Tp);
+        write_result(out_d, out_idx, (size_t)blockIdx.x * k + i, (unsigned int)(key >> 32),
+                     (int)(flat / Tp) + row_offset, (int)(flat % Tp));
     }
 }
 
@@ -1161,9 +1173,8 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const QState *st_
     for (unsigned int i = threadIdx.x; i < k; i += blockDim.x) {
         unsigned long long key = a[i];
         unsigned int flat = (unsigned int)key;
-        out_d[(size_t)blockIdx.x * k + i] = __uint_as_float((unsigned int)(key >> 32));
-        out_idx[((size_t)blockIdx.x * k + i) * 2 + 0] = (int)(flat / Tp) + row_offset;
-        out_idx[((size_t)blockIdx.x * k + i) * 2 + 1] = (int)(flat % Tp);
+        write_result(out_d, out_idx, (size_t)blockIdx.x * k + i, (unsigned int)(key >> 32),
+                     (int)(flat / Tp) + row_offset, (int)(flat % Tp));
     }
 }
 
@@ -1678,7 +1689,7 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
                       void *d_ws, size_t ws_bytes, const void *d_aux, size_t aux_bytes, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (mode != PSH_MODE_EXACT && mode != PSH_MODE_FILTER && mode != PSH_MODE_FFT) return PSH_E_ARG;
-    if (!d_dataset || !d_queries || !d_out_dist || !d_out_idx || !d_ws) return PSH_E_ARG;
+    if (!d_dataset || !d_queries || !d_out_dist || !d_ws) return PSH_E_ARG;  // d_out_idx NULL: packed records
     if (row_stride < T) return PSH_E_ARG;
     Plan pl;
     if (!make_plan(R, T, B, W, H, k, pl)) {
@@ -1707,7 +1718,8 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
         int nq = B - g0 < QG_MAX ? B - g0 : QG_MAX;
         int rc = run_scan_group(d_dataset, R, T, row_stride, d_queries + (size_t)g0 * W, nq, W, H, k, row_offset,
                                 pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap, qspec + (size_t)g0 * fftx::N, auxp, mode, false,
-                                d_out_dist + (size_t)g0 * k, d_out_idx + (size_t)g0 * k * 2, stream);
+                                d_out_dist + (size_t)g0 * k * (d_out_idx ? 1 : 3),
+                                d_out_idx ? d_out_idx + (size_t)g0 * k * 2 : nullptr, stream);
         if (rc != PSH_OK) return rc;
     }
     // one synchronisation: did any candidate buffer overflow (adversarially ordered data)?
@@ -1722,7 +1734,8 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
             int rc = run_scan_group(d_dataset, R, T, row_stride, d_queries + (size_t)g0 * W, nq, W, H, k, row_offset,
                                     pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap, qspec + (size_t)g0 * fftx::N, auxp, mode,
                                     true,
-                                    d_out_dist + (size_t)g0 * k, d_out_idx + (size_t)g0 * k * 2, stream);
+                                    d_out_dist + (size_t)g0 * k * (d_out_idx ? 1 : 3),
+                                d_out_idx ? d_out_idx + (size_t)g0 * k * 2 : nullptr, stream);
             if (rc != PSH_OK) return rc;
             PSH_CUDA(cudaStreamSynchronize(stream));
         }

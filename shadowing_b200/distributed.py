@@ -47,17 +47,25 @@ def sharded_scan(ps, rows: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int
         raise RuntimeError(f"selected index k out of range: k={k} > {cache[1]} windows")
     k_loc = min(k, n_local)
     # packed records [distance bits, trajectory, offset]: ONE collective carries everything
-    rec = torch.empty((B, k, 3), dtype=torch.int32, device=rows.device)
-    if k_loc < k:  # a shard with fewer than k windows pads with +inf records that sort last
+    bufs = getattr(ps, "_shard_bufs", None)
+    if bufs is None or bufs[0].shape != (B, k, 3) or bufs[0].device != rows.device:
+        bufs = (torch.empty((B, k, 3), dtype=torch.int32, device=rows.device),
+                torch.empty((world, B, k, 3), dtype=torch.int32, device=rows.device))
+        ps._shard_bufs = bufs
+    rec, rec_all = bufs
+    if rows.is_cuda and k_loc == k:
+        mode, aux = ps._mode_and_aux(rows, T, W, H)
+        ps._workspace = _lib.scan_topk_packed(rows, T, q, H, k, ps._row_offset, mode, ps._workspace, aux, rec)
+    else:
+        # a shard with fewer than k windows pads with +inf records that sort last
         rec[..., 0] = 0x7F800000
         rec[..., 1] = _PAD_ROW
         rec[..., 2] = 0
-    if k_loc > 0:
-        mode, aux = ps._mode_and_aux(rows, T, W, H)
-        d, i, ps._workspace = _lib.scan_topk(rows, T, q, H, k_loc, ps._row_offset, mode, ps._workspace, aux)
-        rec[:, :k_loc, 0] = d.view(torch.int32)
-        rec[:, :k_loc, 1:] = i
-    rec_all = torch.empty((world, B, k, 3), dtype=torch.int32, device=rows.device)
+        if k_loc > 0:
+            mode, aux = ps._mode_and_aux(rows, T, W, H)
+            d, i, ps._workspace = _lib.scan_topk(rows, T, q, H, k_loc, ps._row_offset, mode, ps._workspace, aux)
+            rec[:, :k_loc, 0] = d.view(torch.int32)
+            rec[:, :k_loc, 1:] = i
     if rows.is_cuda:
         dist.all_gather_into_tensor(rec_all, rec, group=pg)          # one ncclAllGather, B*k*12 bytes per rank
         return _lib.merge_topk_packed(rec_all, Tp)
