@@ -573,8 +573,11 @@ __global__ void __launch_bounds__(fftx::THREADS) fft_prep_y2_kernel(const float 
     for (int i = 0; i < 16; ++i) pfx[16 * tid + i + 1] = off + loc[i];
     __syncthreads();
     float *o = a.Y2 + (size_t)blockIdx.x * a.y2_stride;
-    for (int t = tid; t < a.y2_stride; t += fftx::THREADS)
-        o[t] = t < Tp ? (float)(pfx[t + W] - pfx[t]) : __int_as_float(0x7f800000);
+    // stored at position p = 256 c + 16 a + b for window t = 256 c + 16 b + a (the scan's output order)
+    for (int pos = tid; pos < a.y2_stride; pos += fftx::THREADS) {
+        const int t = (pos & ~255) | ((pos & 15) << 4) | ((pos >> 4) & 15);
+        o[pos] = t < Tp ? (float)(pfx[t + W] - pfx[t]) : __int_as_float(0x7f800000);
+    }
 }
 
 // conj(FFT_4096(q padded))/4096 per query (direct fp64 DFT on the exact twiddle table) and
@@ -647,7 +650,7 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
     float2 *Zs = reinterpret_cast<float2 *>(fsm);
     float *Y2s = reinterpret_cast<float *>(fsm + sizeof(float2) * fftx::N);
     float2 *ex = reinterpret_cast<float2 *>(fsm + sizeof(float2) * fftx::N + sizeof(float) * 2 * p.y2_stride);
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(ex + fftx::EX_FLOAT2);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(ex + fftx::EX2_FLOAT2);
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t barZ = smem_u32(&bars[0]), barY = smem_u32(&bars[1]);
     if (tid == 0) {
@@ -700,24 +703,26 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = fftx::cmul(Zs[tid + 256 * i], __ldg(Qb + tid + 256 * i));
             }
-            if (b == p.nq - 1) {
-                __syncthreads();  // every thread has taken its part of the spectrum
-                if (tid == 0 && npair >= 0) issue_z(npair);
-            }
-            fftx::fft4096<1, false>(v, ex, p.tw, tid, seeds);
+            // behind the transform's only CTA barrier every thread has consumed the staged
+            // spectrum: the next pair's copy is issued there (last query of the group)
+            const bool last_q = b == p.nq - 1;
+            fftx::ifft4096_scan(v, ex, tid, seeds, [&]() {
+                if (last_q && tid == 0 && npair >= 0) issue_z(npair);
+            });
             if (b == 0) { mbar_wait(barY, phY); phY ^= 1; }  // the pair's window energies have landed
             const float q2 = SINGLEQ ? q2_0 : p.st[b].q2, qmax = SINGLEQ ? qmax_0 : p.st[b].qmax;
             const float thr = SINGLEQ ? thr_0 : ld_volatile_f32(&p.st[b].thr_fast);
             const float slack = (2.0f * p.cf_u * qmax * yn + 4.76837158203125e-7f * (q2 + yn * yn)) * 1.0001f;
             const float base = (q2 - slack) - thr;
             unsigned int mask = 0;
-            // rows are padded to 4096 entries with +inf: windows t >= T' can never pass
+            // v[c] belongs to window t = (tid>>4) + 16 (tid&15) + 256 c; the energy rows are stored
+            // in that order (position tid + 256 c) and padded with +inf beyond T': no range checks
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
-                const int t = tid + 256 * c;
-                const float va = fmaf(-2.0f, v[c].x, Y2s[t]) + base;
+                const int pos = tid + 256 * c;
+                const float va = fmaf(-2.0f, v[c].x, Y2s[pos]) + base;
                 if (!(va > 0.0f)) mask |= 1u << c;
-                const float vb = fmaf(-2.0f, v[c].y, Y2s[fftx::N + t]) + base;
+                const float vb = fmaf(-2.0f, v[c].y, Y2s[fftx::N + pos]) + base;
                 if (!(vb > 0.0f)) mask |= 1u << (16 + c);
             }
             if (!has_b) mask &= 0xffffu;
@@ -739,8 +744,9 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
                 const unsigned int fb = (unsigned int)((unsigned long long)rb * (unsigned long long)p.Tp);
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
-                    if (mask & (1u << c)) { if (pos < p.cap) dst[pos] = fa + (unsigned int)(tid + 256 * c); ++pos; }
-                    if (mask & (1u << (16 + c))) { if (pos < p.cap) dst[pos] = fb + (unsigned int)(tid + 256 * c); ++pos; }
+                    const unsigned int t = (unsigned int)((tid >> 4) + 16 * (tid & 15) + 256 * c);
+                    if (mask & (1u << c)) { if (pos < p.cap) dst[pos] = fa + t; ++pos; }
+                    if (mask & (1u << (16 + c))) { if (pos < p.cap) dst[pos] = fb + t; ++pos; }
                 }
             }
             __syncthreads();  // ex (and, after the last query, the energy rows) may be overwritten
@@ -1586,7 +1592,7 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
         fp.cf_u = 512.0f * 5.9604644775390625e-8f;
     }
     const size_t smem_fft = use_fft ? sizeof(float2) * fftx::N + sizeof(float) * 2 * (size_t)aux->y2_stride
-                                          + sizeof(float2) * fftx::EX_FLOAT2 + 16
+                                          + sizeof(float2) * fftx::EX2_FLOAT2 + 16
                                     : 0;
     if (use_fft) {
         PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
