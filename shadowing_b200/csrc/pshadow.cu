@@ -581,30 +581,36 @@ __global__ void __launch_bounds__(fftx::THREADS) fft_prep_y2_kernel(const float 
 }
 
 // conj(FFT_4096(q padded))/4096 per query (direct fp64 DFT on the exact twiddle table) and
-// max_k |Q_k|.  grid = (4096/256, nq): one frequency per thread.
-__global__ void __launch_bounds__(fftx::THREADS) qfft_kernel(const float *__restrict__ q, int W,
-                                                             const double2 *__restrict__ tw64, float2 *Qc, QState *st) {
+// max_k |Q_k|.  grid = (4096/64, nq): 64 frequencies per CTA, 4 threads share one frequency.
+constexpr int QFFT_K = 64;
+
+__global__ void __launch_bounds__(4 * QFFT_K) qfft_kernel(const float *__restrict__ q, int W,
+                                                          const double2 *__restrict__ tw64, float2 *Qc, QState *st) {
     extern __shared__ double qd[];
-    __shared__ double red[fftx::THREADS / 32];
+    __shared__ double red[4 * QFFT_K / 32];
     const int b = blockIdx.y, tid = threadIdx.x;
-    for (int j = tid; j < W; j += fftx::THREADS) qd[j] = (double)q[(size_t)b * W + j];
+    for (int j = tid; j < W; j += 4 * QFFT_K) qd[j] = (double)q[(size_t)b * W + j];
     __syncthreads();
-    const int k = blockIdx.x * fftx::THREADS + tid;
+    const int k = blockIdx.x * QFFT_K + (tid >> 2), part = tid & 3;
+    const int per = (W + 3) / 4;
+    const int j0 = part * per, j1 = min(W, j0 + per);
     double re = 0.0, im = 0.0;
-#pragma unroll 4
-    for (int j = 0; j < W; ++j) {
+#pragma unroll 8
+    for (int j = j0; j < j1; ++j) {
         const double2 w = __ldg(tw64 + ((j * k) & (fftx::N - 1)));  // exp(+i theta): Q_k = sum q_j exp(-i theta)
         re += qd[j] * w.x;
         im -= qd[j] * w.y;
     }
-    Qc[(size_t)b * fftx::N + k] = make_float2((float)(re / fftx::N), (float)(-im / fftx::N));
+    re += __shfl_xor_sync(FULL, re, 1); im += __shfl_xor_sync(FULL, im, 1);
+    re += __shfl_xor_sync(FULL, re, 2); im += __shfl_xor_sync(FULL, im, 2);
+    if (part == 0) Qc[(size_t)b * fftx::N + k] = make_float2((float)(re / fftx::N), (float)(-im / fftx::N));
     double mx = re * re + im * im;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
     if ((tid & 31) == 0) red[tid >> 5] = mx;
     __syncthreads();
     if (tid == 0) {
-        for (int i = 1; i < fftx::THREADS / 32; ++i) mx = fmax(mx, red[i]);
+        for (int i = 1; i < 4 * QFFT_K / 32; ++i) mx = fmax(mx, red[i]);
         const float m = __double2float_ru(sqrt(mx) * (1.0 + 1e-7));
         atomicMax(reinterpret_cast<unsigned int *>(&st[b].qmax), __float_as_uint(m));  // positive floats order as uints
     }
@@ -1541,7 +1547,7 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
     const bool use_fft = (mode == PSH_MODE_FFT) && !safe && aux != nullptr;
     const bool filter = (mode == PSH_MODE_FILTER || (mode == PSH_MODE_FFT && !use_fft)) && !safe;
     if (use_fft) {
-        qfft_kernel<<<dim3(fftx::N / fftx::THREADS, nq), fftx::THREADS, (size_t)W * sizeof(double), stream>>>(
+        qfft_kernel<<<dim3(fftx::N / QFFT_K, nq), 4 * QFFT_K, (size_t)W * sizeof(double), stream>>>(
             d_q, W, aux->tw64, qspec, st);
         PSH_LAUNCHED();
     }
