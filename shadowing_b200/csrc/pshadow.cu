@@ -616,6 +616,9 @@ __global__ void __launch_bounds__(4 * QFFT_K) qfft_kernel(const float *__restric
     }
 }
 
+constexpr int FFT_NB = 2048;      // bins of the in-launch threshold histogram
+constexpr int FFT_REFRESH = 4;    // pairs between two threshold refreshes of a CTA
+
 struct FftScanParams {
     const float2 *Z;
     const float *Y2;
@@ -631,6 +634,12 @@ struct FftScanParams {
     unsigned int *cand;
     unsigned int cap;
     float cf_u;        // CF * 2^-24: |c^_t - c_t| <= cf_u * Qmax * ynorm  (CF = 512, theory ~165)
+    // in-launch threshold tightening: per query a histogram (FFT_NB linear bins over [0, thr at
+    // launch)) of UPPER bounds UB = LB + 2 slack of the windows that passed; the bin edge below
+    // which k upper bounds lie is a valid, tighter threshold (NULL: thresholds stay fixed)
+    unsigned int *hist;
+    unsigned int k;
+    float widen2;      // (1 + 2 (W+8) u)^2 (1 + 1e-6): exact-sequence rounding, both directions
 };
 
 // One CTA per row pair: Z * conj(Q)/N -> inverse FFT -> (D_a[t], D_b[t]) for t = tid + 256 c.
@@ -657,12 +666,19 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
     float *Y2s = reinterpret_cast<float *>(fsm + sizeof(float2) * fftx::N);
     float2 *ex = reinterpret_cast<float2 *>(fsm + sizeof(float2) * fftx::N + sizeof(float) * 2 * p.y2_stride);
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(ex + fftx::EX2_FLOAT2);
+    __shared__ float s_thrq[QG_MAX], s_hscale[QG_MAX];
+    __shared__ unsigned int s_wsum[fftx::THREADS / 32], s_edge;
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t barZ = smem_u32(&bars[0]), barY = smem_u32(&bars[1]);
     if (tid == 0) {
         mbar_init(barZ, 1);
         mbar_init(barY, 1);
         mbar_fence_init();
+    }
+    if (tid < p.nq) {
+        const float t0 = ld_volatile_f32(&p.st[tid].thr_fast);
+        s_thrq[tid] = t0;
+        s_hscale[tid] = (p.hist != nullptr && t0 > 0.0f && t0 < __int_as_float(0x7f800000)) ? (float)FFT_NB / t0 : 0.0f;
     }
     __syncthreads();
 
@@ -689,10 +705,9 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
         for (int i = 0; i < 16; ++i) qreg[i] = __ldg(p.Qc + tid + 256 * i);
     }
     const fftx::TwSeeds seeds = fftx::load_seeds(p.tw, tid);
-    // thresholds only move between launches
-    const float q2_0 = p.st[0].q2, qmax_0 = p.st[0].qmax, thr_0 = ld_volatile_f32(&p.st[0].thr_fast);
+    const float q2_0 = p.st[0].q2, qmax_0 = p.st[0].qmax;
     uint32_t phZ = 0, phY = 0;
-    for (; slot < p.i1; slot += gridDim.x) {
+    for (int iter = 0; slot < p.i1; slot += gridDim.x, ++iter) {
         const long long nslot = slot + gridDim.x;
         const long long npair = nslot < p.i1 ? fft_pair_of_slot(p, nslot) : -1;
         const long long ra = 2 * pair, rb = ra + 1;
@@ -717,19 +732,19 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
             });
             if (b == 0) { mbar_wait(barY, phY); phY ^= 1; }  // the pair's window energies have landed
             const float q2 = SINGLEQ ? q2_0 : p.st[b].q2, qmax = SINGLEQ ? qmax_0 : p.st[b].qmax;
-            const float thr = SINGLEQ ? thr_0 : ld_volatile_f32(&p.st[b].thr_fast);
+            const float thr = s_thrq[b];
             const float slack = (2.0f * p.cf_u * qmax * yn + 4.76837158203125e-7f * (q2 + yn * yn)) * 1.0001f;
-            const float base = (q2 - slack) - thr;
+            const float base0 = q2 - slack;   // LB = (Y2 - 2 D^) + base0, kept iff LB <= thr
             unsigned int mask = 0;
             // v[c] belongs to window t = (tid>>4) + 16 (tid&15) + 256 c; the energy rows are stored
             // in that order (position tid + 256 c) and padded with +inf beyond T': no range checks
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
                 const int pos = tid + 256 * c;
-                const float va = fmaf(-2.0f, v[c].x, Y2s[pos]) + base;
-                if (!(va > 0.0f)) mask |= 1u << c;
-                const float vb = fmaf(-2.0f, v[c].y, Y2s[fftx::N + pos]) + base;
-                if (!(vb > 0.0f)) mask |= 1u << (16 + c);
+                const float va = fmaf(-2.0f, v[c].x, Y2s[pos]) + base0;
+                if (!(va > thr)) mask |= 1u << c;
+                const float vb = fmaf(-2.0f, v[c].y, Y2s[fftx::N + pos]) + base0;
+                if (!(vb > thr)) mask |= 1u << (16 + c);
             }
             if (!has_b) mask &= 0xffffu;
             if (__any_sync(FULL, mask != 0)) {
@@ -748,16 +763,76 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
                 unsigned int *dst = p.cand + (size_t)b * p.cap;
                 const unsigned int fa = (unsigned int)((unsigned long long)ra * (unsigned long long)p.Tp);
                 const unsigned int fb = (unsigned int)((unsigned long long)rb * (unsigned long long)p.Tp);
+                const float hs = s_hscale[b];
+                unsigned int *hq = p.hist + (size_t)b * FFT_NB;
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                     const unsigned int t = (unsigned int)((tid >> 4) + 16 * (tid & 15) + 256 * c);
-                    if (mask & (1u << c)) { if (pos < p.cap) dst[pos] = fa + t; ++pos; }
-                    if (mask & (1u << (16 + c))) { if (pos < p.cap) dst[pos] = fb + t; ++pos; }
+                    if (mask & (1u << c)) {
+                        if (pos < p.cap) dst[pos] = fa + t;
+                        ++pos;
+                        if (hs > 0.0f) {  // upper bound of the window's exact squared distance
+                            const float ub = (fmaf(-2.0f, v[c].x, Y2s[tid + 256 * c]) + base0) + 2.0f * slack;
+                            const float fbin = ub * hs;
+                            if (fbin < (float)FFT_NB) atomicAdd(&hq[fbin > 0.0f ? (int)fbin : 0], 1u);
+                        }
+                    }
+                    if (mask & (1u << (16 + c))) {
+                        if (pos < p.cap) dst[pos] = fb + t;
+                        ++pos;
+                        if (hs > 0.0f) {
+                            const float ub = (fmaf(-2.0f, v[c].y, Y2s[fftx::N + tid + 256 * c]) + base0) + 2.0f * slack;
+                            const float fbin = ub * hs;
+                            if (fbin < (float)FFT_NB) atomicAdd(&hq[fbin > 0.0f ? (int)fbin : 0], 1u);
+                        }
+                    }
                 }
             }
             __syncthreads();  // ex (and, after the last query, the energy rows) may be overwritten
         }
         if (tid == 0 && npair >= 0) issue_y(npair);
+        // threshold refresh: k windows with UB <= edge exist  =>  the k-th exact distance of the whole
+        // ensemble is <= edge (1+gamma)  =>  filtering with edge * widen2 loses nothing
+        if (p.hist != nullptr && (iter < 2 || (iter % FFT_REFRESH) == FFT_REFRESH - 1) && npair >= 0) {
+            for (int b = 0; b < p.nq; ++b) {
+                const float hs = s_hscale[b];
+                if (!(hs > 0.0f)) continue;  // CTA-uniform
+                const uint4 *h4 = reinterpret_cast<const uint4 *>(p.hist + (size_t)b * FFT_NB) + tid * (FFT_NB / fftx::THREADS / 4);
+                unsigned int loc[FFT_NB / fftx::THREADS];
+#pragma unroll
+                for (int i = 0; i < FFT_NB / fftx::THREADS / 4; ++i) {
+                    const uint4 x = __ldcg(h4 + i);
+                    loc[4 * i] = x.x; loc[4 * i + 1] = x.y; loc[4 * i + 2] = x.z; loc[4 * i + 3] = x.w;
+                }
+                unsigned int sum = 0;
+#pragma unroll
+                for (int i = 0; i < FFT_NB / fftx::THREADS; ++i) sum += loc[i];
+                unsigned int incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int u = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += u;
+                }
+                if (lane == 31) s_wsum[tid >> 5] = incl;
+                if (tid == 0) s_edge = 0xffffffffu;
+                __syncthreads();
+                unsigned int cum = incl - sum;
+                for (int w = 0; w < (tid >> 5); ++w) cum += s_wsum[w];
+                if (cum < p.k && p.k <= cum + sum) {  // exactly one thread
+#pragma unroll
+                    for (int i = 0; i < FFT_NB / fftx::THREADS; ++i) {
+                        if (cum < p.k && p.k <= cum + loc[i]) s_edge = (unsigned int)(tid * (FFT_NB / fftx::THREADS) + i + 1);
+                        cum += loc[i];
+                    }
+                }
+                __syncthreads();
+                if (tid == 0 && s_edge != 0xffffffffu) {
+                    const float tn = ((float)s_edge / hs) * p.widen2;
+                    if (tn < s_thrq[b]) s_thrq[b] = tn;
+                }
+                __syncthreads();
+            }
+        }
         pair = npair;
     }
 }
@@ -979,8 +1054,10 @@ __device__ unsigned long long select_generic(const unsigned long long *src, unsi
 __global__ void __launch_bounds__(SEL_THREADS) select_kernel(QState *st_all, unsigned long long *keys_all,
                                                               unsigned int cap, unsigned int k, int W, int final_sort,
                                                               unsigned int Tp, int row_offset, float *out_d,
-                                                              int *out_idx) {
+                                                              int *out_idx, unsigned int *fft_hist) {
     __shared__ unsigned int hist[SEL_BINS];
+    if (fft_hist != nullptr)  // fresh in-launch threshold histogram for the next FFT round
+        for (int i = threadIdx.x; i < FFT_NB; i += SEL_THREADS) fft_hist[(size_t)blockIdx.x * FFT_NB + i] = 0u;
     __shared__ unsigned long long list[SEL_LIST];
     __shared__ unsigned long long s_prefix;
     __shared__ unsigned int s_need, s_done, s_out, s_min, s_max, s_bin, s_below, s_nlist, s_fast;
@@ -1377,7 +1454,7 @@ struct Plan {
     unsigned int cap;
     long long n0;      // rows of the seeding chunk
     int growth;
-    size_t off_state, off_keys, off_cand, off_qspec, total;
+    size_t off_state, off_keys, off_cand, off_qspec, off_hist, total;
 };
 
 constexpr int SEED_FACTOR = 16;  // seeding chunk holds ~16 k windows
@@ -1406,7 +1483,8 @@ bool make_plan(long long R, long long T, int B, int W, int H, long long k, Plan 
     pl.off_keys = align_up((size_t)B * sizeof(QState), 256);
     pl.off_cand = pl.off_keys + (size_t)B * 2 * (size_t)pl.cap * sizeof(unsigned long long);
     pl.off_qspec = pl.off_cand + align_up((size_t)B * (size_t)pl.cap * sizeof(unsigned int), 256);
-    pl.total = pl.off_qspec + (size_t)B * fftx::N * sizeof(float2);  // query spectra (fft flavour)
+    pl.off_hist = pl.off_qspec + (size_t)B * fftx::N * sizeof(float2);  // query spectra (fft flavour)
+    pl.total = pl.off_hist + (size_t)B * FFT_NB * sizeof(unsigned int);  // in-launch threshold histograms
     return true;
 }
 
@@ -1538,7 +1616,7 @@ int psh_debug_fft4096(const void *d_in, void *d_out, int n, int dir, const void 
 static int run_scan_group(const float *d_dataset, long long R, long long T, long long row_stride,
                           const float *d_q, int nq, int W, int H, long long k, int row_offset,
                           const Plan &pl, QState *st, unsigned long long *keys, unsigned int *cand, float2 *qspec,
-                          const FftAux *aux, int mode, bool safe, float *d_out_dist, int *d_out_idx,
+                          unsigned int *fhist, const FftAux *aux, int mode, bool safe, float *d_out_dist, int *d_out_idx,
                           cudaStream_t stream) {
     (void)H;
     qprep_kernel<<<(nq + 3) / 4, 128, 0, stream>>>(d_q, W, nq, st);
@@ -1596,6 +1674,11 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
         fp.npairs = p.npairs; fp.R = R; fp.perm = p.perm; fp.inv_np = p.inv_np;
         fp.st = st; fp.cand = cand; fp.cap = pl.cap;
         fp.cf_u = 512.0f * 5.9604644775390625e-8f;
+        fp.hist = fhist; fp.k = (unsigned int)k;
+        {
+            const double w1 = 1.0 + 2.0 * (double)(W + 8) * 5.9604644775390625e-8;
+            fp.widen2 = (float)(w1 * w1 * (1.0 + 1e-6));
+        }
     }
     const size_t smem_fft = use_fft ? sizeof(float2) * fftx::N + sizeof(float) * 2 * (size_t)aux->y2_stride
                                           + sizeof(float2) * fftx::EX2_FLOAT2 + 16
@@ -1625,6 +1708,7 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
     while (done < nslots) {
         long long next;
         if (safe) next = done + safe_slots;
+        else if (use_fft && done > 0) next = done == seed_slots ? (long long)ceil((double)done * pl.growth) : nslots;
         else next = done == 0 ? seed_slots : (long long)ceil((double)done * ratio);
         if (next <= done) next = done + 1;
         if (next > nslots) next = nslots;
@@ -1674,7 +1758,8 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
             ProfScope ps(stream, 1);
             const int fin = (fuse_final && next == nslots) ? 1 : 0;
             select_kernel<<<nq, SEL_THREADS, 0, stream>>>(st, keys, pl.cap, (unsigned int)k, W, fin,
-                                                          (unsigned int)pl.Tp, row_offset, d_out_dist, d_out_idx);
+                                                          (unsigned int)pl.Tp, row_offset, d_out_dist, d_out_idx,
+                                                          use_fft ? fhist : nullptr);
         }
         PSH_LAUNCHED();
         done = next;
@@ -1717,6 +1802,7 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(ws + pl.off_keys);
     unsigned int *cand = reinterpret_cast<unsigned int *>(ws + pl.off_cand);
     float2 *qspec = reinterpret_cast<float2 *>(ws + pl.off_qspec);
+    unsigned int *fhist_all = reinterpret_cast<unsigned int *>(ws + pl.off_hist);
     FftAux aux;
     const FftAux *auxp = nullptr;
     if (mode == PSH_MODE_FFT && d_aux != nullptr) {
@@ -1729,7 +1815,7 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
     for (int g0 = 0; g0 < B; g0 += QG_MAX) {
         int nq = B - g0 < QG_MAX ? B - g0 : QG_MAX;
         int rc = run_scan_group(d_dataset, R, T, row_stride, d_queries + (size_t)g0 * W, nq, W, H, k, row_offset,
-                                pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap, qspec + (size_t)g0 * fftx::N, auxp, mode, false,
+                                pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap, qspec + (size_t)g0 * fftx::N, fhist_all + (size_t)g0 * FFT_NB, auxp, mode, false,
                                 d_out_dist + (size_t)g0 * k * (d_out_idx ? 1 : 3),
                                 d_out_idx ? d_out_idx + (size_t)g0 * k * 2 : nullptr, stream);
         if (rc != PSH_OK) return rc;
@@ -1744,7 +1830,7 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
         for (int i = 0; i < nq; ++i) ovf = ovf || hst[i].overflow != 0;
         if (ovf) {
             int rc = run_scan_group(d_dataset, R, T, row_stride, d_queries + (size_t)g0 * W, nq, W, H, k, row_offset,
-                                    pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap, qspec + (size_t)g0 * fftx::N, auxp, mode,
+                                    pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap, qspec + (size_t)g0 * fftx::N, fhist_all + (size_t)g0 * FFT_NB, auxp, mode,
                                     true,
                                     d_out_dist + (size_t)g0 * k * (d_out_idx ? 1 : 3),
                                 d_out_idx ? d_out_idx + (size_t)g0 * k * 2 : nullptr, stream);
