@@ -28,7 +28,8 @@ enum {
     PSH_E_K = -2,          /* k exceeds the number of windows (reference: torch.topk raises)  */
     PSH_E_WORKSPACE = -3,  /* workspace smaller than psh_scan_workspace_bytes()               */
     PSH_E_TOO_LARGE = -4,  /* R*T' >= 2^32 windows in one call: shard the rows and merge      */
-    PSH_E_UNSUPPORTED = -5 /* context length beyond the shared-memory budget of the scan      */
+    PSH_E_UNSUPPORTED = -5, /* context length beyond the shared-memory budget of the scan     */
+    PSH_E_OVERFLOW = -6     /* psh_scan_overflowed: repeat the scan without PSH_FLAG_NOSYNC   */
 };
 
 /* scan modes */
@@ -40,6 +41,10 @@ enum {
                          /* (needs psh_fft_prepare aux, T <= 4096; else behaves as FILTER);   */
                          /* same exact re-rank, results identical to PSH_MODE_EXACT           */
 };
+
+/* OR-ed into `mode`: enqueue only, do not synchronise; the caller must call
+ * psh_scan_overflowed() (which synchronises) before trusting the results. */
+#define PSH_FLAG_NOSYNC 0x100
 
 int psh_version(void);
 const char *psh_error_string(int code);
@@ -75,6 +80,11 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
                       float *d_out_dist, int32_t *d_out_idx,
                       void *d_ws, size_t ws_bytes, const void *d_aux, size_t aux_bytes, void *stream);
 
+/* After a PSH_FLAG_NOSYNC scan (and whatever the caller enqueued behind it): synchronise the
+ * stream and report PSH_OK, or PSH_E_OVERFLOW if a candidate buffer overflowed (adversarially
+ * ordered data) -- then the outputs are invalid and the scan must be repeated without the flag. */
+int psh_scan_overflowed(const void *d_ws, int B, void *stream);
+
 /*
  * Dataset-side precomputation for PSH_MODE_FFT (no reference counterpart; the reference
  * recomputes everything per call).  Fills d_aux (>= psh_fft_aux_bytes, 256-byte aligned) with
@@ -100,7 +110,10 @@ int psh_merge_topk(const float *d_dist_parts, const int32_t *d_idx_parts, int G,
 /* Same merge on packed records (G, B, k, 3) int32 = [distance bits, trajectory, offset]: the
  * layout one ncclAllGather of the per-rank results produces. */
 int psh_merge_topk_packed(const int32_t *d_rec_parts, int G, int B, int64_t k, int64_t Tp,
-                          float *d_out_dist, int32_t *d_out_idx, void *stream);
+                          float *d_out_dist, int32_t *d_out_idx, int32_t *d_overflow_flag, void *stream);
+/* d_overflow_flag (may be NULL; zero it first): set to 1 if any shard's PSH_FLAG_NOSYNC scan
+ * overflowed a candidate buffer (it poisons its first record); every rank sees the same flag,
+ * so all ranks repeat the step with synchronous scans together. */
 
 /*
  * Gather the winning paths with their out-context: replaces path_shadowing.py:210-216.

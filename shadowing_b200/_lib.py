@@ -13,6 +13,8 @@ LIB_PATH = _PKG / "libpshadow.so"
 PSH_MODE_EXACT = 0
 PSH_MODE_FILTER = 1
 PSH_MODE_FFT = 2
+PSH_FLAG_NOSYNC = 0x100
+PSH_E_OVERFLOW = -6
 FFT_MAX_T = 4096
 
 _lib = None
@@ -45,6 +47,8 @@ def lib() -> ctypes.CDLL:
         L.psh_scan_workspace_bytes.argtypes = [i64, i64, ci, ci, ci, i64]
         L.psh_scan_topk_f32.restype = ci
         L.psh_scan_topk_f32.argtypes = [vp, i64, i64, i64, vp, ci, ci, ci, i64, i32, ci, vp, vp, vp, sz, vp, sz, vp]
+        L.psh_scan_overflowed.restype = ci
+        L.psh_scan_overflowed.argtypes = [vp, ci, vp]
         L.psh_fft_aux_bytes.restype = sz
         L.psh_fft_aux_bytes.argtypes = [i64, i64, ci, ci]
         L.psh_fft_prepare.restype = ci
@@ -54,7 +58,7 @@ def lib() -> ctypes.CDLL:
         L.psh_merge_topk.restype = ci
         L.psh_merge_topk.argtypes = [vp, vp, ci, ci, i64, i64, vp, vp, vp]
         L.psh_merge_topk_packed.restype = ci
-        L.psh_merge_topk_packed.argtypes = [vp, ci, ci, i64, i64, vp, vp, vp]
+        L.psh_merge_topk_packed.argtypes = [vp, ci, ci, i64, i64, vp, vp, vp, vp]
         L.psh_gather_paths.restype = ci
         L.psh_gather_paths.argtypes = [vp, i64, i64, i64, vp, i64, i32, ci, vp, vp]
         L.psh_rv_aggregate.restype = ci
@@ -97,6 +101,17 @@ def scan_topk_packed(ds: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int, 
                                  _stream(ds))
     _check(rc, "psh_scan_topk_f32")
     return workspace
+
+
+def scan_overflowed(workspace: torch.Tensor, B: int) -> bool:
+    """Synchronise and report whether a PSH_FLAG_NOSYNC scan overflowed a candidate buffer."""
+    L = lib()
+    with torch.cuda.device(workspace.device):
+        rc = L.psh_scan_overflowed(workspace.data_ptr(), B, _stream(workspace))
+    if rc == PSH_E_OVERFLOW:
+        return True
+    _check(rc, "psh_scan_overflowed")
+    return False
 
 
 def fft_prepare(ds: torch.Tensor, T: int, W: int, H: int) -> torch.Tensor:
@@ -168,8 +183,9 @@ def merge_topk(dist_parts: torch.Tensor, idx_parts: torch.Tensor, Tp: int):
     return dist, idx
 
 
-def merge_topk_packed(rec_parts: torch.Tensor, Tp: int):
-    """(G,B,k,3) i32 [distance bits, r, t] -> merged (B,k) f32, (B,k,2) i32."""
+def merge_topk_packed(rec_parts: torch.Tensor, Tp: int, flag: torch.Tensor | None = None):
+    """(G,B,k,3) i32 [distance bits, r, t] -> merged (B,k) f32, (B,k,2) i32.  `flag` (int32[1],
+    zeroed by the caller) is set if any shard's NOSYNC scan overflowed."""
     L = lib()
     G, B, k, _ = rec_parts.shape
     rec_parts = rec_parts.contiguous()
@@ -177,7 +193,7 @@ def merge_topk_packed(rec_parts: torch.Tensor, Tp: int):
     idx = torch.empty((B, k, 2), dtype=torch.int32, device=rec_parts.device)
     with torch.cuda.device(rec_parts.device):
         rc = L.psh_merge_topk_packed(rec_parts.data_ptr(), G, B, k, Tp, dist.data_ptr(), idx.data_ptr(),
-                                     _stream(rec_parts))
+                                     flag.data_ptr() if flag is not None else None, _stream(rec_parts))
     _check(rc, "psh_merge_topk_packed")
     return dist, idx
 

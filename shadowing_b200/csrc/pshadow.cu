@@ -1241,7 +1241,10 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(QState *st_all, uns
     for (unsigned int i = tid; i < k; i += SEL_THREADS) {
         const unsigned long long key = list[i];
         const unsigned int flat = (unsigned int)key;
-        write_result(out_d, out_idx, (size_t)blockIdx.x * k + i, (unsigned int)(key >> 32),
+        // packed output of a NOSYNC scan: an overflowed query poisons its first record so that every
+        // rank sees it after the all-gather (merge_kernel raises the flag)
+        const bool poison = out_idx == nullptr && i == 0 && st->overflow != 0;
+        write_result(out_d, out_idx, (size_t)blockIdx.x * k + i, poison ? 0xffffffffu : (unsigned int)(key >> 32),
                      (int)(flat / Tp) + row_offset, (int)(flat % Tp));
     }
 }
@@ -1262,7 +1265,10 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const QState *st_
     for (unsigned int i = threadIdx.x; i < k; i += blockDim.x) {
         unsigned long long key = a[i];
         unsigned int flat = (unsigned int)key;
-        write_result(out_d, out_idx, (size_t)blockIdx.x * k + i, (unsigned int)(key >> 32),
+        // packed output of a NOSYNC scan: an overflowed query poisons its first record so that every
+        // rank sees it after the all-gather (merge_kernel raises the flag)
+        const bool poison = out_idx == nullptr && i == 0 && st->overflow != 0;
+        write_result(out_d, out_idx, (size_t)blockIdx.x * k + i, poison ? 0xffffffffu : (unsigned int)(key >> 32),
                      (int)(flat / Tp) + row_offset, (int)(flat % Tp));
     }
 }
@@ -1279,7 +1285,7 @@ __global__ void __launch_bounds__(SEL_THREADS) merge_kernel(const float *d_parts
                                                              int istride, int G, int B,
                                                              unsigned int k, unsigned long long Tp, unsigned int npow2,
                                                              unsigned long long *scratch, int use_smem,
-                                                             float *out_d, int *out_idx) {
+                                                             float *out_d, int *out_idx, int *flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x;
     unsigned long long *a = use_smem ? reinterpret_cast<unsigned long long *>(smem_raw)
@@ -1290,6 +1296,7 @@ __global__ void __launch_bounds__(SEL_THREADS) merge_kernel(const float *d_parts
         if (i < n) {
             unsigned int g = i / k, j = i - g * k;
             float d = d_parts[(((size_t)g * B + b) * k + j) * dstride];
+            if (flag != nullptr && __float_as_uint(d) == 0xffffffffu) atomicOr(flag, 1);  // a shard overflowed
             key = ((unsigned long long)__float_as_uint(d) << 32) | i;
         }
         a[i] = key;
@@ -1533,6 +1540,7 @@ const char *psh_error_string(int code) {
         case PSH_E_WORKSPACE: return "workspace too small or misaligned";
         case PSH_E_TOO_LARGE: return "more than 2^32-1 windows in one call: shard the rows and merge";
         case PSH_E_UNSUPPORTED: return "context length exceeds the shared-memory budget of the scan";
+        case PSH_E_OVERFLOW: return "a candidate buffer overflowed in a PSH_FLAG_NOSYNC scan: repeat the call without the flag";
         default: break;
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
@@ -1785,6 +1793,8 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
                       float *d_out_dist, int32_t *d_out_idx,
                       void *d_ws, size_t ws_bytes, const void *d_aux, size_t aux_bytes, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    const bool nosync = (mode & PSH_FLAG_NOSYNC) != 0;
+    mode &= ~PSH_FLAG_NOSYNC;
     if (mode != PSH_MODE_EXACT && mode != PSH_MODE_FILTER && mode != PSH_MODE_FFT) return PSH_E_ARG;
     if (!d_dataset || !d_queries || !d_out_dist || !d_ws) return PSH_E_ARG;  // d_out_idx NULL: packed records
     if (row_stride < T) return PSH_E_ARG;
@@ -1820,6 +1830,7 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
                                 d_out_idx ? d_out_idx + (size_t)g0 * k * 2 : nullptr, stream);
         if (rc != PSH_OK) return rc;
     }
+    if (nosync) return PSH_OK;  // the caller checks psh_scan_overflowed() before trusting the results
     // one synchronisation: did any candidate buffer overflow (adversarially ordered data)?
     static thread_local QState hst[QG_MAX];
     for (int g0 = 0; g0 < B; g0 += QG_MAX) {
@@ -1841,8 +1852,23 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
     return PSH_OK;
 }
 
+int psh_scan_overflowed(const void *d_ws, int B, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!d_ws || B <= 0) return PSH_E_ARG;
+    const QState *st = static_cast<const QState *>(d_ws);
+    static thread_local QState hst[QG_MAX];
+    int ovf = 0;
+    for (int g0 = 0; g0 < B; g0 += QG_MAX) {
+        int nq = B - g0 < QG_MAX ? B - g0 : QG_MAX;
+        PSH_CUDA(cudaMemcpyAsync(hst, st + g0, sizeof(QState) * nq, cudaMemcpyDeviceToHost, stream));
+        PSH_CUDA(cudaStreamSynchronize(stream));
+        for (int i = 0; i < nq; ++i) ovf |= hst[i].overflow != 0 ? 1 : 0;
+    }
+    return ovf ? PSH_E_OVERFLOW : PSH_OK;
+}
+
 static int merge_impl(const float *d_parts, const int *i_parts, int dstride, int istride, int G, int B, int64_t k,
-                      int64_t Tp, float *d_out_dist, int32_t *d_out_idx, cudaStream_t stream) {
+                      int64_t Tp, float *d_out_dist, int32_t *d_out_idx, int *d_flag, cudaStream_t stream) {
     if (!d_parts || !i_parts || !d_out_dist || !d_out_idx || G <= 0 || B <= 0 || k <= 0 || Tp <= 0) return PSH_E_ARG;
     unsigned long long n = (unsigned long long)G * (unsigned long long)k;
     if (n > 0x7fffffffull) return PSH_E_TOO_LARGE;
@@ -1855,7 +1881,7 @@ static int merge_impl(const float *d_parts, const int *i_parts, int dstride, int
         PSH_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     merge_kernel<<<B, SEL_THREADS, smem, stream>>>(d_parts, i_parts, dstride, istride, G, B, (unsigned int)k,
                                                    (unsigned long long)Tp, npow2, scratch, use_smem, d_out_dist,
-                                                   d_out_idx);
+                                                   d_out_idx, d_flag);
     PSH_LAUNCHED();
     if (scratch) PSH_CUDA(cudaFreeAsync(scratch, stream));
     return PSH_OK;
@@ -1863,22 +1889,23 @@ static int merge_impl(const float *d_parts, const int *i_parts, int dstride, int
 
 int psh_merge_topk(const float *d_dist_parts, const int32_t *d_idx_parts, int G, int B,
                    int64_t k, int64_t Tp, float *d_out_dist, int32_t *d_out_idx, void *stream_) {
-    return merge_impl(d_dist_parts, d_idx_parts, 1, 2, G, B, k, Tp, d_out_dist, d_out_idx, (cudaStream_t)stream_);
+    return merge_impl(d_dist_parts, d_idx_parts, 1, 2, G, B, k, Tp, d_out_dist, d_out_idx, nullptr,
+                      (cudaStream_t)stream_);
 }
 
 int psh_merge_topk_packed(const int32_t *d_rec_parts, int G, int B, int64_t k, int64_t Tp,
-                          float *d_out_dist, int32_t *d_out_idx, void *stream_) {
+                          float *d_out_dist, int32_t *d_out_idx, int32_t *d_overflow_flag, void *stream_) {
     if (!d_rec_parts) return PSH_E_ARG;
     return merge_impl(reinterpret_cast<const float *>(d_rec_parts), d_rec_parts + 1, 3, 3, G, B, k, Tp, d_out_dist,
-                      d_out_idx, (cudaStream_t)stream_);
+                      d_out_idx, d_overflow_flag, (cudaStream_t)stream_);
 }
 
 int psh_gather_paths(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride,
                      const int32_t *d_idx, int64_t n, int32_t row_offset, int L,
                      float *d_out, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (!d_dataset || !d_idx || !d_out || R <= 0 || T <= 0 || n < 0 || L <= 0 || L > T || row_stride < T)
-        return PSH_E_ARG;
+    if ((!d_dataset && R > 0) || !d_idx || !d_out || R < 0 || T <= 0 || n < 0 || L <= 0 || L > T || row_stride < T)
+        return PSH_E_ARG;  // R == 0: an empty shard, every path is written as zeros
     if (n == 0) return PSH_OK;
     const int warps = 8;
     gather_kernel<<<(unsigned int)((n + warps - 1) / warps), warps * 32, 0, stream>>>(

@@ -25,9 +25,41 @@ def shard_bounds(R: int, world: int, rank: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def _local_records(ps, rows, T, q, H, k, rec, nosync: bool):
+    """This rank's k best windows as packed (B,k,3) int32 records [distance bits, r, t] in `rec`."""
+    B, W = q.shape
+    n_local = rows.shape[0] * (T - W - H + 1)
+    k_loc = min(k, n_local)
+    if rows.is_cuda and k_loc == k:
+        mode, aux = ps._mode_and_aux(rows, T, W, H)
+        ps._workspace = _lib.scan_topk_packed(rows, T, q, H, k, ps._row_offset,
+                                              mode | (_lib.PSH_FLAG_NOSYNC if nosync else 0), ps._workspace, aux, rec)
+        return
+    # a shard with fewer than k windows pads with +inf records that sort last
+    rec[..., 0] = 0x7F800000
+    rec[..., 1] = _PAD_ROW
+    rec[..., 2] = 0
+    if k_loc > 0:
+        mode, aux = ps._mode_and_aux(rows, T, W, H)
+        d, i, ps._workspace = _lib.scan_topk(rows, T, q, H, k_loc, ps._row_offset, mode, ps._workspace, aux)
+        rec[:, :k_loc, 0] = d.view(torch.int32)
+        rec[:, :k_loc, 1:] = i
+
+
+def _exchange_and_merge(ps, rows, rec, rec_all, Tp, flag):
+    pg = ps._pg
+    if rows.is_cuda:
+        dist.all_gather_into_tensor(rec_all, rec, group=pg)          # one ncclAllGather, B*k*12 bytes per rank
+        return _lib.merge_topk_packed(rec_all, Tp, flag)
+    dist.all_gather(list(rec_all.unbind(0)), rec, group=pg)          # gloo (CPU tests) has no *_into_tensor
+    return _lib.merge_topk(rec_all[..., 0].contiguous().view(torch.float32), rec_all[..., 1:].contiguous(), Tp)
+
+
 def sharded_scan(ps, rows: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int):
     """Local exact top-k on this rank's rows, all-gather, merge.  Every rank returns the global
-    (dist (B,k), idx (B,k,2)) with GLOBAL trajectory indices."""
+    (dist (B,k), idx (B,k,2)) with GLOBAL trajectory indices.  On CUDA the scan, the all-gather
+    and the merge are enqueued back to back without a host synchronisation; the candidate-buffer
+    overflow flag travels inside the records and is read once per step by `finish_sharded`."""
     pg = ps._pg
     world = dist.get_world_size(pg)
     B, W = q.shape
@@ -45,32 +77,35 @@ def sharded_scan(ps, rows: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int
         ps._total_windows = cache
     if k > cache[1]:
         raise RuntimeError(f"selected index k out of range: k={k} > {cache[1]} windows")
-    k_loc = min(k, n_local)
-    # packed records [distance bits, trajectory, offset]: ONE collective carries everything
     bufs = getattr(ps, "_shard_bufs", None)
     if bufs is None or bufs[0].shape != (B, k, 3) or bufs[0].device != rows.device:
         bufs = (torch.empty((B, k, 3), dtype=torch.int32, device=rows.device),
-                torch.empty((world, B, k, 3), dtype=torch.int32, device=rows.device))
+                torch.empty((world, B, k, 3), dtype=torch.int32, device=rows.device),
+                torch.zeros(1, dtype=torch.int32, device=rows.device))
         ps._shard_bufs = bufs
-    rec, rec_all = bufs
-    if rows.is_cuda and k_loc == k:
-        mode, aux = ps._mode_and_aux(rows, T, W, H)
-        ps._workspace = _lib.scan_topk_packed(rows, T, q, H, k, ps._row_offset, mode, ps._workspace, aux, rec)
-    else:
-        # a shard with fewer than k windows pads with +inf records that sort last
-        rec[..., 0] = 0x7F800000
-        rec[..., 1] = _PAD_ROW
-        rec[..., 2] = 0
-        if k_loc > 0:
-            mode, aux = ps._mode_and_aux(rows, T, W, H)
-            d, i, ps._workspace = _lib.scan_topk(rows, T, q, H, k_loc, ps._row_offset, mode, ps._workspace, aux)
-            rec[:, :k_loc, 0] = d.view(torch.int32)
-            rec[:, :k_loc, 1:] = i
-    if rows.is_cuda:
-        dist.all_gather_into_tensor(rec_all, rec, group=pg)          # one ncclAllGather, B*k*12 bytes per rank
-        return _lib.merge_topk_packed(rec_all, Tp)
-    dist.all_gather(list(rec_all.unbind(0)), rec, group=pg)          # gloo (CPU tests) has no *_into_tensor
-    return _lib.merge_topk(rec_all[..., 0].contiguous().view(torch.float32), rec_all[..., 1:].contiguous(), Tp)
+    rec, rec_all, flag = bufs
+    _local_records(ps, rows, T, q, H, k, rec, nosync=True)
+    out = _exchange_and_merge(ps, rows, rec, rec_all, Tp, flag)
+    ps._pending_flag = flag if rows.is_cuda else None
+    return out
+
+
+def finish_sharded(ps, rows: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int, out):
+    """Second half of the sharded scan: the single host synchronisation of a step.  If a candidate
+    buffer overflowed on ANY rank (adversarially ordered data; every rank reads the same flag from
+    the gathered records) all ranks repeat the step together with synchronous scans, which re-run
+    the overflowing queries in the safe schedule."""
+    flag = getattr(ps, "_pending_flag", None)
+    if flag is None:
+        return out
+    ps._pending_flag = None
+    if int(flag.item()) == 0:
+        return out
+    flag.zero_()
+    B, W = q.shape
+    rec, rec_all, _ = ps._shard_bufs
+    _local_records(ps, rows, T, q, H, k, rec, nosync=False)
+    return _exchange_and_merge(ps, rows, rec, rec_all, T - W - H + 1, None)
 
 
 def sharded_gather(ps, rows: torch.Tensor, T: int, idx: torch.Tensor, L: int) -> torch.Tensor:

@@ -207,8 +207,8 @@ class PathShadowing:
             dist, idx, self._workspace = _lib.scan_topk(rows, T, q, H, k, self._row_offset, mode,
                                                         self._workspace, aux, out)
             return dist, idx
-        from .distributed import sharded_scan
-        return sharded_scan(self, rows, T, q, H, k)
+        from .distributed import finish_sharded, sharded_scan
+        return finish_sharded(self, rows, T, q, H, k, sharded_scan(self, rows, T, q, H, k))
 
     def batched_distance(self, x: torch.Tensor, y: torch.Tensor, k: int, n_splits: int,
                          cuda: bool) -> tuple[torch.Tensor, torch.Tensor]:

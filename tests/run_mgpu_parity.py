@@ -27,18 +27,41 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    for (R, T, W, H, k, B) in [(1024, 4096, 252, 20, 1024, 2), (37, 700, 20, 5, 300, 3), (3, 600, 16, 4, 900, 1)]:
+    cases = [(1024, 4096, 252, 20, 1024, 2, False), (37, 700, 20, 5, 300, 3, False), (3, 600, 16, 4, 900, 1, False),
+             (1, 600, 16, 4, 100, 1, False),          # world > rows: empty shards
+             (1024, 1024, 32, 0, 64, 1, True)]        # adversarial order: candidate buffers overflow on every rank
+    for (R, T, W, H, k, B, adversarial) in cases:
         ds, q = make_inputs(R, T, W, B, seed=500 + R)
+        if adversarial:
+            # every rank's seed rows (its first permuted slots) are far, all its other rows near:
+            # the candidate buffers overflow and all ranks must repeat the step together
+            import math
+            ds = ds * 1e-3
+            Tp = T - W - H + 1
+            for rk in range(world):
+                lo_, hi_ = shard_bounds(R, world, rk)
+                n = hi_ - lo_
+                p = max(int(0.6180339887498949 * n), 1) if n > 2 else 1
+                while n > 2 and math.gcd(p, n) != 1:
+                    p += 1
+                p = (p % n or 1) if n > 2 else 1
+                n0 = min(max(-(-16 * k // Tp), 1), n)
+                for i in range(n0):
+                    ds[lo_ + (i * p) % n] *= 1e5
         lo, hi = shard_bounds(R, world, rank)
-        obj = sb.PathShadowing(sb.Identity(W), sb.RelativeMSE(), ds[lo:hi], sb.PredictionContext(H), device=dev,
-                               row_offset=lo, process_group=dist.group.WORLD)
+        obj = sb.PathShadowing(sb.Identity(W), sb.RelativeMSE(), ds[lo:hi], sb.PredictionContext(H or None), device=dev,
+                               row_offset=lo, process_group=dist.group.WORLD,
+                               scan_mode="filter" if adversarial else "auto")
         d, paths, idx = obj.shadow(q, k=k)
-        pred, pstd = obj.predict(q, k=k, to_predict=sb.RealizedVariance([2, 4]), eta=0.1)
         do, po, io = oracle.shadow(ds, q, k, H)
-        mo, so = oracle.predict_from_paths(do, po, H, [2, 4], False, "softmax", 0.1)
+        if H:
+            pred, pstd = obj.predict(q, k=k, to_predict=sb.RealizedVariance([2, 4]), eta=0.1)
+            mo, so = oracle.predict_from_paths(do, po, H, [2, 4], False, "softmax", 0.1)
+        else:
+            pred = pstd = mo = so = np.zeros(1)
         good = (np.array_equal(d.view(np.uint32), do.view(np.uint32)) and np.array_equal(idx, io)
                 and np.array_equal(paths, po) and np.allclose(pred, mo, rtol=1e-6) and np.allclose(pstd, so, rtol=1e-5))
-        print(f"rank {rank}/{world} R={R} T={T} W={W} k={k} B={B}: {'OK' if good else 'MISMATCH'}", flush=True)
+        print(f"rank {rank}/{world} R={R} T={T} W={W} k={k} B={B} adv={adversarial}: {'OK' if good else 'MISMATCH'}", flush=True)
         ok = ok and good
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
