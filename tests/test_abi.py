@@ -16,8 +16,10 @@ ROOT = Path(__file__).resolve().parents[1]
 def test_library_exports_every_declared_symbol():
     hdr = (ROOT / "include" / "pshadow.h").read_text()
     names = set(re.findall(r"\b(psh_[a-z0-9_]+)\s*\(", hdr))
-    assert {"psh_scan_topk_f32", "psh_merge_topk", "psh_gather_paths", "psh_rv_aggregate",
-            "psh_scan_workspace_bytes", "psh_version", "psh_error_string", "psh_launch_count"} <= names
+    assert {"psh_scan_topk_f32", "psh_merge_topk", "psh_merge_topk_packed", "psh_gather_paths", "psh_rv_aggregate",
+            "psh_scan_workspace_bytes", "psh_scan_overflowed", "psh_fft_aux_bytes", "psh_fft_prepare",
+            "psh_debug_fft4096", "psh_profile_begin", "psh_profile_end",
+            "psh_version", "psh_error_string", "psh_launch_count"} <= names
     so = ROOT / "shadowing_b200" / "libpshadow.so"
     assert so.exists(), "build with __graft_entry__.build()"
     L = ctypes.CDLL(str(so))
@@ -40,6 +42,8 @@ def test_version_errors_and_workspace_sizing():
     assert L.psh_fft_aux_bytes(8, 8192, 252, 20) == 0   # T > 4096: fft flavour unsupported
     assert L.psh_gather_paths(None, 1, 1, 1, None, 1, 0, 1, None, None) == -1
     assert L.psh_merge_topk(None, None, 1, 1, 1, 1, None, None, None) == -1
+    assert L.psh_scan_overflowed(None, 1, None) == -1
+    assert b"overflow" in L.psh_error_string(-6)
 
 
 def test_plugin_surface_matches_reference_names():

@@ -137,6 +137,48 @@ def test_adversarial_order_overflows_then_recovers(mode):
     assert_topk_equal(d, idx, do, io)
 
 
+def test_nosync_packed_records_and_overflow_flag():
+    """The multi-GPU building blocks on one device: packed [distance bits, r, t] records from a
+    PSH_FLAG_NOSYNC scan, the deferred overflow status, and the poisoned record that makes
+    psh_merge_topk_packed raise its flag when a shard overflowed."""
+    ds, q = make_inputs(200, 1500, 64, 3, seed=41)
+    rows = torch.tensor(ds[:, 0, :]).cuda()
+    qd = torch.tensor(q[:, 0, :]).cuda()
+    k, H = 100, 6
+    do, io = oracle.shadow_topk(ds, q, k, H, row_offset=7)
+    for mode in (_lib.PSH_MODE_FILTER, _lib.PSH_MODE_FFT):
+        aux = _lib.fft_prepare(rows, 1500, 64, H) if mode == _lib.PSH_MODE_FFT else None
+        rec = torch.empty((3, k, 3), dtype=torch.int32, device="cuda")
+        ws = _lib.scan_topk_packed(rows, 1500, qd, H, k, 7, mode | _lib.PSH_FLAG_NOSYNC, None, aux, rec)
+        assert not _lib.scan_overflowed(ws, 3)
+        r = rec.cpu().numpy()
+        assert np.array_equal(r[..., 0].view(np.uint32), do.view(np.uint32)) and np.array_equal(r[..., 1:], io)
+    # adversarial order (as in test_adversarial_order_overflows_then_recovers): the NOSYNC scan must report it
+    R, T, W, k = 512, 1024, 32, 64
+    ds, q = make_inputs(R, T, W, 1, seed=33)
+    Tp = T - W + 1
+    n0 = min(max(-(-16 * k // Tp), 1), R)
+    P = _perm_stride(R)
+    ds = ds * 1e-3
+    for i in range(n0):
+        ds[(i * P) % R] *= 1e5
+    rows = torch.tensor(ds[:, 0, :]).cuda()
+    qd = torch.tensor(q[:, 0, :]).cuda()
+    rec = torch.empty((1, k, 3), dtype=torch.int32, device="cuda")
+    ws = _lib.scan_topk_packed(rows, T, qd, 0, k, 0, _lib.PSH_MODE_FILTER | _lib.PSH_FLAG_NOSYNC, None, None, rec)
+    assert _lib.scan_overflowed(ws, 1)
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _lib.merge_topk_packed(rec[None], Tp, flag)
+    assert int(flag.item()) == 1
+    ws = _lib.scan_topk_packed(rows, T, qd, 0, k, 0, _lib.PSH_MODE_FILTER, ws, None, rec)   # synchronous: safe re-run
+    do, io = oracle.shadow_topk(ds, q, k, 0)
+    r = rec.cpu().numpy()
+    assert np.array_equal(r[..., 0].view(np.uint32), do.view(np.uint32)) and np.array_equal(r[..., 1:], io)
+    flag.zero_()
+    _lib.merge_topk_packed(rec[None], Tp, flag)
+    assert int(flag.item()) == 0
+
+
 def test_ties_are_ordered_by_flat_index():
     """Identical rows: every distance value appears R times; order must be (d, r*T'+t)."""
     base, q = make_inputs(1, 600, 40, 1, seed=3)
