@@ -15,7 +15,7 @@ PSH_MODE_FILTER = 1
 PSH_MODE_FFT = 2
 PSH_FLAG_NOSYNC = 0x100
 PSH_E_OVERFLOW = -6
-FFT_MAX_T = 4096
+FFT_MAX_W = 2048   # psh_fft_prepare: context length at most half a 4096-point transform
 
 _lib = None
 

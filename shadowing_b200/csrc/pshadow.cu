@@ -75,9 +75,14 @@ struct ScanParams {
     int epl;               // filter: samples per lane of the squared-prefix pass (odd multiple of 4)
     int pfx_floats;        // filter: floats of the per-warp prefix buffer
     float cw;              // filter: slack coefficient (W + 256) * 2^-24
-    int pair_mode;         // fft flavour: slots enumerate rows of permuted row PAIRS (2*pair + slot&1)
+    int pair_mode;         // fft flavour: slots enumerate the two members of permuted PAIRS of virtual rows
     long long npairs;
     double inv_np;
+    // virtual rows (fft flavour): a trajectory longer than one 4096-point transform is cut into nsegv
+    // overlapping pieces; virtual row v = (row v / nsegv, piece v % nsegv) owns the windows
+    // [piece*hop, piece*hop + span) of its row.  nsegv = 1, span = T' when T <= 4096.
+    int nsegv, hop, span;
+    long long VR;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -226,11 +231,20 @@ __device__ __forceinline__ Task decode_task(const ScanParams &p, unsigned int ta
     long long r = (long long)(prod - q * modn);
     if (r < 0) r += (long long)modn;
     else if (r >= (long long)modn) r -= (long long)modn;
-    if (p.pair_mode) r = 2 * r + (long long)(slot & 1ull);
     Task t;
-    t.tp_eff = r < p.R ? p.Tp : 0;  // the phantom partner of the last row of an odd ensemble
-    t.row = r < p.R ? r : p.R - 1;
-    t.t0 = (int)seg * SEG;
+    if (p.pair_mode) {
+        const long long v = 2 * r + (long long)(slot & 1ull);       // virtual row
+        const long long row = v / p.nsegv;
+        const int piece = (int)(v - row * p.nsegv);
+        t.row = v < p.VR ? row : p.R - 1;
+        t.t0 = piece * p.hop + (int)seg * SEG;
+        t.tp_eff = v < p.VR ? min(p.Tp, piece * p.hop + p.span) : 0;  // phantom partner of an odd count
+        if (t.t0 >= t.tp_eff) { t.t0 = 0; t.tp_eff = 0; }           // nothing of this piece left to scan
+    } else {
+        t.row = r;
+        t.t0 = (int)seg * SEG;
+        t.tp_eff = p.Tp;
+    }
     t.nvalid = min(SEG + p.W - 1, p.T - t.t0);
     return t;
 }
@@ -471,21 +485,30 @@ struct FftAux {            // device pointers into the caller's aux buffer
     float *Y2;             // (R, y2_stride) window energies sum_{j<W} y_{t+j}^2
     long long npairs;
     int y2_stride;
+    int nsegv, hop, span;  // virtual rows, see ScanParams
+    long long VR;
     size_t total;
 };
 
 inline bool fft_aux_layout(long long R, long long T, int W, int H, unsigned char *base, FftAux &a) {
-    if (R <= 0 || T <= 0 || T > fftx::N || W <= 0 || H < 0 || T - W - H + 1 <= 0) return false;
+    if (R <= 0 || T <= 0 || W <= 0 || W > fftx::N / 2 || H < 0 || T - W - H + 1 <= 0) return false;
     const long long Tp = T - W - H + 1;
-    a.npairs = (R + 1) / 2;
-    (void)Tp;
-    a.y2_stride = fftx::N;  // padded with +inf beyond T' so the scan epilogue needs no range checks
+    if (T <= fftx::N) { a.nsegv = 1; a.hop = fftx::N; a.span = (int)Tp; }
+    else {
+        a.hop = (fftx::N - W + 1) & ~3;                   // windows per piece (multiple of 4: TMA alignment)
+        a.span = a.hop;
+        a.nsegv = (int)((Tp + a.hop - 1) / a.hop);
+    }
+    a.VR = R * (long long)a.nsegv;
+    if (a.VR > 0x7fffffffLL) return false;
+    a.npairs = (a.VR + 1) / 2;
+    a.y2_stride = fftx::N;  // padded with +inf beyond the piece's windows: the scan epilogue needs no range checks
     size_t off = 0;
     a.tw32 = reinterpret_cast<float2 *>(base + off); off += sizeof(float2) * fftx::N;
     a.tw64 = reinterpret_cast<double2 *>(base + off); off += sizeof(double2) * fftx::N;
     a.ynorm = reinterpret_cast<float *>(base + off); off += (sizeof(float) * (size_t)a.npairs + 255) / 256 * 256;
     a.Z = reinterpret_cast<float2 *>(base + off); off += sizeof(float2) * fftx::N * (size_t)a.npairs;
-    a.Y2 = reinterpret_cast<float *>(base + off); off += (sizeof(float) * (size_t)R * (size_t)a.y2_stride + 255) / 256 * 256;
+    a.Y2 = reinterpret_cast<float *>(base + off); off += (sizeof(float) * (size_t)a.VR * (size_t)a.y2_stride + 255) / 256 * 256;
     a.total = off;
     return true;
 }
@@ -514,17 +537,21 @@ __global__ void __launch_bounds__(fftx::THREADS) fft_prep_spectra_kernel(const f
     __shared__ float2 ex[fftx::EX_FLOAT2];
     __shared__ double red[fftx::THREADS / 32];
     const int tid = threadIdx.x;
+    (void)R;
     const long long pair = blockIdx.x;
-    const long long ra = 2 * pair, rb = ra + 1;
-    const float *ya = ds + ra * row_stride;
-    const float *yb = ds + (rb < R ? rb : ra) * row_stride;
+    const long long va = 2 * pair, vb = va + 1;
+    const bool has_b = vb < a.VR;
+    const long long rowa = va / a.nsegv, rowb = (has_b ? vb : va) / a.nsegv;
+    const int oa = (int)(va - rowa * a.nsegv) * a.hop, ob = (int)((has_b ? vb : va) - rowb * a.nsegv) * a.hop;
+    const float *ya = ds + rowa * row_stride + oa;
+    const float *yb = ds + rowb * row_stride + ob;
     float2 v[16];
     double e = 0.0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const int n = tid + 256 * i;
-        const float xa = n < T ? ya[n] : 0.0f;
-        const float xb = (n < T && rb < R) ? yb[n] : 0.0f;
+        const float xa = oa + n < T ? ya[n] : 0.0f;
+        const float xb = (ob + n < T && has_b) ? yb[n] : 0.0f;
         v[i] = make_float2(xa, xb);
         e += (double)xa * (double)xa + (double)xb * (double)xb;
     }
@@ -548,13 +575,16 @@ __global__ void __launch_bounds__(fftx::THREADS) fft_prep_y2_kernel(const float 
     __shared__ double pfx[fftx::N + 1];
     __shared__ double wsum[fftx::THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float *y = ds + (long long)blockIdx.x * row_stride;
+    const long long row = (long long)blockIdx.x / a.nsegv;
+    const int piece = (int)((long long)blockIdx.x - row * a.nsegv);
+    const int o0 = piece * a.hop;                     // first sample / window of this virtual row
+    const float *y = ds + row * row_stride + o0;
     double loc[16];
     double run = 0.0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const int n = 16 * tid + i;
-        const double x = n < T ? (double)y[n] : 0.0;
+        const double x = o0 + n < T ? (double)y[n] : 0.0;
         run += x * x;
         loc[i] = run;
     }
@@ -576,7 +606,8 @@ __global__ void __launch_bounds__(fftx::THREADS) fft_prep_y2_kernel(const float 
     // stored at position p = 256 c + 16 a + b for window t = 256 c + 16 b + a (the scan's output order)
     for (int pos = tid; pos < a.y2_stride; pos += fftx::THREADS) {
         const int t = (pos & ~255) | ((pos & 15) << 4) | ((pos >> 4) & 15);
-        o[pos] = t < Tp ? (float)(pfx[t + W] - pfx[t]) : __int_as_float(0x7f800000);
+        const bool mine = t < a.span && o0 + t < Tp;   // the windows this virtual row owns
+        o[pos] = mine ? (float)(pfx[t + W] - pfx[t]) : __int_as_float(0x7f800000);
     }
 }
 
@@ -626,7 +657,8 @@ struct FftScanParams {
     const float2 *tw;
     const float2 *Qc;  // (nq, 4096)
     int Tp, y2_stride, nq;
-    long long npairs, R;
+    int nsegv, hop;
+    long long npairs, VR;
     long long i0, i1;  // pair slots of this launch
     long long perm;
     double inv_np;
@@ -687,7 +719,7 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
         bulk_g2s(smem_u32(Zs), p.Z + (size_t)pair * fftx::N, (uint32_t)(sizeof(float2) * fftx::N), barZ);
     };
     auto issue_y = [&](long long pair) {  // thread 0
-        const long long ra = 2 * pair, rb = (ra + 1 < p.R) ? ra + 1 : ra;
+        const long long ra = 2 * pair, rb = (ra + 1 < p.VR) ? ra + 1 : ra;
         const uint32_t bytes = (uint32_t)(sizeof(float) * p.y2_stride);
         mbar_expect_tx(barY, 2 * bytes);
         bulk_g2s(smem_u32(Y2s), p.Y2 + (size_t)ra * p.y2_stride, bytes, barY);
@@ -710,8 +742,8 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
     for (int iter = 0; slot < p.i1; slot += gridDim.x, ++iter) {
         const long long nslot = slot + gridDim.x;
         const long long npair = nslot < p.i1 ? fft_pair_of_slot(p, nslot) : -1;
-        const long long ra = 2 * pair, rb = ra + 1;
-        const bool has_b = rb < p.R;
+        const long long ra = 2 * pair, rb = ra + 1;   // virtual rows
+        const bool has_b = rb < p.VR;
         const float yn = p.ynorm[pair];
         mbar_wait(barZ, phZ); phZ ^= 1;
         for (int b = 0; b < p.nq; ++b) {
@@ -761,8 +793,11 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
                 basepos = __shfl_sync(FULL, basepos, 31);
                 unsigned int pos = basepos + (unsigned int)(incl - cnt);
                 unsigned int *dst = p.cand + (size_t)b * p.cap;
-                const unsigned int fa = (unsigned int)((unsigned long long)ra * (unsigned long long)p.Tp);
-                const unsigned int fb = (unsigned int)((unsigned long long)rb * (unsigned long long)p.Tp);
+                // flat window index of local window 0 of each virtual row: row * T' + piece * hop
+                const unsigned int fa = (unsigned int)((unsigned long long)(ra / p.nsegv) * (unsigned long long)p.Tp
+                                                       + (unsigned long long)(ra % p.nsegv) * (unsigned long long)p.hop);
+                const unsigned int fb = (unsigned int)((unsigned long long)(rb / p.nsegv) * (unsigned long long)p.Tp
+                                                       + (unsigned long long)(rb % p.nsegv) * (unsigned long long)p.hop);
                 const float hs = s_hscale[b];
                 unsigned int *hq = p.hist + (size_t)b * FFT_NB;
 #pragma unroll
@@ -1588,7 +1623,7 @@ int psh_fft_prepare(const float *d_dataset, int64_t R, int64_t T, int64_t row_st
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!d_dataset || !d_aux || row_stride < T) return PSH_E_ARG;
     FftAux a;
-    if (!fft_aux_layout(R, T, W, H, static_cast<unsigned char *>(d_aux), a)) return T > fftx::N ? PSH_E_UNSUPPORTED : PSH_E_ARG;
+    if (!fft_aux_layout(R, T, W, H, static_cast<unsigned char *>(d_aux), a)) return W > fftx::N / 2 ? PSH_E_UNSUPPORTED : PSH_E_ARG;
     if (aux_bytes < a.total || (reinterpret_cast<uintptr_t>(d_aux) & 255u)) return PSH_E_WORKSPACE;
     // twiddle tables: exp(+2 pi i m / 4096) in fp64, rounded once for the fp32 copy
     static std::vector<double2> h64;
@@ -1606,7 +1641,7 @@ int psh_fft_prepare(const float *d_dataset, int64_t R, int64_t T, int64_t row_st
     PSH_CUDA(cudaMemcpyAsync(a.tw32, h32.data(), sizeof(float2) * fftx::N, cudaMemcpyHostToDevice, stream));
     fft_prep_spectra_kernel<<<(unsigned int)a.npairs, fftx::THREADS, 0, stream>>>(d_dataset, R, (int)T, row_stride, a);
     PSH_LAUNCHED();
-    fft_prep_y2_kernel<<<(unsigned int)R, fftx::THREADS, 0, stream>>>(d_dataset, (int)T, row_stride, W,
+    fft_prep_y2_kernel<<<(unsigned int)a.VR, fftx::THREADS, 0, stream>>>(d_dataset, (int)T, row_stride, W,
                                                                      (int)(T - W - H + 1), a);
     PSH_LAUNCHED();
     return PSH_OK;
@@ -1639,7 +1674,12 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
     }
     ScanParams p;
     p.ds = d_dataset; p.row_stride = row_stride; p.T = (int)T; p.Tp = (int)pl.Tp; p.W = W;
-    p.nseg = (int)((pl.Tp + SEG - 1) / SEG);
+    // tasks per row; in the fft flavour per VIRTUAL row (a piece of `span` windows of a long trajectory)
+    p.nsegv = use_fft ? aux->nsegv : 1;
+    p.hop = use_fft ? aux->hop : 0;
+    p.span = use_fft ? aux->span : (int)pl.Tp;
+    p.VR = use_fft ? aux->VR : R;
+    p.nseg = (int)((p.span + SEG - 1) / SEG);
     p.R = R; p.perm = perm_stride(R);
     p.queries = d_q; p.nq = nq; p.st = st; p.keys = keys; p.cand = cand; p.cap = pl.cap;
     p.bulk_ok = ((reinterpret_cast<uintptr_t>(d_dataset) & 15u) == 0 && (row_stride & 3) == 0) ? 1 : 0;
@@ -1672,14 +1712,15 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
     }
     p.inv_R = 1.0 / (double)R;
     p.pair_mode = use_fft ? 1 : 0;
-    p.npairs = (R + 1) / 2;
+    p.npairs = use_fft ? aux->npairs : (R + 1) / 2;
     p.inv_np = 1.0 / (double)p.npairs;
     if (use_fft) p.perm = perm_stride(p.npairs);
     FftScanParams fp;
     if (use_fft) {
         fp.Z = aux->Z; fp.Y2 = aux->Y2; fp.ynorm = aux->ynorm; fp.tw = aux->tw32; fp.Qc = qspec;
         fp.Tp = (int)pl.Tp; fp.y2_stride = aux->y2_stride; fp.nq = nq;
-        fp.npairs = p.npairs; fp.R = R; fp.perm = p.perm; fp.inv_np = p.inv_np;
+        fp.npairs = p.npairs; fp.VR = aux->VR; fp.nsegv = aux->nsegv; fp.hop = aux->hop;
+        fp.perm = p.perm; fp.inv_np = p.inv_np;
         fp.st = st; fp.cand = cand; fp.cap = pl.cap;
         fp.cf_u = 512.0f * 5.9604644775390625e-8f;
         fp.hist = fhist; fp.k = (unsigned int)k;
@@ -1700,12 +1741,15 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
     // (always exact), then geometric growth; in safe mode every chunk fits the candidate buffer
     // even if all of its windows are appended
     const bool fuse_final = k <= SEL_LIST;                  // last select also sorts and decodes
-    const long long unit = use_fft ? 2 : 1;                 // rows per slot
+    const long long unit = use_fft ? 2 : 1;                 // (virtual) rows per slot
     const long long nslots = use_fft ? p.npairs : R;
+    const long long win_per_slot = unit * (long long)p.span; // windows a slot can contribute at most
     long long done = 0;
-    long long safe_slots = ((long long)pl.cap - k) / (pl.Tp * unit);
+    long long safe_slots = ((long long)pl.cap - k) / win_per_slot;
     if (safe_slots < 1) safe_slots = 1;
-    const long long seed_slots = (pl.n0 + unit - 1) / unit;
+    long long seed_slots = (SEED_FACTOR * k + win_per_slot - 1) / win_per_slot;
+    if (seed_slots < 1) seed_slots = 1;
+    if (seed_slots > nslots) seed_slots = nslots;
     // evenly geometric rounds after the seed: ratio = (nslots/seed)^(1/rounds) <= growth
     double ratio = (double)pl.growth;
     if (nslots > seed_slots) {

@@ -117,7 +117,7 @@ class PathShadowing:
         # every mode returns bit-identical results; they differ in how candidates are filtered:
         #   exact  -- every window with the reference's sub/mul/add sequence
         #   filter -- 1 FMA per element lower bound, exact re-rank of survivors
-        #   fft    -- lower bound through one inverse FFT per trajectory pair (T <= 4096)
+        #   fft    -- lower bound through one inverse 4096-point FFT per pair of trajectory pieces
         #   auto   -- fft when the context is long enough to pay for it, else filter
         self._scan_mode = scan_mode
         self._resident = None  # (key, device rows (R, row_stride), T)
@@ -174,10 +174,12 @@ class PathShadowing:
     def _mode_and_aux(self, rows: torch.Tensor, T: int, W: int, H: int):
         mode = self._scan_mode
         if mode == "auto":
-            mode = "fft" if (T <= _lib.FFT_MAX_T and W >= 64 and T >= 1024) else "filter"
+            # the FFT flavour pays off for long contexts on trajectories that fill a 4096-point
+            # transform reasonably (longer ones are cut into overlapping pieces)
+            mode = "fft" if (64 <= W <= 1024 and T >= 1024) else "filter"
         if mode == "exact":
             return _lib.PSH_MODE_EXACT, None
-        if mode == "filter" or T > _lib.FFT_MAX_T:
+        if mode == "filter" or W > _lib.FFT_MAX_W:
             return _lib.PSH_MODE_FILTER, None
         key = (rows.data_ptr(), tuple(rows.shape), T, W, H)
         if self._fft_aux is None or self._fft_aux[0] != key:

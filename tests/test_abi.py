@@ -39,7 +39,8 @@ def test_version_errors_and_workspace_sizing():
     # null pointers are rejected before any device work
     assert L.psh_scan_topk_f32(None, 1, 100, 100, None, 1, 10, 0, 1, 0, 0, None, None, None, 0, None, 0, None) == -1
     assert L.psh_fft_aux_bytes(32768, 4096, 252, 20) > 2 * 32768 * 4096 * 4 // 2
-    assert L.psh_fft_aux_bytes(8, 8192, 252, 20) == 0   # T > 4096: fft flavour unsupported
+    assert L.psh_fft_aux_bytes(8, 8192, 252, 20) > 3 * 8 * 4096 * 4   # T > 4096: three overlapping pieces per row
+    assert L.psh_fft_aux_bytes(8, 8192, 3000, 20) == 0                # context longer than half a transform
     assert L.psh_gather_paths(None, 1, 1, 1, None, 1, 0, 1, None, None) == -1
     assert L.psh_merge_topk(None, None, 1, 1, 1, 1, None, None, None) == -1
     assert L.psh_scan_overflowed(None, 1, None) == -1

@@ -40,6 +40,8 @@ def test_golden_shadow_bit_exact(golden, mode):
     (2048, 512, 20, 20, 16, 40),      # many queries: several query groups
     (5, 300, 252, 20, 1, 2),          # k = 1, fewer rows than seed rows
     (16, 2000, 1, 0, 9, 2),           # W = 1
+    (24, 8192, 252, 20, 500, 2),      # T > 4096: the fft flavour cuts rows into overlapping pieces
+    (7, 12001, 100, 0, 300, 1),       # odd number of virtual rows, ragged last piece
 ])
 def test_oracle_parity_seeded(R, T, W, H, k, B, mode):
     ds, q = make_inputs(R, T, W, B, seed=100 + R)
