@@ -1,7 +1,7 @@
 """Averaging probabilities over the k shadowing paths.
 
 The reference imports `Softmax`, `Uniform`, `DiscreteProba` from the un-vendored
-`scatspectra` v2.0.2 (path_shadowing.py:9); their source is not under /root/reference, so the
+`scatspectra` v2.0.2 (path_shadowing.py:9); their source is not in the reference tree, so the
 weight formula here is PARITY-UNPINNED: w ∝ exp(-d² / (2 η²)) -- "the width of a Gaussian in
 the Gaussian average" (plot_utils.py:59-65).  It is isolated in `softmax_weights`.
 Call-site contracts honoured (path_shadowing.py:228-230,251-252; plot_utils.py:74-76):

@@ -1051,6 +1051,7 @@ __device__ unsigned long long select_generic(const unsigned long long *src, unsi
                 if (tid >= o) incl += v;
             }
             unsigned int excl = incl - sum;
+            __syncwarp();  // every lane has read *s_need / *s_prefix before one lane rewrites them
             if (excl < need && need <= incl) {  // exactly one lane
                 unsigned int cc = excl;
 #pragma unroll

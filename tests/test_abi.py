@@ -139,3 +139,12 @@ def test_no_cpu_fallback_without_device():
     obj = sb.PathShadowing(sb.Identity(8), sb.RelativeMSE(), np.zeros((2, 1, 64), np.float32), sb.PredictionContext(2))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         obj.shadow(np.ones((1, 1, 8), np.float32), k=2)
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under shadowing_b200/ may import, load or call it."""
+    pkg = ROOT / "shadowing_b200"
+    for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("Makefile")):
+        text = f.read_text()
+        assert "oracle" not in text.lower(), f"{f} mentions the oracle"
+        assert "/root/reference" not in text, f"{f} reads the reference tree"
