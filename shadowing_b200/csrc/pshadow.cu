@@ -15,6 +15,7 @@
 #include <stdint.h>
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <vector>
@@ -132,11 +133,17 @@ __device__ __forceinline__ float dist_from_s(float s, float qn) { return __fdiv_
 // query preparation: ||q|| in torch's contiguous-reduction order (8 interleaved partial sums,
 // lanes added 0..7, scalar tail), state reset.  path_distance.py:65 `x.norm(dim=-1)`.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) qprep_kernel(const float *__restrict__ q, int W, int nq, QState *st) {
+__global__ void __launch_bounds__(128) qprep_kernel(const float *__restrict__ q, int W, int nq, QState *st,
+                                                    uint4 *zero_a, int zero_a_vec4, uint4 *zero_b, int zero_b_vec4) {
     // one warp per query; lanes 0..7 own torch's 8 interleaved partial sums
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (b >= nq) return;
+    // fft flavour: this query's in-launch threshold histogram and seed histogram + ticket start at zero
+    if (zero_a != nullptr)
+        for (int i = lane; i < zero_a_vec4; i += 32) zero_a[(size_t)b * zero_a_vec4 + i] = make_uint4(0u, 0u, 0u, 0u);
+    if (zero_b != nullptr)
+        for (int i = lane; i < zero_b_vec4; i += 32) zero_b[(size_t)b * zero_b_vec4 + i] = make_uint4(0u, 0u, 0u, 0u);
     const float *x = q + (size_t)b * W;
     const int n8 = (W / 8) * 8;
     float acc = 0.0f;
@@ -649,6 +656,12 @@ __global__ void __launch_bounds__(4 * QFFT_K) qfft_kernel(const float *__restric
 
 constexpr int FFT_NB = 2048;      // bins of the in-launch threshold histogram
 constexpr int FFT_REFRESH = 4;    // pairs between two threshold refreshes of a CTA
+// seed launch (fft_scan_kernel<.., SEED = true>): histogram of per-thread minima of the upper bound
+// over one wave of row pairs.  Bins are logarithmic -- the upper 16 bits of the float (8 exponent +
+// 7 mantissa bits: 0.8 % wide), SEED_NB of them centred on Q2, i.e. 16 binades either side -- so no
+// range estimate is needed before the first window has been looked at.
+constexpr int SEED_NB = 4096;
+constexpr int SEED_STRIDE = SEED_NB + 32;   // uints per query: bins, then the launch's CTA ticket
 
 struct FftScanParams {
     const float2 *Z;
@@ -672,6 +685,7 @@ struct FftScanParams {
     unsigned int *hist;
     unsigned int k;
     float widen2;      // (1 + 2 (W+8) u)^2 (1 + 1e-6): exact-sequence rounding, both directions
+    unsigned int *seed;  // (nq, SEED_STRIDE) seed histograms + ticket (seed launch only)
 };
 
 // One CTA per row pair: Z * conj(Q)/N -> inverse FFT -> (D_a[t], D_b[t]) for t = tid + 256 c.
@@ -691,7 +705,14 @@ __device__ __forceinline__ long long fft_pair_of_slot(const FftScanParams &p, lo
     return pair;
 }
 
-template <bool SINGLEQ>
+//
+// SEED = true (the seed launch of the seedless schedule): no window is appended.  Every thread
+// folds the upper bounds UB = LB + 2 slack of its 32 windows into their minimum and adds it to the
+// query's logarithmic seed histogram; the last CTA to finish finds the bin edge below which k
+// minima lie -- k distinct windows whose exact squared distance is <= edge -- and publishes
+// thr_fast = edge * widen2: the threshold the main launch over ALL pairs starts from (and
+// tightens further by itself).  This replaces two exact seed rounds and two selects.
+template <bool SINGLEQ, bool SEED>
 __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftScanParams p) {
     extern __shared__ __align__(128) unsigned char fsm[];
     float2 *Zs = reinterpret_cast<float2 *>(fsm);
@@ -710,7 +731,7 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
     if (tid < p.nq) {
         const float t0 = ld_volatile_f32(&p.st[tid].thr_fast);
         s_thrq[tid] = t0;
-        s_hscale[tid] = (p.hist != nullptr && t0 > 0.0f && t0 < __int_as_float(0x7f800000)) ? (float)FFT_NB / t0 : 0.0f;
+        s_hscale[tid] = (!SEED && p.hist != nullptr && t0 > 0.0f && t0 < __int_as_float(0x7f800000)) ? (float)FFT_NB / t0 : 0.0f;
     }
     __syncthreads();
 
@@ -727,7 +748,7 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
     };
 
     long long slot = p.i0 + blockIdx.x;
-    if (slot >= p.i1) return;
+    if (!SEED && slot >= p.i1) return;   // (a seed launch has one CTA per slot; all of them take a ticket)
     long long pair = fft_pair_of_slot(p, slot);
     if (tid == 0) { issue_z(pair); issue_y(pair); }
 
@@ -767,6 +788,29 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
             const float thr = s_thrq[b];
             const float slack = (2.0f * p.cf_u * qmax * yn + 4.76837158203125e-7f * (q2 + yn * yn)) * 1.0001f;
             const float base0 = q2 - slack;   // LB = (Y2 - 2 D^) + base0, kept iff LB <= thr
+            if (SEED) {
+                // min over the thread's windows of (Y2 - 2 D^); adding the constants afterwards is
+                // the same as taking the min of the UBs (fp addition is monotone)
+                float mn = __int_as_float(0x7f800000);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const int pos = tid + 256 * c;
+                    mn = fminf(mn, fmaf(-2.0f, v[c].x, Y2s[pos]));
+                    if (has_b) mn = fminf(mn, fmaf(-2.0f, v[c].y, Y2s[fftx::N + pos]));
+                }
+                const float ub = fmaxf((mn + base0) + 2.0f * slack, 0.0f);
+                const bool act = ub < __int_as_float(0x7f800000);   // false for +inf (no valid window) and NaN
+                int bin = (int)(__float_as_uint(ub) >> 16) - ((int)(__float_as_uint(q2) >> 16) - SEED_NB / 2);
+                bin = bin < 0 ? 0 : (bin > SEED_NB - 1 ? SEED_NB - 1 : bin);
+                const unsigned int am = __ballot_sync(FULL, act);
+                if (act) {
+                    const unsigned int peers = __match_any_sync(am, bin);
+                    if (lane == __ffs(peers) - 1)
+                        atomicAdd(&p.seed[(size_t)b * SEED_STRIDE + bin], (unsigned int)__popc(peers));
+                }
+                __syncthreads();  // ex (and, after the last query, the energy rows) may be overwritten
+                continue;
+            }
             unsigned int mask = 0;
             // v[c] belongs to window t = (tid>>4) + 16 (tid&15) + 256 c; the energy rows are stored
             // in that order (position tid + 256 c) and padded with +inf beyond T': no range checks
@@ -828,7 +872,7 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
         if (tid == 0 && npair >= 0) issue_y(npair);
         // threshold refresh: k windows with UB <= edge exist  =>  the k-th exact distance of the whole
         // ensemble is <= edge (1+gamma)  =>  filtering with edge * widen2 loses nothing
-        if (p.hist != nullptr && (iter < 2 || (iter % FFT_REFRESH) == FFT_REFRESH - 1) && npair >= 0) {
+        if (!SEED && p.hist != nullptr && (iter < 2 || (iter % FFT_REFRESH) == FFT_REFRESH - 1) && npair >= 0) {
             for (int b = 0; b < p.nq; ++b) {
                 const float hs = s_hscale[b];
                 if (!(hs > 0.0f)) continue;  // CTA-uniform
@@ -869,6 +913,52 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
             }
         }
         pair = npair;
+    }
+    if (SEED) {
+        // last CTA done: every other CTA's histogram increments are visible behind its fence + ticket
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_edge = atomicAdd(&p.seed[SEED_NB], 1u);
+        __syncthreads();
+        if (s_edge != gridDim.x - 1) return;
+        __threadfence();
+        constexpr int PER = SEED_NB / fftx::THREADS;
+        for (int b = 0; b < p.nq; ++b) {
+            __syncthreads();
+            const uint4 *h4 = reinterpret_cast<const uint4 *>(p.seed + (size_t)b * SEED_STRIDE) + tid * (PER / 4);
+            unsigned int loc[PER];
+#pragma unroll
+            for (int i = 0; i < PER / 4; ++i) {
+                const uint4 x = __ldcg(h4 + i);
+                loc[4 * i] = x.x; loc[4 * i + 1] = x.y; loc[4 * i + 2] = x.z; loc[4 * i + 3] = x.w;
+            }
+            unsigned int sum = 0;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) sum += loc[i];
+            unsigned int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int u = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += u;
+            }
+            if (lane == 31) s_wsum[tid >> 5] = incl;
+            __syncthreads();
+            unsigned int cum = incl - sum;
+            for (int w = 0; w < (tid >> 5); ++w) cum += s_wsum[w];
+            if (cum < p.k && p.k <= cum + sum) {  // at most one thread; none: fewer than k minima -> thr stays +inf
+                int bin = 0;
+#pragma unroll
+                for (int i = 0; i < PER; ++i) {
+                    if (cum < p.k && p.k <= cum + loc[i]) bin = tid * PER + i;
+                    cum += loc[i];
+                }
+                // upper edge of the bin (exclusive); the clamped top bin has no finite edge
+                const int eb = (int)(__float_as_uint(p.st[b].q2) >> 16) - SEED_NB / 2 + bin + 1;
+                float thr = __int_as_float(0x7f800000);
+                if (bin < SEED_NB - 1 && eb > 0 && eb < 0x7f80) thr = __uint_as_float((unsigned int)eb << 16) * p.widen2;
+                p.st[b].thr_fast = thr;
+            }
+        }
     }
 }
 
@@ -1497,7 +1587,7 @@ struct Plan {
     unsigned int cap;
     long long n0;      // rows of the seeding chunk
     int growth;
-    size_t off_state, off_keys, off_cand, off_qspec, off_hist, total;
+    size_t off_state, off_keys, off_cand, off_qspec, off_hist, off_seed, total;
 };
 
 constexpr int SEED_FACTOR = 16;  // seeding chunk holds ~16 k windows
@@ -1527,7 +1617,8 @@ bool make_plan(long long R, long long T, int B, int W, int H, long long k, Plan 
     pl.off_cand = pl.off_keys + (size_t)B * 2 * (size_t)pl.cap * sizeof(unsigned long long);
     pl.off_qspec = pl.off_cand + align_up((size_t)B * (size_t)pl.cap * sizeof(unsigned int), 256);
     pl.off_hist = pl.off_qspec + (size_t)B * fftx::N * sizeof(float2);  // query spectra (fft flavour)
-    pl.total = pl.off_hist + (size_t)B * FFT_NB * sizeof(unsigned int);  // in-launch threshold histograms
+    pl.off_seed = pl.off_hist + (size_t)B * FFT_NB * sizeof(unsigned int);  // in-launch threshold histograms
+    pl.total = pl.off_seed + (size_t)B * SEED_STRIDE * sizeof(unsigned int);  // seed histograms + tickets
     return true;
 }
 
@@ -1540,6 +1631,12 @@ int sm_count() {
         if (g_sm_count <= 0) g_sm_count = 148;
     }
     return g_sm_count;
+}
+
+// A/B switch for measurements: PSH_SEEDLESS=0 keeps the exact-seeded chunk schedule everywhere
+bool seedless_enabled() {
+    const char *e = getenv("PSH_SEEDLESS");  // read per call: tests toggle it
+    return !(e != nullptr && e[0] == '0');
 }
 
 // optional per-kernel timing (bench.py's roofline leg): CUDA events on the caller's stream
@@ -1657,16 +1754,35 @@ int psh_debug_fft4096(const void *d_in, void *d_out, int n, int dir, const void 
     return PSH_OK;
 }
 
+// final ordering of the k keys when it was not fused into the last select (k > SEL_LIST)
+static int launch_finalize(const Plan &pl, QState *st, unsigned long long *keys, int nq, long long k, int row_offset,
+                           float *d_out_dist, int *d_out_idx, cudaStream_t stream) {
+    unsigned int npow2 = 1; while (npow2 < (unsigned int)k) npow2 <<= 1;
+    int use_smem = npow2 <= SORT_SMEM_MAX ? 1 : 0;
+    size_t fsmem = use_smem ? (size_t)npow2 * sizeof(unsigned long long) : 0;
+    if (fsmem > 48 * 1024)
+        PSH_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    {
+        ProfScope ps(stream, 1);
+        finalize_kernel<<<nq, SEL_THREADS, fsmem, stream>>>(st, keys, pl.cap, (unsigned int)k, npow2, use_smem,
+                                                            (unsigned int)pl.Tp, row_offset, d_out_dist, d_out_idx);
+    }
+    PSH_LAUNCHED();
+    return PSH_OK;
+}
+
 static int run_scan_group(const float *d_dataset, long long R, long long T, long long row_stride,
                           const float *d_q, int nq, int W, int H, long long k, int row_offset,
                           const Plan &pl, QState *st, unsigned long long *keys, unsigned int *cand, float2 *qspec,
-                          unsigned int *fhist, const FftAux *aux, int mode, bool safe, float *d_out_dist, int *d_out_idx,
-                          cudaStream_t stream) {
+                          unsigned int *fhist, unsigned int *shist, const FftAux *aux, int mode, bool safe,
+                          float *d_out_dist, int *d_out_idx, cudaStream_t stream) {
     (void)H;
-    qprep_kernel<<<(nq + 3) / 4, 128, 0, stream>>>(d_q, W, nq, st);
+    const bool use_fft = (mode == PSH_MODE_FFT) && !safe && aux != nullptr;
+    qprep_kernel<<<(nq + 3) / 4, 128, 0, stream>>>(d_q, W, nq, st,
+                                                   use_fft ? reinterpret_cast<uint4 *>(fhist) : nullptr, FFT_NB / 4,
+                                                   use_fft ? reinterpret_cast<uint4 *>(shist) : nullptr, SEED_STRIDE / 4);
     PSH_LAUNCHED();
 
-    const bool use_fft = (mode == PSH_MODE_FFT) && !safe && aux != nullptr;
     const bool filter = (mode == PSH_MODE_FILTER || (mode == PSH_MODE_FFT && !use_fft)) && !safe;
     if (use_fft) {
         qfft_kernel<<<dim3(fftx::N / QFFT_K, nq), 4 * QFFT_K, (size_t)W * sizeof(double), stream>>>(
@@ -1734,14 +1850,63 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
                                           + sizeof(float2) * fftx::EX2_FLOAT2 + 16
                                     : 0;
     if (use_fft) {
-        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
-        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+    }
+    const bool fuse_final = k <= SEL_LIST;                  // last select also sorts and decodes
+
+    // ---- seedless schedule (large ensembles): seed launch -> ONE launch over all pairs -> exact
+    // re-rank of the survivors -> select.  The seed launch turns one wave of row pairs into a
+    // valid starting threshold (see fft_scan_kernel<.., SEED>), so no exact seed round, no
+    // intermediate select and no exact threshold exist before the final select: the re-rank keeps
+    // every survivor (s_thr = +inf, tau = ~0 from qprep) and the select picks the k best keys.
+    if (use_fft && seedless_enabled()) {
+        long long nseed = (long long)sm_count() * 2;
+        if (nseed > p.npairs / 8) nseed = p.npairs / 8;
+        if (nseed >= 1 && nseed * (long long)fftx::THREADS >= 8 * k) {
+            fp.seed = shist;
+            fp.i0 = 0; fp.i1 = nseed;
+            {
+                ProfScope ps(stream, 0);
+                if (nq == 1) fft_scan_kernel<true, true><<<(unsigned int)nseed, fftx::THREADS, smem_fft, stream>>>(fp);
+                else fft_scan_kernel<false, true><<<(unsigned int)nseed, fftx::THREADS, smem_fft, stream>>>(fp);
+            }
+            PSH_LAUNCHED();
+            fp.i0 = 0; fp.i1 = p.npairs;
+            long long ctas = p.npairs;
+            const long long max_ctas = (long long)sm_count() * 2;
+            if (ctas > max_ctas) ctas = max_ctas;
+            {
+                ProfScope ps(stream, 0);
+                if (nq == 1) fft_scan_kernel<true, false><<<(unsigned int)ctas, fftx::THREADS, smem_fft, stream>>>(fp);
+                else fft_scan_kernel<false, false><<<(unsigned int)ctas, fftx::THREADS, smem_fft, stream>>>(fp);
+            }
+            PSH_LAUNCHED();
+            unsigned int rb = (pl.cap + RR_THREADS - 1) / RR_THREADS;
+            const unsigned int rb_max = (unsigned int)sm_count() * 2u;
+            if (rb > rb_max) rb = rb_max;
+            {
+                ProfScope ps(stream, 1);
+                rerank_kernel<<<dim3(rb, nq), RR_THREADS, smem_rr, stream>>>(
+                    d_dataset, row_stride, (unsigned int)pl.Tp, W, d_q, st, cand, keys, pl.cap);
+            }
+            PSH_LAUNCHED();
+            {
+                ProfScope ps(stream, 1);
+                select_kernel<<<nq, SEL_THREADS, 0, stream>>>(st, keys, pl.cap, (unsigned int)k, W, fuse_final ? 1 : 0,
+                                                              (unsigned int)pl.Tp, row_offset, d_out_dist, d_out_idx, nullptr);
+            }
+            PSH_LAUNCHED();
+            if (fuse_final) return PSH_OK;
+            return launch_finalize(pl, st, keys, nq, k, row_offset, d_out_dist, d_out_idx, stream);
+        }
     }
 
     // chunk schedule over permuted slots (rows, or row pairs in the fft flavour): seed chunk
     // (always exact), then geometric growth; in safe mode every chunk fits the candidate buffer
     // even if all of its windows are appended
-    const bool fuse_final = k <= SEL_LIST;                  // last select also sorts and decodes
     const long long unit = use_fft ? 2 : 1;                 // (virtual) rows per slot
     const long long nslots = use_fft ? p.npairs : R;
     const long long win_per_slot = unit * (long long)p.span; // windows a slot can contribute at most
@@ -1775,8 +1940,8 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
             if (ctas > max_ctas) ctas = max_ctas;
             {
                 ProfScope ps(stream, 0);
-                if (nq == 1) fft_scan_kernel<true><<<(unsigned int)ctas, fftx::THREADS, smem_fft, stream>>>(fp);
-                else fft_scan_kernel<false><<<(unsigned int)ctas, fftx::THREADS, smem_fft, stream>>>(fp);
+                if (nq == 1) fft_scan_kernel<true, false><<<(unsigned int)ctas, fftx::THREADS, smem_fft, stream>>>(fp);
+                else fft_scan_kernel<false, false><<<(unsigned int)ctas, fftx::THREADS, smem_fft, stream>>>(fp);
             }
             PSH_LAUNCHED();
         } else {
@@ -1818,18 +1983,7 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
         done = next;
     }
     if (fuse_final) return PSH_OK;
-    unsigned int npow2 = 1; while (npow2 < (unsigned int)k) npow2 <<= 1;
-    int use_smem = npow2 <= SORT_SMEM_MAX ? 1 : 0;
-    size_t fsmem = use_smem ? (size_t)npow2 * sizeof(unsigned long long) : 0;
-    if (fsmem > 48 * 1024)
-        PSH_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-    {
-        ProfScope ps(stream, 1);
-        finalize_kernel<<<nq, SEL_THREADS, fsmem, stream>>>(st, keys, pl.cap, (unsigned int)k, npow2, use_smem,
-                                                            (unsigned int)pl.Tp, row_offset, d_out_dist, d_out_idx);
-    }
-    PSH_LAUNCHED();
-    return PSH_OK;
+    return launch_finalize(pl, st, keys, nq, k, row_offset, d_out_dist, d_out_idx, stream);
 }
 
 int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride,
@@ -1858,6 +2012,7 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
     unsigned int *cand = reinterpret_cast<unsigned int *>(ws + pl.off_cand);
     float2 *qspec = reinterpret_cast<float2 *>(ws + pl.off_qspec);
     unsigned int *fhist_all = reinterpret_cast<unsigned int *>(ws + pl.off_hist);
+    unsigned int *shist_all = reinterpret_cast<unsigned int *>(ws + pl.off_seed);
     FftAux aux;
     const FftAux *auxp = nullptr;
     if (mode == PSH_MODE_FFT && d_aux != nullptr) {
@@ -1870,7 +2025,7 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
     for (int g0 = 0; g0 < B; g0 += QG_MAX) {
         int nq = B - g0 < QG_MAX ? B - g0 : QG_MAX;
         int rc = run_scan_group(d_dataset, R, T, row_stride, d_queries + (size_t)g0 * W, nq, W, H, k, row_offset,
-                                pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap, qspec + (size_t)g0 * fftx::N, fhist_all + (size_t)g0 * FFT_NB, auxp, mode, false,
+                                pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap, qspec + (size_t)g0 * fftx::N, fhist_all + (size_t)g0 * FFT_NB, shist_all + (size_t)g0 * SEED_STRIDE, auxp, mode, false,
                                 d_out_dist + (size_t)g0 * k * (d_out_idx ? 1 : 3),
                                 d_out_idx ? d_out_idx + (size_t)g0 * k * 2 : nullptr, stream);
         if (rc != PSH_OK) return rc;
@@ -1886,7 +2041,7 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
         for (int i = 0; i < nq; ++i) ovf = ovf || hst[i].overflow != 0;
         if (ovf) {
             int rc = run_scan_group(d_dataset, R, T, row_stride, d_queries + (size_t)g0 * W, nq, W, H, k, row_offset,
-                                    pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap, qspec + (size_t)g0 * fftx::N, fhist_all + (size_t)g0 * FFT_NB, auxp, mode,
+                                    pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap, qspec + (size_t)g0 * fftx::N, fhist_all + (size_t)g0 * FFT_NB, shist_all + (size_t)g0 * SEED_STRIDE, auxp, mode,
                                     true,
                                     d_out_dist + (size_t)g0 * k * (d_out_idx ? 1 : 3),
                                 d_out_idx ? d_out_idx + (size_t)g0 * k * 2 : nullptr, stream);

@@ -320,3 +320,83 @@ def test_full_size_properties_cfg2():
     for dist_, (rr, tt) in zip(do[0], io[0]):
         if dist_ < d[0, -1]:
             assert (int(rows[rr]), int(tt)) in got
+
+
+# ---------------------------------------------------------------------------------------------
+# seedless fft schedule (large ensembles): seed launch -> one launch over all pairs -> re-rank ->
+# select.  Results must be bit-identical to the oracle and to the exact-seeded chunk schedule.
+# ---------------------------------------------------------------------------------------------
+def _shadow_both_schedules(ds, q, W, H, k, monkeypatch):
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("PSH_SEEDLESS", flag)
+        obj = _obj(ds, W, H or None, scan_mode="fft")
+        obj.shadow(q[:1], k=k)  # residency + fft aux
+        n0 = _lib.launch_count()
+        out[flag] = obj.shadow(q, k=k) + (_lib.launch_count() - n0,)
+    return out
+
+
+@pytest.mark.parametrize("R,T,W,H,k,B", [
+    (2048, 4096, 252, 20, 1024, 1),   # north-star window/k, 1024 row pairs
+    (2048, 4096, 252, 20, 1024, 3),   # several queries share the seed and the main launch
+    (1100, 8192, 100, 0, 300, 2),     # virtual rows (T > 4096), no horizon
+    (4096, 1024, 64, 8, 4096, 1),     # k at the limit of the fused final sort
+    (4099, 1500, 80, 5, 5000, 1),     # k > SEL_LIST: separate finalise kernel, odd number of rows
+])
+def test_seedless_schedule_bit_exact(R, T, W, H, k, B, monkeypatch):
+    ds, q = make_inputs(R, T, W, B, seed=700 + R)
+    out = _shadow_both_schedules(ds, q, W, H, k, monkeypatch)
+    do, po, io = oracle.shadow(ds, q, k, H)
+    for flag in ("1", "0"):
+        d, paths, idx, _ = out[flag]
+        assert_topk_equal(d, idx, do, io)
+        assert np.array_equal(paths, po)
+    # the seedless schedule really ran: qprep, qfft, seed, scan, rerank, select (+finalise) + gather
+    assert out["1"][3] < out["0"][3] and out["1"][3] <= 8
+
+
+def test_seedless_scale_mismatch_recovers(monkeypatch):
+    """Dataset 1000x the query's scale: every upper bound lies beyond the seed histogram's 16
+    binades above Q2, the seed threshold stays +inf, the candidate buffer overflows and the safe
+    schedule must still return the exact answer."""
+    monkeypatch.setenv("PSH_SEEDLESS", "1")
+    R, T, W, H, k = 2048, 2048, 64, 4, 128
+    ds, q = make_inputs(R, T, W, 1, seed=77)
+    ds = ds * 1000.0
+    d, _, idx = _obj(ds, W, H, scan_mode="fft").shadow(q, k=k)
+    do, io = oracle.shadow_topk(ds, q, k, H)
+    assert_topk_equal(d, idx, do, io)
+
+
+def test_seedless_many_near_copies(monkeypatch):
+    """More than k windows closer than 2^-8 ||q|| (below the seed histogram's lowest bin): the seed
+    threshold is the lowest bin's edge and the main launch tightens it by itself."""
+    monkeypatch.setenv("PSH_SEEDLESS", "1")
+    R, T, W, H, k = 2048, 2048, 64, 0, 512
+    ds, q = make_inputs(R, T, W, 1, seed=78)
+    rng = np.random.default_rng(5)
+    reps = np.tile(q[0, 0], T // W)
+    ds[::2, 0, :] = reps[None, :] * (1.0 + 1e-4 * rng.standard_normal((R // 2, T)).astype(np.float32))
+    d, _, idx = _obj(ds, W, None, scan_mode="fft").shadow(q, k=k)
+    do, io = oracle.shadow_topk(ds, q, k, H)
+    assert_topk_equal(d, idx, do, io)
+
+
+def test_seedless_adversarial_seed_pairs(monkeypatch):
+    """The seed wave only sees far rows, everything else is near: thresholds start loose, the
+    in-launch tightening (or, failing that, the overflow re-run) must keep the answer exact."""
+    monkeypatch.setenv("PSH_SEEDLESS", "1")
+    R, T, W, H, k = 4096, 1024, 32, 0, 64
+    ds, q = make_inputs(R, T, W, 1, seed=79)
+    npairs = R // 2
+    P = _perm_stride(npairs)
+    nseed = min(2 * torch.cuda.get_device_properties(0).multi_processor_count, npairs // 8)
+    ds = ds * 1e-3
+    for i in range(nseed):
+        pr = (i * P) % npairs
+        ds[2 * pr] *= 1e5
+        ds[2 * pr + 1] *= 1e5
+    d, _, idx = _obj(ds, W, None, scan_mode="fft").shadow(q, k=k)
+    do, io = oracle.shadow_topk(ds, q, k, H)
+    assert_topk_equal(d, idx, do, io)
