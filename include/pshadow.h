@@ -80,9 +80,11 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
                       float *d_out_dist, int32_t *d_out_idx,
                       void *d_ws, size_t ws_bytes, const void *d_aux, size_t aux_bytes, void *stream);
 
-/* After a PSH_FLAG_NOSYNC scan (and whatever the caller enqueued behind it): synchronise the
- * stream and report PSH_OK, or PSH_E_OVERFLOW if a candidate buffer overflowed (adversarially
- * ordered data) -- then the outputs are invalid and the scan must be repeated without the flag. */
+/* After one or more PSH_FLAG_NOSYNC scans on the same workspace (and whatever the caller enqueued
+ * behind them): synchronise the stream and report PSH_OK, or PSH_E_OVERFLOW if a candidate buffer
+ * overflowed in ANY of those scans since the previous check (adversarially ordered data; the
+ * flag is sticky in the workspace and cleared by this call) -- then their outputs are invalid
+ * and they must be repeated without the flag. */
 int psh_scan_overflowed(const void *d_ws, int B, void *stream);
 
 /*

@@ -50,8 +50,11 @@ struct QState {
     float thr_fast;              // s_thr widened by the exact sequence's own rounding (filter compare)
     float q2;                    // sum q_j^2 (fp64 accumulated, rounded once)
     float qmax;                  // max_k |FFT(q)_k| (fft flavour), rounded up
-    unsigned int pad[5];
+    unsigned int sticky;         // overflow of ANY scan since the last psh_scan_overflowed(): survives qprep,
+    unsigned int magic;          // valid only while magic == QSTATE_MAGIC (the workspace starts as garbage)
+    unsigned int pad[3];
 };
+constexpr unsigned int QSTATE_MAGIC = 0x50534831u;
 static_assert(sizeof(QState) == 64, "QState layout");
 
 struct ScanParams {
@@ -159,6 +162,8 @@ __global__ void __launch_bounds__(128) qprep_kernel(const float *__restrict__ q,
     for (int o = 16; o > 0; o >>= 1) q2 += __shfl_xor_sync(FULL, q2, o);
     if (lane == 0) {
         QState z;
+        z.sticky = (st[b].magic == QSTATE_MAGIC) ? st[b].sticky : 0u;
+        z.magic = QSTATE_MAGIC;
         z.tau_key = ~0ull;
         z.s_thr = __int_as_float(0x7f800000);
         z.qnorm = __fsqrt_rn(s);
@@ -169,7 +174,7 @@ __global__ void __launch_bounds__(128) qprep_kernel(const float *__restrict__ q,
         z.thr_fast = __int_as_float(0x7f800000);
         z.q2 = (float)q2;
         z.qmax = 0.0f;
-        for (int i = 0; i < 5; ++i) z.pad[i] = 0;
+        for (int i = 0; i < 3; ++i) z.pad[i] = 0;
         st[b] = z;
     }
 }
@@ -996,7 +1001,7 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(const float *__restr
     QState *st = st_all + b;
     const unsigned int craw = st->ccount;
     const unsigned int C = min(craw, cap);
-    if (craw > cap && threadIdx.x == 0 && blockIdx.x == 0) st->overflow = 1;
+    if (craw > cap && threadIdx.x == 0 && blockIdx.x == 0) { st->overflow = 1; st->sticky = 1; }
     const unsigned int groups = (C + 31u) / 32u;
     if (blockIdx.x * RR_WARPS >= groups) return;
     for (int j = threadIdx.x; j < W; j += RR_THREADS) qsh[j] = queries[(size_t)b * W + j];
@@ -1195,7 +1200,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(QState *st_all, uns
     unsigned long long *dst = keys_all + ((size_t)blockIdx.x * 2 + (cur ^ 1)) * cap;
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) {
-        if (cnt_raw > cap) st->overflow = 1;
+        if (cnt_raw > cap) { st->overflow = 1; st->sticky = 1; }
         s_min = 0xffffffffu; s_max = 0u; s_out = 0; s_nlist = 0; s_fast = 0;
     }
     const unsigned long long *kept = src;  // where the k (or M <= k) surviving keys live
@@ -1633,6 +1638,24 @@ int sm_count() {
     return g_sm_count;
 }
 
+// pinned host staging for the end-of-call status read (per thread, grown on demand, never freed)
+QState *host_stage(int n) {
+    static thread_local QState *buf = nullptr;
+    static thread_local int cap = 0;
+    if (n > cap) {
+        if (buf != nullptr) cudaFreeHost(buf);
+        buf = nullptr; cap = 0;
+        const int want = n < QG_MAX ? QG_MAX : n;
+        if (cudaHostAlloc(reinterpret_cast<void **>(&buf), sizeof(QState) * (size_t)want, cudaHostAllocDefault) != cudaSuccess) {
+            buf = nullptr;
+            cudaGetLastError();
+            return nullptr;
+        }
+        cap = want;
+    }
+    return buf;
+}
+
 // A/B switch for measurements: PSH_SEEDLESS=0 keeps the exact-seeded chunk schedule everywhere
 bool seedless_enabled() {
     const char *e = getenv("PSH_SEEDLESS");  // read per call: tests toggle it
@@ -1752,6 +1775,11 @@ int psh_debug_fft4096(const void *d_in, void *d_out, int n, int dir, const void 
                                                       static_cast<const float2 *>(d_aux), dir);
     PSH_LAUNCHED();
     return PSH_OK;
+}
+
+static __global__ void clear_sticky_kernel(QState *st, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st[i].sticky = 0u;
 }
 
 // final ordering of the k keys when it was not fused into the last select (k > SEL_LIST)
@@ -2032,13 +2060,15 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
     }
     if (nosync) return PSH_OK;  // the caller checks psh_scan_overflowed() before trusting the results
     // one synchronisation: did any candidate buffer overflow (adversarially ordered data)?
-    static thread_local QState hst[QG_MAX];
+    QState *hst = host_stage(B);
+    if (hst == nullptr) return (int)cudaErrorMemoryAllocation;
+    PSH_CUDA(cudaMemcpyAsync(hst, st, sizeof(QState) * B, cudaMemcpyDeviceToHost, stream));
+    PSH_CUDA(cudaStreamSynchronize(stream));
+    bool redone = false;
     for (int g0 = 0; g0 < B; g0 += QG_MAX) {
         int nq = B - g0 < QG_MAX ? B - g0 : QG_MAX;
-        PSH_CUDA(cudaMemcpyAsync(hst, st + g0, sizeof(QState) * nq, cudaMemcpyDeviceToHost, stream));
-        PSH_CUDA(cudaStreamSynchronize(stream));
         bool ovf = false;
-        for (int i = 0; i < nq; ++i) ovf = ovf || hst[i].overflow != 0;
+        for (int i = 0; i < nq; ++i) ovf = ovf || hst[g0 + i].overflow != 0;
         if (ovf) {
             int rc = run_scan_group(d_dataset, R, T, row_stride, d_queries + (size_t)g0 * W, nq, W, H, k, row_offset,
                                     pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap, qspec + (size_t)g0 * fftx::N, fhist_all + (size_t)g0 * FFT_NB, shist_all + (size_t)g0 * SEED_STRIDE, auxp, mode,
@@ -2046,8 +2076,13 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
                                     d_out_dist + (size_t)g0 * k * (d_out_idx ? 1 : 3),
                                 d_out_idx ? d_out_idx + (size_t)g0 * k * 2 : nullptr, stream);
             if (rc != PSH_OK) return rc;
-            PSH_CUDA(cudaStreamSynchronize(stream));
+            redone = true;
         }
+    }
+    if (redone) {  // this call has dealt with its own overflow: nothing is left pending for psh_scan_overflowed
+        clear_sticky_kernel<<<(B + 127) / 128, 128, 0, stream>>>(st, B);
+        PSH_LAUNCHED();
+        PSH_CUDA(cudaStreamSynchronize(stream));
     }
     return PSH_OK;
 }
@@ -2055,14 +2090,17 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
 int psh_scan_overflowed(const void *d_ws, int B, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!d_ws || B <= 0) return PSH_E_ARG;
-    const QState *st = static_cast<const QState *>(d_ws);
-    static thread_local QState hst[QG_MAX];
+    QState *st = const_cast<QState *>(static_cast<const QState *>(d_ws));
+    QState *hst = host_stage(B);
+    if (hst == nullptr) return (int)cudaErrorMemoryAllocation;
+    PSH_CUDA(cudaMemcpyAsync(hst, st, sizeof(QState) * B, cudaMemcpyDeviceToHost, stream));
+    PSH_CUDA(cudaStreamSynchronize(stream));
     int ovf = 0;
-    for (int g0 = 0; g0 < B; g0 += QG_MAX) {
-        int nq = B - g0 < QG_MAX ? B - g0 : QG_MAX;
-        PSH_CUDA(cudaMemcpyAsync(hst, st + g0, sizeof(QState) * nq, cudaMemcpyDeviceToHost, stream));
-        PSH_CUDA(cudaStreamSynchronize(stream));
-        for (int i = 0; i < nq; ++i) ovf |= hst[i].overflow != 0 ? 1 : 0;
+    for (int i = 0; i < B; ++i)
+        ovf |= (hst[i].overflow != 0 || (hst[i].magic == QSTATE_MAGIC && hst[i].sticky != 0)) ? 1 : 0;
+    if (ovf) {  // reported once: the next check starts clean
+        clear_sticky_kernel<<<(B + 127) / 128, 128, 0, stream>>>(st, B);
+        PSH_LAUNCHED();
     }
     return ovf ? PSH_E_OVERFLOW : PSH_OK;
 }

@@ -187,9 +187,10 @@ class PathShadowing:
         return _lib.PSH_MODE_FFT, self._fft_aux[1]
 
     # ------------------------------------------------------------------ scan
-    def _scan_device(self, x: torch.Tensor, rows: torch.Tensor, T: int, k: int, out=None):
+    def _scan_device(self, x: torch.Tensor, rows: torch.Tensor, T: int, k: int, out=None, nosync: bool = False):
         """x (B, 1, W) -> device (dist (B,k), idx (B,k,2)); all-reduced across the process group
-        when the ensemble is sharded."""
+        when the ensemble is sharded.  `nosync`: enqueue only (a pipeline of scans on one stream);
+        the caller must call `_check_pipeline()` before trusting any of the results."""
         self._check_plugins()
         dev = rows.device
         if x.dtype != torch.float32:
@@ -206,11 +207,28 @@ class PathShadowing:
             if k > n_windows:
                 raise RuntimeError(f"selected index k out of range: k={k} > {n_windows} windows")
             mode, aux = self._mode_and_aux(rows, T, W, H)
-            dist, idx, self._workspace = _lib.scan_topk(rows, T, q, H, k, self._row_offset, mode,
-                                                        self._workspace, aux, out)
+            dist, idx, self._workspace = _lib.scan_topk(
+                rows, T, q, H, k, self._row_offset, mode | (_lib.PSH_FLAG_NOSYNC if nosync else 0),
+                self._workspace, aux, out)
+            self._pipeline_B = q.shape[0]
             return dist, idx
         from .distributed import finish_sharded, sharded_scan
-        return finish_sharded(self, rows, T, q, H, k, sharded_scan(self, rows, T, q, H, k))
+        res = sharded_scan(self, rows, T, q, H, k)
+        return res if nosync else finish_sharded(self, rows, T, q, H, k, res)
+
+    def _check_pipeline(self) -> None:
+        """Synchronise behind a pipeline of `nosync` scans; raises if any of them overflowed a
+        candidate buffer (adversarially ordered data: those scans must be repeated synchronously)."""
+        if self._pg is None:
+            bad = _lib.scan_overflowed(self._workspace, self._pipeline_B)
+        else:
+            flag = getattr(self, "_pending_flag", None)
+            bad = flag is not None and int(flag.item()) != 0
+            if bad:
+                flag.zero_()
+            self._pending_flag = None
+        if bad:
+            raise _lib.PshadowError(_lib.PSH_E_OVERFLOW, "nosync scan pipeline")
 
     def batched_distance(self, x: torch.Tensor, y: torch.Tensor, k: int, n_splits: int,
                          cuda: bool) -> tuple[torch.Tensor, torch.Tensor]:
@@ -225,7 +243,8 @@ class PathShadowing:
         dist, idx = self._scan_device(_torch(_dim_array(x)), rows, T, k)
         return dist.cpu(), idx.cpu()
 
-    def shadow_device(self, x_context: ArrayType, k: int = 1, _packed: torch.Tensor | None = None):
+    def shadow_device(self, x_context: ArrayType, k: int = 1, _packed: torch.Tensor | None = None,
+                      _nosync: bool = False):
         """`shadow` without the device->host copy: (dist (B,k), paths (B,k,1,W+H), idx (B,k,2))
         as CUDA tensors (used by `predict` to keep the whole pipeline on the GPU)."""
         if self.embedding.kernel.shape[-1] != 0 and self.embedding.kernel.shape[-1] != x_context.shape[-1]:
@@ -239,7 +258,7 @@ class PathShadowing:
             nd, ni = B * k, B * k * 2
             out = (_packed[:nd].view(torch.float32).view(B, k), _packed[nd:nd + ni].view(B, k, 2))
             out_paths = _packed[nd + ni:nd + ni + B * k * L].view(torch.float32).view(B, k, 1, L)
-        dist, idx = self._scan_device(x, rows, T, k, out)
+        dist, idx = self._scan_device(x, rows, T, k, out, nosync=_nosync and self._pg is None)
         if self._pg is None:
             paths = _lib.gather_paths(rows, T, idx, L, self._row_offset, out_paths)
         else:
@@ -270,9 +289,15 @@ class PathShadowing:
             self._staging = (torch.empty(words, dtype=torch.int32, device=self._dev()),
                              torch.empty(words, dtype=torch.int32, pin_memory=True))
         dev_buf, host_buf = self._staging
-        self.shadow_device(x_context, k, _packed=dev_buf)
+        # scan, gather and the copy back are enqueued together; the single synchronisation is the
+        # status read, which also tells whether a candidate buffer overflowed (adversarially
+        # ordered data) -- then the synchronous scan repeats it in its safe schedule
+        self.shadow_device(x_context, k, _packed=dev_buf, _nosync=True)
         host_buf.copy_(dev_buf, non_blocking=True)
-        torch.cuda.current_stream(dev_buf.device).synchronize()
+        if _lib.scan_overflowed(self._workspace, B):
+            self.shadow_device(x_context, k, _packed=dev_buf)
+            host_buf.copy_(dev_buf, non_blocking=True)
+            torch.cuda.current_stream(dev_buf.device).synchronize()
         flat = host_buf.numpy().copy()
         nd, ni = B * k, B * k * 2
         return (flat[:nd].view(np.float32).reshape(B, k),

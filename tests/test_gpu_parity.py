@@ -400,3 +400,37 @@ def test_seedless_adversarial_seed_pairs(monkeypatch):
     d, _, idx = _obj(ds, W, None, scan_mode="fft").shadow(q, k=k)
     do, io = oracle.shadow_topk(ds, q, k, H)
     assert_topk_equal(d, idx, do, io)
+
+
+def test_nosync_pipeline_sticky_overflow():
+    """A pipeline of enqueue-only scans on one workspace (bench.py's device loop): results equal
+    the synchronous ones, and an overflow in ANY scan of the pipeline is still reported at the
+    single check at its end (the per-call state is reset by every scan, the sticky flag is not)."""
+    R, T, W, H, k = 2048, 2048, 64, 4, 128
+    ds, q = make_inputs(R, T, W, 4, seed=91)
+    obj = _obj(ds, W, H, scan_mode="fft")
+    rows, T_ = obj._resident_rows()
+    qd = torch.tensor(q).cuda()
+    outs = []
+    for i in range(4):
+        out = (torch.empty((1, k), dtype=torch.float32, device="cuda"),
+               torch.empty((1, k, 2), dtype=torch.int32, device="cuda"))
+        outs.append(obj._scan_device(qd[i:i + 1], rows, T_, k, out=out, nosync=True))
+    obj._check_pipeline()
+    do, io = oracle.shadow_topk(ds, q, k, H)
+    for i, (d, idx) in enumerate(outs):
+        assert_topk_equal(d.cpu().numpy(), idx.cpu().numpy(), do[i:i + 1], io[i:i + 1])
+    # scan 1 of 3 overflows (query at 1e-3 of the data's scale: seed threshold +inf), scans 2-3 are clean
+    obj._scan_device(qd[:1] * 1e-3, rows, T_, k, nosync=True)
+    obj._scan_device(qd[1:2], rows, T_, k, nosync=True)
+    obj._scan_device(qd[2:3], rows, T_, k, nosync=True)
+    with pytest.raises(_lib.PshadowError):
+        obj._check_pipeline()
+    # reported once; the next pipeline starts clean, and the synchronous call repairs by itself
+    obj._scan_device(qd[1:2], rows, T_, k, nosync=True)
+    obj._check_pipeline()
+    d, idx = obj._scan_device(qd[:1] * 1e-3, rows, T_, k)
+    do, io = oracle.shadow_topk(ds, q[:1] * np.float32(1e-3), k, H)
+    assert_topk_equal(d.cpu().numpy(), idx.cpu().numpy(), do, io)
+    obj._scan_device(qd[1:2], rows, T_, k, nosync=True)
+    obj._check_pipeline()
