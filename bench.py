@@ -262,9 +262,9 @@ def run_ours(args):
     L.psh_profile_begin()
     for i in range(args.steps):
         step_device(args.warmup + i)
-    ms_kind = (ctypes.c_double * 2)()
-    n_kind = (ctypes.c_uint64 * 2)()
-    L.psh_profile_end(ms_kind, n_kind, 2)
+    ms_kind = (ctypes.c_double * 3)()
+    n_kind = (ctypes.c_uint64 * 3)()
+    L.psh_profile_end(ms_kind, n_kind, 3)
     obj._check_pipeline()
     torch.cuda.synchronize()
 
@@ -317,6 +317,7 @@ def run_ours(args):
                          "kernel": "scan kernels of one step (all chunk launches)",
                          "kernel_ms_per_step": scan_ms_per_step, "kernel_launches_per_step": n_kind[0] / args.steps,
                          "select_ms_per_step": ms_kind[1] / args.steps,
+                         "merge_ms_per_step": ms_kind[2] / args.steps,
                          "alg_bytes_per_step": alg_bytes,
                          "fp32": {"note": "binding roof (SURVEY 8d): lane-ops/s vs SMs*128*clock",
                                   "flop_per_window": flop_per_win, "achieved_tlaneops": fp32_rate / 1e12,

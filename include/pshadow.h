@@ -104,7 +104,8 @@ int psh_debug_fft4096(const void *d_in, void *d_out, int n, int dir, const void 
 /*
  * k-way merge of G per-shard results into the global top-k: replaces the cat + topk +
  * fancy-index merge (path_shadowing.py:170-173) across GPUs.
- *   d_dist_parts (G, B, k) fp32, d_idx_parts (G, B, k, 2) int32 (global trajectory ids)
+ *   d_dist_parts (G, B, k) fp32, d_idx_parts (G, B, k, 2) int32 (global trajectory ids); every
+ *                shard's k records ascending in (distance, r*Tp+t), as psh_scan_topk_f32 writes them
  *   Tp           windows per trajectory (tie order is (distance, r*Tp+t))
  */
 int psh_merge_topk(const float *d_dist_parts, const int32_t *d_idx_parts, int G, int B,
@@ -116,6 +117,30 @@ int psh_merge_topk_packed(const int32_t *d_rec_parts, int G, int B, int64_t k, i
 /* d_overflow_flag (may be NULL; zero it first): set to 1 if any shard's PSH_FLAG_NOSYNC scan
  * overflowed a candidate buffer (it poisons its first record); every rank sees the same flag,
  * so all ranks repeat the step with synchronous scans together. */
+
+/*
+ * Multi-GPU, one process per GPU: all-gather of the per-rank records over NVLink peer memory fused
+ * with the merge -- ONE kernel instead of ncclAllGather + psh_merge_topk_packed (no reference
+ * counterpart; the reference is single-process).  Every rank creates an exchange buffer of
+ * psh_xchg_bytes(G, B, k) bytes (cudaMalloc, zeroed), publishes its 64-byte CUDA IPC handle, and
+ * maps the other ranks' buffers with psh_xchg_open.  psh_allgather_merge_packed is collective:
+ * every rank calls it with the same (B, k, Tp) and the same epoch = 1, 2, 3, ... (one per call);
+ *   d_rec_local (B, k, 3) int32 records of this rank (psh_scan_topk_f32 with d_out_idx = NULL)
+ *   bufs        HOST array of G device pointers, bufs[g] = rank g's exchange buffer as mapped in
+ *               this process (bufs[rank] = the own buffer)
+ *   d_flag      int32, zeroed by the caller: bit 0 = a shard's NOSYNC scan overflowed,
+ *               bit 1 = a peer's records did not arrive within 30 s (results invalid)
+ * Each CTA stores its query's records into every rank's buffer, raises a per-(rank, query) flag
+ * (st.release.sys), waits for the G flags of its query and merges (same order as psh_merge_topk).
+ */
+size_t psh_xchg_bytes(int G, int B, int64_t k);
+int psh_xchg_create(size_t bytes, void **d_buf, unsigned char *ipc_handle_64);
+int psh_xchg_open(const unsigned char *ipc_handle_64, void **d_peer);
+int psh_xchg_close(void *d_peer);
+int psh_xchg_destroy(void *d_buf);
+int psh_allgather_merge_packed(const int32_t *d_rec_local, void *const *bufs, int G, int rank, int B, int64_t k,
+                               int64_t Tp, uint32_t epoch, float *d_out_dist, int32_t *d_out_idx,
+                               int32_t *d_flag, void *stream);
 
 /*
  * Gather the winning paths with their out-context: replaces path_shadowing.py:210-216.
@@ -146,7 +171,8 @@ uint64_t psh_launch_count(void);
  * Measurement hooks (no reference counterpart): between begin and end every kernel the library
  * launches is bracketed by CUDA events on the caller's stream.  psh_profile_end waits for them
  * and returns summed milliseconds and launch counts per kind: 0 = scan kernels, 1 = select /
- * re-rank / finalise kernels.  Not thread-safe; for bench.py's roofline leg only.
+ * re-rank / finalise kernels, 2 = merge / peer-memory all-gather + merge kernels.  Not
+ * thread-safe; for bench.py's roofline leg only.
  */
 void psh_profile_begin(void);
 int psh_profile_end(double *ms_by_kind, uint64_t *launches_by_kind, int nkinds);

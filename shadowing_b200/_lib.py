@@ -59,6 +59,19 @@ def lib() -> ctypes.CDLL:
         L.psh_merge_topk.argtypes = [vp, vp, ci, ci, i64, i64, vp, vp, vp]
         L.psh_merge_topk_packed.restype = ci
         L.psh_merge_topk_packed.argtypes = [vp, ci, ci, i64, i64, vp, vp, vp, vp]
+        L.psh_xchg_bytes.restype = ctypes.c_size_t
+        L.psh_xchg_bytes.argtypes = [ci, ci, i64]
+        L.psh_xchg_create.restype = ci
+        L.psh_xchg_create.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp), ctypes.c_char_p]
+        L.psh_xchg_open.restype = ci
+        L.psh_xchg_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
+        L.psh_xchg_close.restype = ci
+        L.psh_xchg_close.argtypes = [vp]
+        L.psh_xchg_destroy.restype = ci
+        L.psh_xchg_destroy.argtypes = [vp]
+        L.psh_allgather_merge_packed.restype = ci
+        L.psh_allgather_merge_packed.argtypes = [vp, ctypes.POINTER(vp), ci, ci, ci, i64, i64, ctypes.c_uint32,
+                                                 vp, vp, vp, vp]
         L.psh_gather_paths.restype = ci
         L.psh_gather_paths.argtypes = [vp, i64, i64, i64, vp, i64, i32, ci, vp, vp]
         L.psh_rv_aggregate.restype = ci
@@ -230,3 +243,57 @@ def rv_aggregate(paths: torch.Tensor, dist: torch.Tensor, H: int, Ts: torch.Tens
                                 std.data_ptr(), _stream(paths))
     _check(rc, "psh_rv_aggregate")
     return mean, std
+
+
+# ---------------------------------------------------------------------------------------------
+# peer-memory exchange (multi-GPU): buffers every rank maps through CUDA IPC
+# ---------------------------------------------------------------------------------------------
+def xchg_bytes(G: int, B: int, k: int) -> int:
+    return int(lib().psh_xchg_bytes(G, B, k))
+
+
+def xchg_create(nbytes: int, device: torch.device) -> tuple[int, bytes]:
+    """cudaMalloc + zero an exchange buffer on `device`; returns (device pointer, 64-byte IPC handle)."""
+    L = lib()
+    ptr = ctypes.c_void_p()
+    handle = ctypes.create_string_buffer(64)
+    with torch.cuda.device(device):
+        _check(L.psh_xchg_create(nbytes, ctypes.byref(ptr), handle), "psh_xchg_create")
+    return int(ptr.value), handle.raw
+
+
+def xchg_open(handle: bytes, device: torch.device) -> int:
+    L = lib()
+    ptr = ctypes.c_void_p()
+    with torch.cuda.device(device):
+        _check(L.psh_xchg_open(handle, ctypes.byref(ptr)), "psh_xchg_open")
+    return int(ptr.value)
+
+
+def xchg_close(ptr: int, device: torch.device) -> None:
+    with torch.cuda.device(device):
+        lib().psh_xchg_close(ptr)
+
+
+def xchg_destroy(ptr: int, device: torch.device) -> None:
+    with torch.cuda.device(device):
+        lib().psh_xchg_destroy(ptr)
+
+
+def allgather_merge_packed(rec: torch.Tensor, bufs: list[int], rank: int, Tp: int, epoch: int,
+                           flag: torch.Tensor | None = None):
+    """rec (B,k,3) i32 [distance bits, r, t] of this rank -> merged (B,k) f32, (B,k,2) i32 over all
+    ranks: ONE kernel stores the records into every rank's exchange buffer over NVLink, waits for
+    the peers' records and merges.  `flag` bit 0: a shard overflowed; bit 1: a peer timed out."""
+    L = lib()
+    B, k, _ = rec.shape
+    G = len(bufs)
+    arr = (ctypes.c_void_p * G)(*bufs)
+    dist = torch.empty((B, k), dtype=torch.float32, device=rec.device)
+    idx = torch.empty((B, k, 2), dtype=torch.int32, device=rec.device)
+    with torch.cuda.device(rec.device):
+        rc = L.psh_allgather_merge_packed(rec.data_ptr(), arr, G, rank, B, k, Tp, epoch, dist.data_ptr(),
+                                          idx.data_ptr(), flag.data_ptr() if flag is not None else None,
+                                          _stream(rec))
+    _check(rc, "psh_allgather_merge_packed")
+    return dist, idx

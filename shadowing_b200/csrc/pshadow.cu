@@ -1412,21 +1412,67 @@ __global__ void __launch_bounds__(SEL_THREADS) finalize_kernel(const QState *st_
 // ------------------------------------------------------------------------------------------
 // Record j of shard g, query b: distance at d_parts[rec * dstride], indices at i_parts[rec * istride + {0,1}],
 // rec = (g*B + b)*k + j  (separate arrays: dstride 1, istride 2; packed [dbits, r, t] records: 3, 3).
-__global__ void __launch_bounds__(SEL_THREADS) merge_kernel(const float *d_parts, const int *i_parts, int dstride,
-                                                             int istride, int G, int B,
-                                                             unsigned int k, unsigned long long Tp, unsigned int npow2,
-                                                             unsigned long long *scratch, int use_smem,
-                                                             float *out_d, int *out_idx, int *flag) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ void merge_body(const float *d_parts, const int *i_parts, int dstride, int istride, int G,
+                                           int B, unsigned int k, unsigned long long Tp, unsigned int npow2,
+                                           unsigned long long *scratch, int use_smem, float *out_d, int *out_idx,
+                                           int *flag, unsigned char *smem_raw) {
     const int b = blockIdx.x;
+    const unsigned int n = (unsigned int)G * k;
+    if (use_smem == 2) {
+        // merge by rank: every shard's list is already ascending in (distance bits, global flat index),
+        // so the output position of element j of list g is j + sum over the other lists of the number
+        // of their elements ordered before it (one binary search each) -- no sort, no tie fix-up.
+        // Elements equal in distance AND flat index (the +inf padding of short shards) order by g.
+        unsigned long long *fl = reinterpret_cast<unsigned long long *>(smem_raw);
+        unsigned int *db = reinterpret_cast<unsigned int *>(fl + n);
+        for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned int g = i / k, j = i - g * k;
+            const size_t rec = ((size_t)g * B + b) * k + j;
+            const unsigned int d = __float_as_uint(__ldcg(d_parts + rec * dstride));
+            if (flag != nullptr && d == 0xffffffffu) atomicOr(flag, 1);  // a shard overflowed
+            const int *ic = i_parts + rec * istride;
+            db[i] = d;
+            fl[i] = (unsigned long long)(unsigned int)__ldcg(ic) * Tp + (unsigned long long)(unsigned int)__ldcg(ic + 1);
+        }
+        __syncthreads();
+        for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned int g = i / k, j = i - g * k;
+            const unsigned int dk = db[i];
+            const unsigned long long fk = fl[i];
+            unsigned int rank = j;
+            for (unsigned int g2 = 0; g2 < (unsigned int)G && rank < k; ++g2) {
+                if (g2 == g) continue;
+                const unsigned int base = g2 * k;
+                unsigned int lo = 0, hi = k;
+                while (lo < hi) {
+                    const unsigned int mid = (lo + hi) >> 1;
+                    const unsigned int d2 = db[base + mid];
+                    bool before = d2 < dk;
+                    if (d2 == dk) {
+                        const unsigned long long f2 = fl[base + mid];
+                        before = f2 < fk || (f2 == fk && g2 < g);
+                    }
+                    if (before) lo = mid + 1; else hi = mid;
+                }
+                rank += lo;
+            }
+            if (rank < k) {
+                const int *ic = i_parts + (((size_t)g * B + b) * k + j) * istride;
+                out_d[(size_t)b * k + rank] = __uint_as_float(dk);
+                out_idx[((size_t)b * k + rank) * 2 + 0] = __ldcg(ic);
+                out_idx[((size_t)b * k + rank) * 2 + 1] = __ldcg(ic + 1);
+            }
+        }
+        return;
+    }
     unsigned long long *a = use_smem ? reinterpret_cast<unsigned long long *>(smem_raw)
                                      : scratch + (size_t)b * npow2;
-    const unsigned int n = (unsigned int)G * k;
     for (unsigned int i = threadIdx.x; i < npow2; i += blockDim.x) {
         unsigned long long key = ~0ull;
         if (i < n) {
             unsigned int g = i / k, j = i - g * k;
-            float d = d_parts[(((size_t)g * B + b) * k + j) * dstride];
+            // L2 loads: in the peer-memory exchange these records were written by other GPUs
+            float d = __ldcg(d_parts + (((size_t)g * B + b) * k + j) * dstride);
             if (flag != nullptr && __float_as_uint(d) == 0xffffffffu) atomicOr(flag, 1);  // a shard overflowed
             key = ((unsigned long long)__float_as_uint(d) << 32) | i;
         }
@@ -1448,13 +1494,13 @@ __global__ void __launch_bounds__(SEL_THREADS) merge_kernel(const float *d_parts
                 unsigned int sc = (unsigned int)a[c];
                 unsigned int gc = sc / k, jc = sc - gc * k;
                 const int *ic = i_parts + (((size_t)gc * B + b) * k + jc) * istride;
-                unsigned long long fc = (unsigned long long)ic[0] * Tp + (unsigned long long)ic[1];
+                unsigned long long fc = (unsigned long long)__ldcg(ic) * Tp + (unsigned long long)__ldcg(ic + 1);
                 unsigned int rank = 0;
                 for (unsigned int e = lo; e <= hi; ++e) {
                     unsigned int se = (unsigned int)a[e];
                     unsigned int ge = se / k, je = se - ge * k;
                     const int *ie = i_parts + (((size_t)ge * B + b) * k + je) * istride;
-                    unsigned long long fe = (unsigned long long)ie[0] * Tp + (unsigned long long)ie[1];
+                    unsigned long long fe = (unsigned long long)__ldcg(ie) * Tp + (unsigned long long)__ldcg(ie + 1);
                     rank += (fe < fc) ? 1u : 0u;
                 }
                 if (rank == want) { slot = sc; break; }
@@ -1463,9 +1509,84 @@ __global__ void __launch_bounds__(SEL_THREADS) merge_kernel(const float *d_parts
         unsigned int g = slot / k, j = slot - g * k;
         const int *src = i_parts + (((size_t)g * B + b) * k + j) * istride;
         out_d[(size_t)b * k + i] = __uint_as_float(db);
-        out_idx[((size_t)b * k + i) * 2 + 0] = src[0];
-        out_idx[((size_t)b * k + i) * 2 + 1] = src[1];
+        out_idx[((size_t)b * k + i) * 2 + 0] = __ldcg(src);
+        out_idx[((size_t)b * k + i) * 2 + 1] = __ldcg(src + 1);
     }
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) merge_kernel(const float *d_parts, const int *i_parts, int dstride,
+                                                             int istride, int G, int B,
+                                                             unsigned int k, unsigned long long Tp, unsigned int npow2,
+                                                             unsigned long long *scratch, int use_smem,
+                                                             float *out_d, int *out_idx, int *flag) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    merge_body(d_parts, i_parts, dstride, istride, G, B, k, Tp, npow2, scratch, use_smem, out_d, out_idx, flag, smem_raw);
+}
+
+// ------------------------------------------------------------------------------------------
+// all-gather over NVLink peer memory fused with the merge (multi-GPU, one process per GPU).
+// Every rank owns an exchange buffer that all other ranks have mapped (CUDA IPC):
+//     [parity 0/1][ records (G, B, k, 3) int32 | flags (G, B) uint32 ]
+// CTA b of rank r stores query b's k packed records into slot r of EVERY rank's buffer (plain
+// stores over NVLink), fences (system scope), then raises flag (r, b) on every rank with the
+// step's epoch; it then waits until the G flags of query b in its OWN buffer carry the epoch
+// and merges the G*k records exactly like merge_kernel.  One launch replaces ncclAllGather +
+// merge_kernel.  Parities alternate per step: a rank can be at most one step ahead of a peer
+// (its next merge waits for that peer's flag), so two buffers suffice.
+// A peer that never arrives (crashed rank) raises bit 1 of `flag` after `timeout_ns` instead of
+// hanging the GPU.
+// ------------------------------------------------------------------------------------------
+constexpr int XCHG_MAX_PEERS = 16;
+struct XchgParams {
+    int *rec[XCHG_MAX_PEERS];            // this parity's record area on every rank
+    unsigned int *flags[XCHG_MAX_PEERS]; // this parity's flag area on every rank
+    const int *local_rec;                // (B, k, 3) this rank's records
+    int G, rank;
+    unsigned int epoch;
+    unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) xchg_merge_kernel(const XchgParams x, int B, unsigned int k,
+                                                                  unsigned long long Tp, unsigned int npow2,
+                                                                  unsigned long long *scratch, int use_smem,
+                                                                  float *out_d, int *out_idx, int *flag) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const unsigned int n3 = k * 3u;
+    const int *src = x.local_rec + (size_t)b * n3;
+    for (int g = 0; g < x.G; ++g) {
+        int *dst = x.rec[g] + ((size_t)x.rank * B + b) * n3;
+        for (unsigned int i = tid; i < n3; i += SEL_THREADS) dst[i] = src[i];
+    }
+    __syncthreads();
+    if (tid < x.G) {
+        __threadfence_system();   // the CTA's record stores (ordered before by the barrier) precede the flag
+        st_release_sys(x.flags[tid] + (size_t)x.rank * B + b, x.epoch);
+        const unsigned int *mine = x.flags[x.rank] + (size_t)tid * B + b;
+        const unsigned long long t0 = globaltimer_ns();
+        while (ld_acquire_sys(mine) != x.epoch) {
+            if (globaltimer_ns() - t0 > x.timeout_ns) { if (flag != nullptr) atomicOr(flag, 2); break; }
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
+    const int *all = x.rec[x.rank];
+    merge_body(reinterpret_cast<const float *>(all), all + 1, 3, 3, x.G, B, k, Tp, npow2, scratch, use_smem, out_d,
+               out_idx, flag, smem_raw);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1654,6 +1775,13 @@ QState *host_stage(int n) {
         cap = want;
     }
     return buf;
+}
+
+// merge by rank needs 12 bytes of shared memory per record (G*k records per query)
+constexpr unsigned long long MERGE_RANK_SMEM_MAX = 200 * 1024;
+bool merge_sort_forced() {   // PSH_MERGE_SORT=1: always the bitonic-sort merge (tests / A-B measurements)
+    const char *e = getenv("PSH_MERGE_SORT");
+    return e != nullptr && e[0] == '1';
 }
 
 // A/B switch for measurements: PSH_SEEDLESS=0 keeps the exact-seeded chunk schedule everywhere
@@ -2113,10 +2241,12 @@ static int merge_impl(const float *d_parts, const int *i_parts, int dstride, int
     unsigned int npow2 = 1; while (npow2 < n) npow2 <<= 1;
     int use_smem = npow2 <= SORT_SMEM_MAX ? 1 : 0;
     size_t smem = use_smem ? (size_t)npow2 * sizeof(unsigned long long) : 0;
+    if (n * 12ull <= MERGE_RANK_SMEM_MAX && !merge_sort_forced()) { use_smem = 2; smem = (size_t)n * 12; }  // merge by rank
     unsigned long long *scratch = nullptr;
     if (!use_smem) PSH_CUDA(cudaMallocAsync(&scratch, (size_t)B * npow2 * sizeof(unsigned long long), stream));
     if (smem > 48 * 1024)
         PSH_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps_merge(stream, 2);
     merge_kernel<<<B, SEL_THREADS, smem, stream>>>(d_parts, i_parts, dstride, istride, G, B, (unsigned int)k,
                                                    (unsigned long long)Tp, npow2, scratch, use_smem, d_out_dist,
                                                    d_out_idx, d_flag);
@@ -2136,6 +2266,86 @@ int psh_merge_topk_packed(const int32_t *d_rec_parts, int G, int B, int64_t k, i
     if (!d_rec_parts) return PSH_E_ARG;
     return merge_impl(reinterpret_cast<const float *>(d_rec_parts), d_rec_parts + 1, 3, 3, G, B, k, Tp, d_out_dist,
                       d_out_idx, d_overflow_flag, (cudaStream_t)stream_);
+}
+
+// ---- exchange buffers for the peer-memory all-gather (multi-GPU) ----
+static size_t xchg_rec_bytes(int G, int B, int64_t k) { return align_up((size_t)G * B * (size_t)k * 3 * sizeof(int), 256); }
+static size_t xchg_flag_bytes(int G, int B) { return align_up((size_t)G * B * sizeof(unsigned int), 256); }
+
+size_t psh_xchg_bytes(int G, int B, int64_t k) {
+    if (G <= 0 || G > XCHG_MAX_PEERS || B <= 0 || k <= 0) return 0;
+    return 2 * (xchg_rec_bytes(G, B, k) + xchg_flag_bytes(G, B));
+}
+
+int psh_xchg_create(size_t bytes, void **d_buf, unsigned char *handle64) {
+    if (!d_buf || !handle64 || bytes == 0) return PSH_E_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void *p = nullptr;
+    PSH_CUDA(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); cudaGetLastError(); return (int)e; }
+    memcpy(handle64, &h, 64);
+    *d_buf = p;
+    return PSH_OK;
+}
+
+int psh_xchg_open(const unsigned char *handle64, void **d_peer) {
+    if (!handle64 || !d_peer) return PSH_E_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(d_peer, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    return PSH_OK;
+}
+
+int psh_xchg_close(void *d_peer) {
+    if (!d_peer) return PSH_E_ARG;
+    PSH_CUDA(cudaIpcCloseMemHandle(d_peer));
+    return PSH_OK;
+}
+
+int psh_xchg_destroy(void *d_buf) {
+    if (!d_buf) return PSH_E_ARG;
+    PSH_CUDA(cudaFree(d_buf));
+    return PSH_OK;
+}
+
+int psh_allgather_merge_packed(const int32_t *d_rec_local, void *const *bufs, int G, int rank, int B, int64_t k,
+                               int64_t Tp, uint32_t epoch, float *d_out_dist, int32_t *d_out_idx,
+                               int32_t *d_flag, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!d_rec_local || !bufs || !d_out_dist || !d_out_idx || G <= 0 || G > XCHG_MAX_PEERS || rank < 0 || rank >= G ||
+        B <= 0 || k <= 0 || Tp <= 0 || epoch == 0)
+        return PSH_E_ARG;
+    unsigned long long n = (unsigned long long)G * (unsigned long long)k;
+    if (n > 0x7fffffffull) return PSH_E_TOO_LARGE;
+    XchgParams x;
+    const size_t rb = xchg_rec_bytes(G, B, k), fb = xchg_flag_bytes(G, B);
+    const size_t par = (size_t)(epoch & 1u) * (rb + fb);
+    for (int g = 0; g < G; ++g) {
+        if (!bufs[g]) return PSH_E_ARG;
+        unsigned char *base = static_cast<unsigned char *>(bufs[g]) + par;
+        x.rec[g] = reinterpret_cast<int *>(base);
+        x.flags[g] = reinterpret_cast<unsigned int *>(base + rb);
+    }
+    x.local_rec = d_rec_local; x.G = G; x.rank = rank; x.epoch = epoch;
+    x.timeout_ns = 30ull * 1000ull * 1000ull * 1000ull;
+    unsigned int npow2 = 1; while (npow2 < n) npow2 <<= 1;
+    int use_smem = npow2 <= SORT_SMEM_MAX ? 1 : 0;
+    size_t smem = use_smem ? (size_t)npow2 * sizeof(unsigned long long) : 0;
+    if (n * 12ull <= MERGE_RANK_SMEM_MAX && !merge_sort_forced()) { use_smem = 2; smem = (size_t)n * 12; }  // merge by rank
+    unsigned long long *scratch = nullptr;
+    if (!use_smem) PSH_CUDA(cudaMallocAsync(&scratch, (size_t)B * npow2 * sizeof(unsigned long long), stream));
+    if (smem > 48 * 1024)
+        PSH_CUDA(cudaFuncSetAttribute(xchg_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps_merge(stream, 2);
+    xchg_merge_kernel<<<B, SEL_THREADS, smem, stream>>>(x, B, (unsigned int)k, (unsigned long long)Tp, npow2, scratch,
+                                                        use_smem, d_out_dist, d_out_idx, d_flag);
+    PSH_LAUNCHED();
+    if (scratch) PSH_CUDA(cudaFreeAsync(scratch, stream));
+    return PSH_OK;
 }
 
 int psh_gather_paths(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride,

@@ -9,6 +9,8 @@ paths are gathered by their owner and assembled with an all-reduce (x + 0 == x e
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -46,9 +48,71 @@ def _local_records(ps, rows, T, q, H, k, rec, nosync: bool):
         rec[:, :k_loc, 1:] = i
 
 
+class _PeerExchange:
+    """Exchange buffers of all ranks mapped into this process (CUDA IPC over NVLink peer access).
+    Creation is collective: every rank allocates its buffer, the 64-byte IPC handles travel through
+    one all_gather_object, and the ranks agree (all-reduce MIN) on whether every mapping worked."""
+
+    def __init__(self, pg, device: torch.device, B: int, k: int):
+        self.world, self.rank = dist.get_world_size(pg), dist.get_rank(pg)
+        self.device, self.shape, self.epoch = device, (B, k), 0
+        self.bufs: list[int] = []
+        self.own = 0
+        ok = 1
+        handle = b""
+        try:
+            self.own, handle = _lib.xchg_create(_lib.xchg_bytes(self.world, B, k), device)
+        except Exception:
+            ok = 0
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=pg)
+        if ok and all(handles):
+            try:
+                for g, h in enumerate(handles):
+                    self.bufs.append(self.own if g == self.rank else _lib.xchg_open(h, device))
+            except Exception:
+                ok = 0
+        else:
+            ok = 0
+        agree = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=pg)
+        self.ok = bool(agree.item())
+        if not self.ok:
+            self.close()
+
+    def close(self):
+        for g, p in enumerate(self.bufs):
+            if g != self.rank and p:
+                _lib.xchg_close(p, self.device)
+        self.bufs = []
+        if self.own:
+            _lib.xchg_destroy(self.own, self.device)
+            self.own = 0
+
+
+def _peer_exchange(ps, device, B, k):
+    """The peer-memory exchange for (B, k), or None when disabled (PSH_P2P=0) / unavailable --
+    then the step uses ncclAllGather + merge_kernel."""
+    if os.environ.get("PSH_P2P", "1") == "0":
+        return None
+    ex = getattr(ps, "_xchg", None)
+    if ex is None or ex.shape != (B, k):
+        if ex is not None:
+            torch.cuda.synchronize(device)
+            dist.barrier(group=ps._pg)     # nobody is still writing into the buffers being replaced
+            ex.close()
+        ex = _PeerExchange(ps._pg, device, B, k)
+        ps._xchg = ex
+    return ex if ex.ok else None
+
+
 def _exchange_and_merge(ps, rows, rec, rec_all, Tp, flag):
     pg = ps._pg
     if rows.is_cuda:
+        ex = _peer_exchange(ps, rows.device, rec.shape[0], rec.shape[1])
+        if ex is not None:
+            ex.epoch += 1
+            return _lib.allgather_merge_packed(rec, ex.bufs, ex.rank, Tp, ex.epoch, flag)
         dist.all_gather_into_tensor(rec_all, rec, group=pg)          # one ncclAllGather, B*k*12 bytes per rank
         return _lib.merge_topk_packed(rec_all, Tp, flag)
     dist.all_gather(list(rec_all.unbind(0)), rec, group=pg)          # gloo (CPU tests) has no *_into_tensor
@@ -99,9 +163,12 @@ def finish_sharded(ps, rows: torch.Tensor, T: int, q: torch.Tensor, H: int, k: i
     if flag is None:
         return out
     ps._pending_flag = None
-    if int(flag.item()) == 0:
+    status = int(flag.item())
+    if status == 0:
         return out
     flag.zero_()
+    if status & 2:
+        raise RuntimeError("peer-memory all-gather: a rank did not deliver its records within the timeout")
     B, W = q.shape
     rec, rec_all, _ = ps._shard_bufs
     _local_records(ps, rows, T, q, H, k, rec, nosync=False)

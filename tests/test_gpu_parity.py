@@ -269,7 +269,9 @@ def test_predict_end_to_end_chunks():
     assert np.allclose(p1, mo, rtol=1e-6) and np.allclose(s1, so, rtol=1e-5)
 
 
-def test_merge_topk_equals_global():
+@pytest.mark.parametrize("force_sort", ["0", "1"])   # merge by rank (default) / bitonic-sort merge
+def test_merge_topk_equals_global(force_sort, monkeypatch):
+    monkeypatch.setenv("PSH_MERGE_SORT", force_sort)
     ds, q = make_inputs(64, 700, 30, 3, seed=14)
     k, H = 128, 10
     rows = torch.tensor(ds[:, 0, :]).cuda()
@@ -434,3 +436,26 @@ def test_nosync_pipeline_sticky_overflow():
     assert_topk_equal(d.cpu().numpy(), idx.cpu().numpy(), do, io)
     obj._scan_device(qd[1:2], rows, T_, k, nosync=True)
     obj._check_pipeline()
+
+
+@pytest.mark.parametrize("force_sort", ["0", "1"])
+def test_merge_ties_and_padding(force_sort, monkeypatch):
+    """Merge of shards that tie in distance (identical rows live on different shards) and of a short
+    shard padded with +inf records: order must be (distance, global flat index), padding last."""
+    monkeypatch.setenv("PSH_MERGE_SORT", force_sort)
+    base, q = make_inputs(1, 600, 40, 2, seed=3)
+    ds = np.repeat(base, 12, axis=0)
+    k, H, Tp = 200, 10, 600 - 40 - 10 + 1
+    rows = torch.tensor(ds[:, 0, :]).cuda()
+    qd = torch.tensor(q[:, 0, :]).cuda()
+    recs = []
+    for s in range(0, 12, 4):
+        d, i, _ = _lib.scan_topk(rows[s:s + 4].contiguous(), 600, qd, H, k, s)
+        recs.append(torch.cat([d.view(torch.int32).unsqueeze(-1), i], dim=-1))
+    pad = torch.empty_like(recs[0])
+    pad[..., 0] = 0x7F800000
+    pad[..., 1] = 2 ** 31 - 1
+    pad[..., 2] = 0
+    d, i = _lib.merge_topk_packed(torch.stack(recs + [pad, pad]), Tp)
+    do, io = oracle.shadow_topk(ds, q, k, H)
+    assert np.array_equal(d.cpu().numpy(), do) and np.array_equal(i.cpu().numpy(), io)
