@@ -59,6 +59,7 @@ class ClockSampler(threading.Thread):
         self.idx = gpu_index
         self.sm, self.mx, self.reasons, self.power = [], [], set(), []
         self._halt = threading.Event()
+        self.period = float(os.environ.get("BENCH_CLOCK_PERIOD_S", "0.01"))
         self.nvml = None
         try:
             import pynvml
@@ -107,7 +108,7 @@ class ClockSampler(threading.Thread):
                     self._sample_smi()
             except Exception:
                 pass
-            self._halt.wait(0.01 if self.nvml is not None else 0.1)
+            self._halt.wait(self.period if self.nvml is not None else max(self.period, 0.1))
 
     def stop(self):
         self._halt.set()

@@ -16,6 +16,7 @@ combination raises NotImplementedError (no silent fallback).
 """
 from __future__ import annotations
 
+import weakref
 from pathlib import Path
 from typing import Callable
 
@@ -77,6 +78,12 @@ def _load_npy_dir(dpath: Path) -> np.ndarray:
         raise FileNotFoundError(f"no .npy batches under {dpath}")
     arrs = [_dim_array(np.load(f)) for f in files]
     return np.concatenate(arrs, axis=0)
+
+
+def _recycle(pool: list, outstanding: list, host_buf: torch.Tensor) -> None:
+    """Finaliser of a result buffer handed out by `shadow`: every numpy view of it is gone."""
+    outstanding[0] -= 1
+    pool.append(host_buf)
 
 
 class PathShadowing:
@@ -280,29 +287,50 @@ class PathShadowing:
         if self._pg is not None or not torch.cuda.is_available():
             dist, paths, idx = self.shadow_device(x_context, k)
             return _numpy(dist), _numpy(paths), _numpy(idx)
-        # results land in ONE device buffer [dist | idx | paths] (4-byte words) that is copied to
-        # persistent pinned staging with a single async copy + one sync
+        # results land in ONE device buffer [dist | idx | paths] (4-byte words) that is copied with a
+        # single async copy into a pinned host buffer; the returned numpy arrays are views of that
+        # buffer (no second copy), which goes back to a small pool when the caller drops them
         shp = _dim_array(x_context).shape
         B, L = shp[0], shp[-1] + self.context.get_out_times()
         words = B * k * (3 + L)
         if self._staging is None or self._staging[0].numel() != words:
-            self._staging = (torch.empty(words, dtype=torch.int32, device=self._dev()),
-                             torch.empty(words, dtype=torch.int32, pin_memory=True))
-        dev_buf, host_buf = self._staging
+            self._staging = (torch.empty(words, dtype=torch.int32, device=self._dev()), [], [0])
+        dev_buf, pool, outstanding = self._staging
+        if pool:
+            host_buf = pool.pop()
+        elif outstanding[0] < self._POOL_MAX:
+            host_buf = torch.empty(words, dtype=torch.int32, pin_memory=True)
+        else:
+            host_buf = None   # the caller keeps many results alive: fall back to pageable copies
+        stage = host_buf if host_buf is not None else self._spill_buffer(words)
         # scan, gather and the copy back are enqueued together; the single synchronisation is the
         # status read, which also tells whether a candidate buffer overflowed (adversarially
         # ordered data) -- then the synchronous scan repeats it in its safe schedule
         self.shadow_device(x_context, k, _packed=dev_buf, _nosync=True)
-        host_buf.copy_(dev_buf, non_blocking=True)
+        stage.copy_(dev_buf, non_blocking=True)
         if _lib.scan_overflowed(self._workspace, B):
             self.shadow_device(x_context, k, _packed=dev_buf)
-            host_buf.copy_(dev_buf, non_blocking=True)
+            stage.copy_(dev_buf, non_blocking=True)
             torch.cuda.current_stream(dev_buf.device).synchronize()
-        flat = host_buf.numpy().copy()
+        if host_buf is not None:
+            flat = host_buf.numpy()
+            outstanding[0] += 1
+            weakref.finalize(flat, _recycle, pool, outstanding, host_buf)
+        else:
+            flat = stage.numpy().copy()
         nd, ni = B * k, B * k * 2
         return (flat[:nd].view(np.float32).reshape(B, k),
                 flat[nd + ni:].view(np.float32).reshape(B, k, 1, L),
                 flat[nd:nd + ni].reshape(B, k, 2))
+
+    _POOL_MAX = 8   # pinned result buffers handed out at once before falling back to copies
+
+    def _spill_buffer(self, words: int) -> torch.Tensor:
+        sp = getattr(self, "_spill", None)
+        if sp is None or sp.numel() != words:
+            sp = torch.empty(words, dtype=torch.int32, pin_memory=True)
+            self._spill = sp
+        return sp
 
     # ------------------------------------------------------------------ aggregation
     @staticmethod

@@ -21,3 +21,9 @@ print("_lib.scan_topk  ", T(lambda i: _lib.scan_topk(rows, Tt, q2[i:i+1], bench.
 d, p, ix = obj.shadow_device(qp[0:1], k=1024)
 print("gather          ", T(lambda i: _lib.gather_paths(rows, Tt, ix, 272, 0)))
 print("h2d q           ", T(lambda i: qp[i:i+1][:, 0, :].to("cuda:0", non_blocking=True).contiguous()))
+import cProfile, pstats, io
+pr = cProfile.Profile()
+pr.enable()
+for i in range(200): obj.shadow(qp[i % 50:i % 50 + 1], k=1024)
+pr.disable()
+s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(18); print(s.getvalue()[:6000])
