@@ -55,6 +55,11 @@ def lib() -> ctypes.CDLL:
         L.orc_shadow_topk.restype = ctypes.c_int
         L.orc_shadow_topk.argtypes = [fp, i64, i64, i64, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                       i64, ctypes.c_int32, fp, ip, ctypes.c_int]
+        L.orc_embed_topk.restype = ctypes.c_int
+        L.orc_embed_topk.argtypes = [fp, i64, i64, i64, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, fp,
+                                     ctypes.c_int, i64, ctypes.c_int32, fp, ip, ctypes.c_int]
+        L.orc_embed_row.restype = None
+        L.orc_embed_row.argtypes = [fp, i64, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, fp]
         L.orc_gather_paths.restype = None
         L.orc_gather_paths.argtypes = [fp, i64, ip, i64, ctypes.c_int, fp]
         L.orc_num_threads.restype = ctypes.c_int
@@ -143,6 +148,56 @@ def shadow(dataset, x_context, k: int, H: int):
     q = _queries(x_context)
     d, idx = shadow_topk(dataset, q, k, H)
     return d, gather_paths(dataset, idx, q.shape[1] + H), idx
+
+
+# ----------------------------------------------------------------------------------------
+# general linear embedding (PathEmbedding(kernel), Foveal): path_embedding.py:117-132,142-172
+# ----------------------------------------------------------------------------------------
+def foveal_kernel(alpha: float, beta: float, max_context: int) -> np.ndarray:
+    """(d, W) kernel of Foveal(alpha, beta, max_context) restated from path_embedding.py:152-170:
+    d = floor(log W / log alpha) trailing boxes of lengths int(alpha**n), weight length**-beta."""
+    dim = int(np.floor(np.log(max_context) / np.log(alpha)))
+    K = np.zeros((dim, max_context), np.float32)
+    for n in range(1, dim + 1):
+        le = int(alpha ** n)
+        K[n - 1, max_context - le:] = np.float32(le ** (-beta))
+    return K
+
+
+def embed_queries(kernel, x_context) -> np.ndarray:
+    """ex (B, d): the context embedded (one window); fp64 dot products rounded once."""
+    K = _f32(kernel).reshape(kernel.shape[0], -1)
+    q = _queries(x_context)
+    return (K.astype(np.float64) @ q.astype(np.float64).T).T.astype(np.float32)
+
+
+def embed_row(y, kernel, H: int) -> np.ndarray:
+    """(T', d) embedded windows of one trajectory."""
+    K = _f32(kernel).reshape(kernel.shape[0], -1)
+    y = _f32(y).reshape(-1)
+    d, W = K.shape
+    out = np.empty((y.shape[0] - W - H + 1, d), np.float32)
+    lib().orc_embed_row(_fp(y), y.shape[0], _fp(K), d, W, H, _fp(out))
+    return out
+
+
+def embed_topk(dataset, kernel, ex, k: int, H: int, row_offset: int = 0, nthreads: int = 0):
+    """k closest windows in EMBEDDED space: ex (B, d) embedded queries, kernel (d, W) or (d,1,W).
+    (d (B,k) f32 ascending, idx (B,k,2) i32 [r,t]); ties by (d, r*T'+t)."""
+    ds = _rows(dataset)
+    K = _f32(kernel).reshape(kernel.shape[0], -1)
+    ex = _f32(ex)
+    R, T = ds.shape
+    d_, W = K.shape
+    B = ex.shape[0]
+    assert ex.shape[1] == d_
+    d = np.empty((B, k), np.float32)
+    idx = np.empty((B, k, 2), np.int32)
+    rc = lib().orc_embed_topk(_fp(ds), R, T, T, _fp(K), d_, W, H, _fp(ex), B, k, row_offset, _fp(d),
+                              idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), nthreads)
+    if rc != 0:
+        raise RuntimeError(f"oracle: invalid arguments (rc={rc})")
+    return d, idx
 
 
 # ----------------------------------------------------------------------------------------

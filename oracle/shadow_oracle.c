@@ -115,6 +115,62 @@ static int rec_cmp(const void *a, const void *b) {
     return rec_less(x, y) ? -1 : (rec_less(y, x) ? 1 : 0);
 }
 
+/* one row of distances of one query: buf[t], t < T' */
+typedef void (*rowdist_fn)(const void *ctx, int64_t r, float *buf);
+
+/* k smallest records of one query over all R*T' windows, ascending in (distance, flat index) */
+static int topk_rows(rowdist_fn fn, const void *ctx, int64_t R, int64_t Tp, int64_t k, int32_t row_offset,
+                     float *out_d, int32_t *out_idx, int nthreads) {
+    rec_t *heaps = malloc(sizeof(rec_t) * (size_t)k * (size_t)nthreads);
+    int64_t *hn = calloc((size_t)nthreads, sizeof(int64_t));
+    if (!heaps || !hn) { free(heaps); free(hn); return -2; }
+#pragma omp parallel num_threads(nthreads)
+    {
+#ifdef _OPENMP
+        int tid = omp_get_thread_num();
+#else
+        int tid = 0;
+#endif
+        rec_t *h = heaps + (size_t)tid * (size_t)k;
+        int64_t n = 0;
+        float *buf = malloc(sizeof(float) * (size_t)Tp);
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t r = 0; r < R; ++r) {
+            fn(ctx, r, buf);
+            for (int64_t t = 0; t < Tp; ++t) {
+                rec_t x; x.dbits = f2u(buf[t]); x.pad = 0; x.flat = r * Tp + t;
+                if (n == k && !(x.dbits < h[0].dbits || (x.dbits == h[0].dbits && x.flat < h[0].flat))) continue;
+                heap_offer(h, &n, k, x);
+            }
+        }
+        hn[tid] = n;
+        free(buf);
+    }
+    /* merge thread heaps */
+    int64_t tot = 0;
+    for (int t = 0; t < nthreads; ++t) tot += hn[t];
+    rec_t *all = malloc(sizeof(rec_t) * (size_t)tot);
+    int64_t o = 0;
+    for (int t = 0; t < nthreads; ++t) {
+        memcpy(all + o, heaps + (size_t)t * (size_t)k, sizeof(rec_t) * (size_t)hn[t]);
+        o += hn[t];
+    }
+    qsort(all, (size_t)tot, sizeof(rec_t), rec_cmp);
+    for (int64_t i = 0; i < k; ++i) {
+        out_d[i] = u2f(all[i].dbits);
+        out_idx[i * 2 + 0] = (int32_t)(all[i].flat / Tp) + row_offset;
+        out_idx[i * 2 + 1] = (int32_t)(all[i].flat % Tp);
+    }
+    free(all); free(heaps); free(hn);
+    return 0;
+}
+
+typedef struct { const float *ds; int64_t row_stride, T; const float *q; int W, H; } ident_ctx;
+static void ident_row(const void *c_, int64_t r, float *buf) {
+    const ident_ctx *c = c_;
+    orc_distances(c->ds, c->row_stride, c->T, r, r + 1, c->q, c->W, c->H, buf);
+}
+
 /*
  * shadow scan: the k closest windows to each of B queries (path_shadowing.py:97-179 with the
  * split loop collapsed -- the merge of per-split top-k's equals the global top-k).
@@ -133,48 +189,71 @@ int orc_shadow_topk(const float *ds, int64_t R, int64_t T, int64_t row_stride,
     nthreads = 1;
 #endif
     for (int b = 0; b < B; ++b) {
-        const float *qb = q + (int64_t)b * W;
-        rec_t *heaps = malloc(sizeof(rec_t) * (size_t)k * (size_t)nthreads);
-        int64_t *hn = calloc((size_t)nthreads, sizeof(int64_t));
-        if (!heaps || !hn) { free(heaps); free(hn); return -2; }
-#pragma omp parallel num_threads(nthreads)
-        {
+        ident_ctx c = { ds, row_stride, T, q + (int64_t)b * W, W, H };
+        int rc = topk_rows(ident_row, &c, R, Tp, k, row_offset, out_d + (int64_t)b * k,
+                           out_idx + (int64_t)b * k * 2, nthreads);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+/*
+ * General LINEAR embedding (PathEmbedding with a (d,1,W) kernel, e.g. Foveal; path_embedding.py:
+ * 117-132,142-172): the reference embeds every window with conv1d, e_n(t) = sum_j K[n][j] y[t+j]
+ * (kernel zero-padded by H, so t < T' = T-W-H+1), and measures RelativeMSE between the embedded
+ * query ex (d values) and e(t) over the d dimensions (path_distance.py:62-65).
+ * oneDNN's fp32 accumulation order inside the conv is not replayable, so this
+ * oracle DEFINES e_n(t) as the fp64 dot product rounded once to fp32 -- the reference's values
+ * differ from it by its own fp32 rounding (~1e-7 relative; pinned within tolerance by
+ * tests/test_oracle.py against a live-reference fixture) -- and then follows the reference's
+ * sequence exactly: s = fl(s + fl(fl(ex_n - e_n)^2)), n ascending; sqrt; divide by ||ex|| (8-lane).
+ */
+typedef struct { const float *ds; int64_t row_stride, T; const float *K; int d, W, H; const float *ex; } emb_ctx;
+static void emb_row(const void *c_, int64_t r, float *buf) {
+    const emb_ctx *c = c_;
+    int64_t Tp = c->T - c->W - c->H + 1;
+    const float *y = c->ds + r * c->row_stride;
+    float den = orc_qnorm(c->ex, c->d);
+    for (int64_t t = 0; t < Tp; ++t) {
+        float s = 0.0f;
+        for (int n = 0; n < c->d; ++n) {
+            const float *kn = c->K + (int64_t)n * c->W;
+            double e = 0.0;
+            for (int j = 0; j < c->W; ++j) e += (double)kn[j] * (double)y[t + j];
+            float df = c->ex[n] - (float)e;
+            float sq = df * df;
+            s = s + sq;
+        }
+        buf[t] = sqrtf(s) / den;
+    }
+}
+
+/* embedded windows of one row: out[t*d + n] = e_n(t) (test helper) */
+void orc_embed_row(const float *y, int64_t T, const float *K, int d, int W, int H, float *out) {
+    int64_t Tp = T - W - H + 1;
+    for (int64_t t = 0; t < Tp; ++t)
+        for (int n = 0; n < d; ++n) {
+            double e = 0.0;
+            for (int j = 0; j < W; ++j) e += (double)K[(int64_t)n * W + j] * (double)y[t + j];
+            out[t * d + n] = (float)e;
+        }
+}
+
+int orc_embed_topk(const float *ds, int64_t R, int64_t T, int64_t row_stride,
+                   const float *K, int d, int W, int H, const float *ex, int B, int64_t k, int32_t row_offset,
+                   float *out_d, int32_t *out_idx, int nthreads) {
+    int64_t Tp = T - W - H + 1;
+    if (Tp <= 0 || k <= 0 || k > R * Tp) return -1;
 #ifdef _OPENMP
-            int tid = omp_get_thread_num();
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
 #else
-            int tid = 0;
+    nthreads = 1;
 #endif
-            rec_t *h = heaps + (size_t)tid * (size_t)k;
-            int64_t n = 0;
-            float *buf = malloc(sizeof(float) * (size_t)Tp);
-#pragma omp for schedule(dynamic, 16)
-            for (int64_t r = 0; r < R; ++r) {
-                orc_distances(ds, row_stride, T, r, r + 1, qb, W, H, buf);
-                for (int64_t t = 0; t < Tp; ++t) {
-                    rec_t x; x.dbits = f2u(buf[t]); x.pad = 0; x.flat = r * Tp + t;
-                    if (n == k && !(x.dbits < h[0].dbits || (x.dbits == h[0].dbits && x.flat < h[0].flat))) continue;
-                    heap_offer(h, &n, k, x);
-                }
-            }
-            hn[tid] = n;
-            free(buf);
-        }
-        /* merge thread heaps */
-        int64_t tot = 0;
-        for (int t = 0; t < nthreads; ++t) tot += hn[t];
-        rec_t *all = malloc(sizeof(rec_t) * (size_t)tot);
-        int64_t o = 0;
-        for (int t = 0; t < nthreads; ++t) {
-            memcpy(all + o, heaps + (size_t)t * (size_t)k, sizeof(rec_t) * (size_t)hn[t]);
-            o += hn[t];
-        }
-        qsort(all, (size_t)tot, sizeof(rec_t), rec_cmp);
-        for (int64_t i = 0; i < k; ++i) {
-            out_d[(int64_t)b * k + i] = u2f(all[i].dbits);
-            out_idx[((int64_t)b * k + i) * 2 + 0] = (int32_t)(all[i].flat / Tp) + row_offset;
-            out_idx[((int64_t)b * k + i) * 2 + 1] = (int32_t)(all[i].flat % Tp);
-        }
-        free(all); free(heaps); free(hn);
+    for (int b = 0; b < B; ++b) {
+        emb_ctx c = { ds, row_stride, T, K, d, W, H, ex + (int64_t)b * d };
+        int rc = topk_rows(emb_row, &c, R, Tp, k, row_offset, out_d + (int64_t)b * k,
+                           out_idx + (int64_t)b * k * 2, nthreads);
+        if (rc) return rc;
     }
     return 0;
 }

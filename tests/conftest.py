@@ -64,3 +64,21 @@ def assert_topk_equal(d, idx, d_ref, idx_ref):
                 assert a == r, f"indices differ at query {b}, ranks {i}..{j}"
             # a tie group cut by the k boundary may legitimately hold different members
             i = j + 1
+
+
+def assert_topk_close(d, idx, d_ref, idx_ref, rtol=1e-6):
+    """Tolerance parity for embedded scans (Foveal / PathEmbedding(kernel)): the reference's conv1d
+    accumulates in an order that cannot be replayed, so distances agree to `rtol` (north_star: 1e-6
+    relative fp32) and indices agree up to (i) swaps among windows whose distances lie within the
+    tolerance of each other and (ii) exchanges at the k-th boundary within the tolerance."""
+    d = np.asarray(d); d_ref = np.asarray(d_ref); idx = np.asarray(idx); idx_ref = np.asarray(idx_ref)
+    assert d.shape == d_ref.shape and idx.shape == idx_ref.shape
+    assert np.allclose(d, d_ref, rtol=rtol, atol=0.0), float(np.max(np.abs(d - d_ref) / np.abs(d_ref)))
+    for b in range(d.shape[0]):
+        ref_pos = {tuple(v): j for j, v in enumerate(idx_ref[b])}
+        for j, v in enumerate(idx[b]):
+            jr = ref_pos.get(tuple(v))
+            if jr is None:   # only a window as far as the boundary may be exchanged for another one
+                assert d[b, j] >= d_ref[b, -1] * (1.0 - 4 * rtol), (b, j)
+            else:            # same window: same distance up to the tolerance, wherever it was ranked
+                assert abs(d[b, j] - d_ref[b, jr]) <= 2 * rtol * d_ref[b, jr], (b, j, jr)

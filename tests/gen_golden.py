@@ -78,6 +78,35 @@ def main():
     np.savez(OUT / "forward_topk_B8_d34.npz", x=x.numpy(), y=y.numpy(), ds=ds2.numpy(), idces=id2.numpy())
     print("forward_topk", ds2.shape, id2.shape, id2.dtype)
 
+    # Foveal embedding (path_embedding.py:142-172) on the configuration of the reference's own
+    # self-consistency cell, testing.ipynb:62-78: x_context randn(8,1,126), dataset randn(32,1,4096),
+    # Foveal(1.15, 0.9, 126), PredictionContext(252), k=1024.  Paths are not stored (12 MB): they
+    # are dataset[r, t:t+W+H] of the stored indices.
+    g = torch.Generator().manual_seed(10)
+    ds = torch.randn(32, 1, 4096, generator=g)
+    x = torch.randn(8, 1, 126, generator=g)
+    emb = ref.path_embedding.Foveal(1.15, 0.9, 126)
+    obj = PS(emb, ref.path_distance.RelativeMSE(), ds, ref.path_embedding.PredictionContext(252))
+    d, paths, idx = obj.shadow(x, k=1024, n_splits=4, cuda=False)
+    assert np.array_equal(paths[3, 7, 0], ds.numpy()[idx[3, 7, 0], 0, idx[3, 7, 1]:idx[3, 7, 1] + 378])
+    np.savez_compressed(OUT / "foveal_R32_T4096_W126.npz", dataset=ds.numpy(), x_context=x.numpy(),
+                        kernel=emb.kernel.numpy(), ex=emb(x)[:, 0, :].numpy(), distances=d, indices=idx,
+                        meta=np.array([32, 4096, 126, 252, 1024, 8, 4], np.int64),
+                        foveal=np.array([1.15, 0.9, 126.0]))
+    print("foveal", d.shape, idx.shape, emb.kernel.shape)
+
+    # a generic dense PathEmbedding(kernel) (path_embedding.py:117-132): 5 random rows of 16 taps
+    g = torch.Generator().manual_seed(11)
+    ds = torch.randn(16, 1, 300, generator=g) * 0.01
+    x = torch.randn(3, 1, 16, generator=g) * 0.01
+    emb = ref.path_embedding.PathEmbedding(torch.randn(5, 1, 16, generator=g))
+    obj = PS(emb, ref.path_distance.RelativeMSE(), ds, ref.path_embedding.PredictionContext(4))
+    d, paths, idx = obj.shadow(x, k=64, n_splits=2, cuda=False)
+    np.savez_compressed(OUT / "dense_kernel_R16_T300_W16.npz", dataset=ds.numpy(), x_context=x.numpy(),
+                        kernel=emb.kernel.numpy(), ex=emb(x)[:, 0, :].numpy(), distances=d, indices=idx,
+                        paths=paths, meta=np.array([16, 300, 16, 4, 64, 3, 2], np.int64))
+    print("dense kernel", d.shape, idx.shape)
+
 
 if __name__ == "__main__":
     main()

@@ -116,3 +116,32 @@ def test_live_reference_matches_oracle_on_fresh_inputs():
     do, po, io = oracle.shadow(ds, q, 300, 12)
     assert_topk_equal(do, io, d, idx)
     assert np.array_equal(po, paths)
+
+
+# ---------------------------------------------------------------------------------------------
+# embedded scans (Foveal / PathEmbedding(kernel)): the oracle's fp64-dot-product definition
+# against live-reference fixtures, within north_star's 1e-6 relative tolerance
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["foveal_R32_T4096_W126", "dense_kernel_R16_T300_W16"])
+def test_embed_oracle_matches_reference_fixture(name):
+    from conftest import assert_topk_close
+    g = load_golden(name)
+    K = g["kernel"][:, 0, :]
+    if "foveal" in g:
+        a, b, w = g["foveal"]
+        assert np.array_equal(oracle.foveal_kernel(float(a), float(b), int(w)), K)
+    ex = oracle.embed_queries(K, g["x_context"])
+    assert np.abs(ex - g["ex"]).max() <= 1e-6 * np.abs(g["ex"]).max()   # fp32 conv vs fp64 dot product
+    d, idx = oracle.embed_topk(g["dataset"], K, g["ex"], g["k"], g["H"])
+    assert_topk_close(d, idx, g["distances"], g["indices"])
+    assert (np.diff(d, axis=1) >= 0).all()
+
+
+def test_embed_oracle_identity_kernel_equals_identity_scan():
+    """PathEmbedding(eye(W)) through the embedded oracle == the Identity oracle, bit for bit
+    (an fp64 'dot product' with one unit tap is the sample itself)."""
+    from conftest import make_inputs
+    ds, q = make_inputs(9, 200, 12, 2, seed=4)
+    d1, i1 = oracle.shadow_topk(ds, q, 40, 3)
+    d2, i2 = oracle.embed_topk(ds, np.eye(12, dtype=np.float32), q[:, 0, :], 40, 3)
+    assert np.array_equal(d1, d2) and np.array_equal(i1, i2)
