@@ -80,6 +80,30 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
                       float *d_out_dist, int32_t *d_out_idx,
                       void *d_ws, size_t ws_bytes, const void *d_aux, size_t aux_bytes, void *stream);
 
+/*
+ * The scan in EMBEDDED space: replaces PathShadowing.batched_distance (path_shadowing.py:97-179)
+ * for any LINEAR embedding -- PathEmbedding(kernel) with a (d, 1, W) kernel, e.g. Foveal
+ * (path_embedding.py:117-132, 142-172) -- and RelativeMSE over the d embedded dimensions
+ * (path_distance.py:62-65).  The reference embeds every window with conv1d (kernel zero-padded by
+ * H); here the kernel arrives decomposed into runs of equal taps and every window is evaluated
+ * from a prefix sum of its staged row segment:  e_n(t) = sum_runs c (P[t+b] - P[t+a]).
+ *
+ *   d_qemb   (B, d) contiguous fp32: the EMBEDDED contexts (the caller embeds the few query
+ *            windows itself, as path_shadowing.py:138 does)
+ *   d_runs   (nruns) records {int32 row, int32 a, int32 b, float c}: kernel[row][a..b) == c,
+ *            0 <= a < b <= W, rows ascending (rows without runs are all-zero taps)
+ *   flags    0 or PSH_FLAG_NOSYNC;   everything else as psh_scan_topk_f32 (same workspace size)
+ *
+ * Distances follow the reference's sequence over the embedded dimensions (s accumulated n
+ * ascending, non-fused; sqrt; divide by ||ex|| in torch's order); the embedded values themselves
+ * are box sums accurate to ~2 ulp, whereas the reference's conv1d rounds in an order that cannot be
+ * replayed: parity with the reference is within 1e-6 relative, indices up to near-ties.
+ */
+int psh_scan_topk_embed_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride,
+                            const float *d_qemb, int B, int d, int W, int H, int64_t k,
+                            int32_t row_offset, int flags, const void *d_runs, int nruns,
+                            float *d_out_dist, int32_t *d_out_idx, void *d_ws, size_t ws_bytes, void *stream);
+
 /* After one or more PSH_FLAG_NOSYNC scans on the same workspace (and whatever the caller enqueued
  * behind them): synchronise the stream and report PSH_OK, or PSH_E_OVERFLOW if a candidate buffer
  * overflowed in ANY of those scans since the previous check (adversarially ordered data; the

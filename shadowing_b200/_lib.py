@@ -47,6 +47,9 @@ def lib() -> ctypes.CDLL:
         L.psh_scan_workspace_bytes.argtypes = [i64, i64, ci, ci, ci, i64]
         L.psh_scan_topk_f32.restype = ci
         L.psh_scan_topk_f32.argtypes = [vp, i64, i64, i64, vp, ci, ci, ci, i64, i32, ci, vp, vp, vp, sz, vp, sz, vp]
+        L.psh_scan_topk_embed_f32.restype = ci
+        L.psh_scan_topk_embed_f32.argtypes = [vp, i64, i64, i64, vp, ci, ci, ci, ci, i64, i32, ci, vp, ci,
+                                              vp, vp, vp, ctypes.c_size_t, vp]
         L.psh_scan_overflowed.restype = ci
         L.psh_scan_overflowed.argtypes = [vp, ci, vp]
         L.psh_fft_aux_bytes.restype = sz
@@ -178,6 +181,32 @@ def scan_topk(ds: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int, row_off
                                  aux.data_ptr() if aux is not None else None, aux.numel() if aux is not None else 0,
                                  _stream(ds))
     _check(rc, "psh_scan_topk_f32")
+    return dist, idx, workspace
+
+
+def scan_topk_embed(ds: torch.Tensor, T: int, ex: torch.Tensor, W: int, H: int, k: int, runs: torch.Tensor,
+                    row_offset: int = 0, nosync: bool = False, workspace: torch.Tensor | None = None,
+                    out: tuple[torch.Tensor, torch.Tensor] | None = None):
+    """Scan in embedded space: ex (B, d) f32 cuda embedded queries, runs (nruns, 4) 32-bit words cuda
+    [row, a, b, c] (path_embedding.kernel_runs) -> (dist (B,k) f32, idx (B,k,2) i32) cuda."""
+    L = lib()
+    assert ds.is_cuda and ex.is_cuda and runs.is_cuda and ex.dtype == torch.float32 and ex.is_contiguous()
+    R, row_stride = ds.shape[0], ds.stride(0)
+    B, d = ex.shape
+    need = L.psh_scan_workspace_bytes(R, T, B, W, H, k) or 256
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=ds.device)
+    if out is not None:
+        dist, idx = out
+    else:
+        dist = torch.empty((B, k), dtype=torch.float32, device=ds.device)
+        idx = torch.empty((B, k, 2), dtype=torch.int32, device=ds.device)
+    with torch.cuda.device(ds.device):
+        rc = L.psh_scan_topk_embed_f32(ds.data_ptr(), R, T, row_stride, ex.data_ptr(), B, d, W, H, k, row_offset,
+                                       PSH_FLAG_NOSYNC if nosync else 0, runs.data_ptr(), runs.shape[0],
+                                       dist.data_ptr(), idx.data_ptr(), workspace.data_ptr(), workspace.numel(),
+                                       _stream(ds))
+    _check(rc, "psh_scan_topk_embed_f32")
     return dist, idx, workspace
 
 

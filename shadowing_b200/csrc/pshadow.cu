@@ -486,6 +486,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, EXACT ? 2 : 3) scan_kernel(const
     }
 }
 
+#include "pshadow_embed.cuh"
+
 // ------------------------------------------------------------------------------------------
 // FFT flavour: preparation kernels, query spectrum, scan
 // ------------------------------------------------------------------------------------------
@@ -1931,10 +1933,11 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
                           const float *d_q, int nq, int W, int H, long long k, int row_offset,
                           const Plan &pl, QState *st, unsigned long long *keys, unsigned int *cand, float2 *qspec,
                           unsigned int *fhist, unsigned int *shist, const FftAux *aux, int mode, bool safe,
-                          float *d_out_dist, int *d_out_idx, cudaStream_t stream) {
+                          float *d_out_dist, int *d_out_idx, cudaStream_t stream, const EmbParams *emb = nullptr) {
     (void)H;
     const bool use_fft = (mode == PSH_MODE_FFT) && !safe && aux != nullptr;
-    qprep_kernel<<<(nq + 3) / 4, 128, 0, stream>>>(d_q, W, nq, st,
+    // embedded scan: d_q holds the EMBEDDED queries (nq, d); ||ex|| in torch's order comes from the same kernel
+    qprep_kernel<<<(nq + 3) / 4, 128, 0, stream>>>(d_q, emb ? emb->d : W, nq, st,
                                                    use_fft ? reinterpret_cast<uint4 *>(fhist) : nullptr, FFT_NB / 4,
                                                    use_fft ? reinterpret_cast<uint4 *>(shist) : nullptr, SEED_STRIDE / 4);
     PSH_LAUNCHED();
@@ -1964,7 +1967,19 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
     p.cw = (float)(W + 256) * 5.9604644775390625e-8f;
     p.buf_floats = (int)align_up((size_t)need + RING + 4, 4);
     if (p.buf_floats < 32 * p.epl + 4) p.buf_floats = 32 * p.epl + 4;
-    p.wpad = (int)align_up((size_t)W + 4, 4);
+    p.wpad = (int)align_up((size_t)(emb ? emb->d : W) + 4, 4);
+    EmbParams ep;
+    size_t smem_emb = 0;
+    if (emb) {
+        ep = *emb;
+        ep.ps_n = (int)align_up((size_t)SEG + W + 1, 2);
+        smem_emb = (size_t)nq * p.wpad * sizeof(float) + (size_t)ep.nruns * sizeof(EmbRun)
+                   + (size_t)SCAN_WARPS * ep.ps_n * sizeof(float2)
+                   + (size_t)SCAN_WARPS * 2 * p.buf_floats * sizeof(float) + (size_t)SCAN_WARPS * 2 * sizeof(unsigned long long);
+        if (smem_emb > 200 * 1024) return PSH_E_UNSUPPORTED;
+        PSH_CUDA(cudaFuncSetAttribute(emb_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_emb));
+        PSH_CUDA(cudaFuncSetAttribute(emb_scan_kernel<EMB_QG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_emb));
+    }
     const size_t smem_exact = ((size_t)nq * p.wpad + (size_t)SCAN_WARPS * 2 * p.buf_floats) * sizeof(float)
                               + (size_t)SCAN_WARPS * 2 * sizeof(unsigned long long);
     const size_t smem_filter = smem_exact + (size_t)SCAN_WARPS * p.pfx_floats * sizeof(float);
@@ -2108,7 +2123,14 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
             long long ctas = (ntasks + SCAN_WARPS - 1) / SCAN_WARPS;
             long long max_ctas = (long long)sm_count() * (use_filter ? ctas_per_sm(smem_filter, 3) : ctas_per_sm(smem_exact, 2));
             if (ctas > max_ctas) ctas = max_ctas;
-            if (use_filter) {
+            if (emb) {
+                long long mc = (long long)sm_count() * ctas_per_sm(smem_emb, 2);
+                ctas = (ntasks + SCAN_WARPS - 1) / SCAN_WARPS;
+                if (ctas > mc) ctas = mc;
+                ProfScope ps(stream, 0);
+                if (nq == 1) emb_scan_kernel<1><<<(unsigned int)ctas, SCAN_THREADS, smem_emb, stream>>>(p, ep);
+                else emb_scan_kernel<EMB_QG><<<(unsigned int)ctas, SCAN_THREADS, smem_emb, stream>>>(p, ep);
+            } else if (use_filter) {
                 ProfScope ps(stream, 0);
                 scan_kernel<false><<<(unsigned int)ctas, SCAN_THREADS, smem_filter, stream>>>(p);
             } else {
@@ -2142,12 +2164,14 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
     return launch_finalize(pl, st, keys, nq, k, row_offset, d_out_dist, d_out_idx, stream);
 }
 
-int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride,
+static int scan_entry(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride,
                       const float *d_queries, int B, int W, int H, int64_t k,
                       int32_t row_offset, int mode,
                       float *d_out_dist, int32_t *d_out_idx,
-                      void *d_ws, size_t ws_bytes, const void *d_aux, size_t aux_bytes, void *stream_) {
+                      void *d_ws, size_t ws_bytes, const void *d_aux, size_t aux_bytes, void *stream_,
+                      const EmbParams *emb) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    const int qstride = emb ? emb->d : W;   // floats per query in d_queries
     const bool nosync = (mode & PSH_FLAG_NOSYNC) != 0;
     mode &= ~PSH_FLAG_NOSYNC;
     if (mode != PSH_MODE_EXACT && mode != PSH_MODE_FILTER && mode != PSH_MODE_FFT) return PSH_E_ARG;
@@ -2180,10 +2204,10 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
 
     for (int g0 = 0; g0 < B; g0 += QG_MAX) {
         int nq = B - g0 < QG_MAX ? B - g0 : QG_MAX;
-        int rc = run_scan_group(d_dataset, R, T, row_stride, d_queries + (size_t)g0 * W, nq, W, H, k, row_offset,
+        int rc = run_scan_group(d_dataset, R, T, row_stride, d_queries + (size_t)g0 * qstride, nq, W, H, k, row_offset,
                                 pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap, qspec + (size_t)g0 * fftx::N, fhist_all + (size_t)g0 * FFT_NB, shist_all + (size_t)g0 * SEED_STRIDE, auxp, mode, false,
                                 d_out_dist + (size_t)g0 * k * (d_out_idx ? 1 : 3),
-                                d_out_idx ? d_out_idx + (size_t)g0 * k * 2 : nullptr, stream);
+                                d_out_idx ? d_out_idx + (size_t)g0 * k * 2 : nullptr, stream, emb);
         if (rc != PSH_OK) return rc;
     }
     if (nosync) return PSH_OK;  // the caller checks psh_scan_overflowed() before trusting the results
@@ -2198,11 +2222,11 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
         bool ovf = false;
         for (int i = 0; i < nq; ++i) ovf = ovf || hst[g0 + i].overflow != 0;
         if (ovf) {
-            int rc = run_scan_group(d_dataset, R, T, row_stride, d_queries + (size_t)g0 * W, nq, W, H, k, row_offset,
+            int rc = run_scan_group(d_dataset, R, T, row_stride, d_queries + (size_t)g0 * qstride, nq, W, H, k, row_offset,
                                     pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap, qspec + (size_t)g0 * fftx::N, fhist_all + (size_t)g0 * FFT_NB, shist_all + (size_t)g0 * SEED_STRIDE, auxp, mode,
                                     true,
                                     d_out_dist + (size_t)g0 * k * (d_out_idx ? 1 : 3),
-                                d_out_idx ? d_out_idx + (size_t)g0 * k * 2 : nullptr, stream);
+                                d_out_idx ? d_out_idx + (size_t)g0 * k * 2 : nullptr, stream, emb);
             if (rc != PSH_OK) return rc;
             redone = true;
         }
@@ -2213,6 +2237,29 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
         PSH_CUDA(cudaStreamSynchronize(stream));
     }
     return PSH_OK;
+}
+
+int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride,
+                      const float *d_queries, int B, int W, int H, int64_t k,
+                      int32_t row_offset, int mode,
+                      float *d_out_dist, int32_t *d_out_idx,
+                      void *d_ws, size_t ws_bytes, const void *d_aux, size_t aux_bytes, void *stream_) {
+    return scan_entry(d_dataset, R, T, row_stride, d_queries, B, W, H, k, row_offset, mode, d_out_dist, d_out_idx,
+                      d_ws, ws_bytes, d_aux, aux_bytes, stream_, nullptr);
+}
+
+int psh_scan_topk_embed_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride,
+                            const float *d_qemb, int B, int d, int W, int H, int64_t k,
+                            int32_t row_offset, int flags, const void *d_runs, int nruns,
+                            float *d_out_dist, int32_t *d_out_idx, void *d_ws, size_t ws_bytes, void *stream_) {
+    if (!d_runs || nruns <= 0 || d <= 0 || (flags & ~PSH_FLAG_NOSYNC) != 0) return PSH_E_ARG;
+    EmbParams ep;
+    ep.runs = static_cast<const EmbRun *>(d_runs);
+    ep.nruns = nruns;
+    ep.d = d;
+    ep.ps_n = 0;
+    return scan_entry(d_dataset, R, T, row_stride, d_qemb, B, W, H, k, row_offset, PSH_MODE_EXACT | flags, d_out_dist,
+                      d_out_idx, d_ws, ws_bytes, nullptr, 0, stream_, &ep);
 }
 
 int psh_scan_overflowed(const void *d_ws, int B, void *stream_) {

@@ -3,9 +3,12 @@ shadowing/path_shadowing/path_embedding.py, kept name- and signature-compatible.
 
 On the B200 path the embedding is never *applied* to the dataset: `Identity(W)` tells the scan
 that the embedded window IS the raw window (the reference's conv1d with eye(W),
-path_embedding.py:129-139), and the context manager tells it how many trailing samples of each
+path_embedding.py:129-139); any other linear kernel (`Foveal`, `PathEmbedding(kernel)`) is
+decomposed into runs of equal taps (`kernel_runs`) that the embedded scan evaluates from prefix
+sums in shared memory; and the context manager tells it how many trailing samples of each
 window are out-of-context (pad_context, path_embedding.py:48-51).  `forward` is still provided
-(user code embeds small tensors for plots and checks, e.g. tutorial.ipynb cell 8).
+(the scan embeds the few query windows with it, exactly as the reference does, and user code
+embeds small tensors for plots and checks, e.g. tutorial.ipynb cell 8).
 """
 from __future__ import annotations
 
@@ -74,3 +77,43 @@ class Identity(PathEmbedding):
     def __init__(self, dimension: int):
         self.d = dimension
         super().__init__(torch.eye(dimension)[:, None, :])
+
+
+class Foveal(PathEmbedding):
+    """Foveal embedding: the context seen at a resolution that coarsens with the distance to the
+    present -- `dim = floor(log(max_context) / log(alpha))` trailing box sums of lengths
+    `int(alpha ** n)`, n = 1..dim, each weighted by `length ** -beta`.  Same constructor, attributes
+    (`alpha`, `beta`, `max_context`, `dim`, `slices`) and kernel as path_embedding.py:142-172."""
+
+    def __init__(self, alpha: float, beta: float, max_context: int, device: str = "cpu"):
+        self.alpha = alpha
+        self.beta = beta
+        self.max_context = max_context
+        self.dim = int(np.floor(np.log(max_context) / np.log(alpha)))
+        lengths = [int(alpha ** n) for n in range(1, 1 + self.dim)]
+        self.slices = [slice(-le, None) for le in lengths]
+        kernel = torch.zeros(self.dim, 1, max_context, dtype=torch.float32, device=device)
+        for row, le in enumerate(lengths):
+            kernel[row, :, -le:] = le ** (-beta)
+        super().__init__(kernel)
+
+
+def kernel_runs(kernel: torch.Tensor) -> np.ndarray:
+    """Decompose a (d, 1, W) embedding kernel into runs of equal non-zero taps: a structured array
+    of (row, a, b, c) with kernel[row, 0, a:b] == c, rows ascending -- what the embedded scan
+    evaluates as c * (P[t+b] - P[t+a]) on a prefix sum P.  Foveal: one run per row."""
+    K = kernel.detach().cpu().numpy()
+    if K.ndim != 3 or K.shape[1] != 1:
+        raise RuntimeError(f"expected a (d, 1, W) embedding kernel, got {tuple(K.shape)}")
+    K = K[:, 0, :].astype(np.float32)
+    runs = []
+    for n in range(K.shape[0]):
+        row = K[n]
+        cuts = np.flatnonzero(np.diff(row.view(np.uint32)) != 0) + 1   # bit-pattern changes (NaN-safe)
+        starts = np.concatenate(([0], cuts))
+        ends = np.concatenate((cuts, [row.shape[0]]))
+        for a, b in zip(starts, ends):
+            if row[a] != 0.0:
+                runs.append((n, int(a), int(b), float(row[a])))
+    dt = np.dtype([("row", np.int32), ("a", np.int32), ("b", np.int32), ("c", np.float32)])
+    return np.array(runs, dtype=dt)

@@ -11,8 +11,9 @@ CUDA through libpshadow.so (include/pshadow.h):
   `n_splits` / `n_dataset_splits` are accepted and ignored;
 * `cuda` is accepted and ignored: this implementation has no CPU path.
 
-Only Identity + RelativeMSE + PredictionContext run on the device; any other plugin
-combination raises NotImplementedError (no silent fallback).
+Linear embeddings (Identity: exact/filter/fft scans; Foveal and any PathEmbedding(kernel): the
+embedded scan) + RelativeMSE + PredictionContext run on the device; any other plugin combination
+raises NotImplementedError (no silent fallback).
 """
 from __future__ import annotations
 
@@ -26,7 +27,8 @@ import torch
 from . import _lib
 from .averaging import DiscreteProba, Softmax, Uniform
 from .path_distance import PathDistance, RelativeMSE
-from .path_embedding import ArrayType, ContextManagerBase, Identity, PathEmbedding, PredictionContext
+from .path_embedding import (ArrayType, ContextManagerBase, Foveal, Identity, PathEmbedding, PredictionContext,
+                             kernel_runs)
 from .statistics import RealizedVariance
 
 
@@ -131,6 +133,7 @@ class PathShadowing:
         self._workspace = None
         self._fft_aux = None   # (key, aux buffer) for (resident rows, W, H)
         self._staging = None   # pinned host buffers for the results of shadow()
+        self._runs = None      # (key, device run table) of a non-Identity embedding kernel
 
     # ------------------------------------------------------------------ device residency
     def _dev(self) -> torch.device:
@@ -140,9 +143,10 @@ class PathShadowing:
         return self._device
 
     def _check_plugins(self) -> None:
-        if type(self.embedding) is not Identity:
+        if not isinstance(self.embedding, PathEmbedding) or self.embedding.kernel.dim() != 3:
             raise NotImplementedError(
-                f"the B200 scan implements the Identity embedding; got {type(self.embedding).__name__}")
+                f"the B200 scan implements linear embeddings (PathEmbedding with a (d,1,W) kernel: Identity, "
+                f"Foveal, ...); got {type(self.embedding).__name__}")
         if type(self.distance) is not RelativeMSE:
             raise NotImplementedError(
                 f"the B200 scan implements the RelativeMSE distance; got {type(self.distance).__name__}")
@@ -204,8 +208,10 @@ class PathShadowing:
             raise RuntimeError(f"expected a float32 context, got {x.dtype}")  # reference: conv1d dtype error
         if x.shape[1] != 1:
             raise RuntimeError(f"expected a single-channel context (B, 1, W), got {tuple(x.shape)}")
-        q = x[:, 0, :].to(dev, non_blocking=True).contiguous()
         H = self.context.get_out_times()
+        if type(self.embedding) is not Identity:
+            return self._scan_embedded(x, rows, T, k, H, out, nosync)
+        q = x[:, 0, :].to(dev, non_blocking=True).contiguous()
         W = q.shape[1]
         if self._pg is None:
             n_windows = rows.shape[0] * (T - W - H + 1)
@@ -222,6 +228,36 @@ class PathShadowing:
         from .distributed import finish_sharded, sharded_scan
         res = sharded_scan(self, rows, T, q, H, k)
         return res if nosync else finish_sharded(self, rows, T, q, H, k, res)
+
+    def _scan_embedded(self, x: torch.Tensor, rows: torch.Tensor, T: int, k: int, H: int, out, nosync: bool):
+        """Foveal / PathEmbedding(kernel): the few query windows are embedded on the host with the
+        embedding's own forward -- the reference's `embedding(x)[:, 0, :]`, path_shadowing.py:138 --
+        and the ensemble is scanned in embedded space from prefix sums (never materialised)."""
+        if self._pg is not None:
+            raise NotImplementedError("the sharded scan implements the Identity embedding")
+        kernel = self.embedding.kernel
+        W = int(kernel.shape[-1])
+        if x.shape[-1] != W:
+            raise RuntimeError(f"context length {x.shape[-1]} does not match the embedding kernel ({W})")
+        Tp = T - W - H + 1
+        if Tp <= 0:
+            raise RuntimeError(f"context ({W}) + horizon ({H}) longer than the trajectories ({T})")
+        if k > rows.shape[0] * Tp:
+            raise RuntimeError(f"selected index k out of range: k={k} > {rows.shape[0] * Tp} windows")
+        key = (kernel.data_ptr(), tuple(kernel.shape), kernel._version)
+        if self._runs is None or self._runs[0] != key:
+            runs = kernel_runs(kernel)
+            if runs.shape[0] == 0:
+                raise RuntimeError("the embedding kernel is identically zero")
+            words = torch.from_numpy(runs.view(np.int32).reshape(-1, 4).copy())
+            self._runs = (key, words.to(rows.device))
+        with torch.no_grad():
+            ex = self.embedding.to(x.device)(x)[:, 0, :]          # (B, d), as the reference embeds the context
+        ex = ex.to(rows.device, non_blocking=True).contiguous()
+        dist, idx, self._workspace = _lib.scan_topk_embed(rows, T, ex, W, H, k, self._runs[1], self._row_offset,
+                                                          nosync, self._workspace, out)
+        self._pipeline_B = ex.shape[0]
+        return dist, idx
 
     def _check_pipeline(self) -> None:
         """Synchronise behind a pipeline of `nosync` scans; raises if any of them overflowed a

@@ -215,7 +215,9 @@ def test_input_conventions_and_errors():
         obj.shadow(q, k=8 * 256)                                 # k > number of windows
     with pytest.raises(ValueError):
         obj.predict_from_paths(d3, p3, sb.RealizedVariance([2]), "gaussian", 0.1)
-    bad = sb.PathShadowing(sb.PathEmbedding(torch.ones(3, 1, 20)), sb.RelativeMSE(), ds, sb.PredictionContext(5))
+    class OtherContext(sb.PredictionContext):   # only PredictionContext itself runs on the device
+        pass
+    bad = sb.PathShadowing(sb.Identity(20), sb.RelativeMSE(), ds, OtherContext(5))
     with pytest.raises(NotImplementedError):
         bad.shadow(q, k=4)
 
@@ -459,3 +461,107 @@ def test_merge_ties_and_padding(force_sort, monkeypatch):
     d, i = _lib.merge_topk_packed(torch.stack(recs + [pad, pad]), Tp)
     do, io = oracle.shadow_topk(ds, q, k, H)
     assert np.array_equal(d.cpu().numpy(), do) and np.array_equal(i.cpu().numpy(), io)
+
+
+# ---------------------------------------------------------------------------------------------
+# embedded scans: Foveal and generic PathEmbedding(kernel)  
+# ---------------------------------------------------------------------------------------------
+def _gather_ref(ds, idx, L):
+    ds = np.asarray(ds).reshape(ds.shape[0], -1)
+    return np.stack([np.stack([ds[r, t:t + L] for r, t in row]) for row in idx])[:, :, None, :]
+
+
+@pytest.mark.parametrize("name", ["foveal_R32_T4096_W126", "dense_kernel_R16_T300_W16"])
+def test_embedded_scan_matches_reference_fixture(name):
+    """Live-reference fixtures (testing.ipynb:62-78's Foveal configuration; a dense random kernel):
+    distances within 1e-6 relative, indices equal up to near-ties, paths = the indexed windows."""
+    from conftest import assert_topk_close
+    g = load_golden(name)
+    if "foveal" in g:
+        a, b, w = g["foveal"]
+        emb = sb.Foveal(float(a), float(b), int(w))
+        assert torch.equal(emb.kernel, torch.tensor(g["kernel"]))
+    else:
+        emb = sb.PathEmbedding(torch.tensor(g["kernel"]))
+    obj = sb.PathShadowing(emb, sb.RelativeMSE(), g["dataset"], sb.PredictionContext(g["H"]))
+    d, paths, idx = obj.shadow(g["x_context"], k=g["k"], n_splits=g["n_splits"], cuda=True)
+    assert d.dtype == np.float32 and idx.dtype == np.int32 and paths.shape == (g["B"], g["k"], 1, g["W"] + g["H"])
+    assert_topk_close(d, idx, g["distances"], g["indices"])
+    assert np.array_equal(paths, _gather_ref(g["dataset"], idx, g["W"] + g["H"]))
+    if "paths" in g and np.array_equal(idx, g["indices"]):
+        assert np.array_equal(paths, g["paths"])
+
+
+@pytest.mark.parametrize("R,T,W,H,k,B,alpha,beta", [
+    (512, 4096, 126, 252, 1024, 5, 1.15, 0.9),   # the reference benchmark's embedding, 3 + 2 query groups
+    (700, 1000, 64, 0, 300, 1, 1.3, 0.5),        # no horizon, one query
+    (33, 5000, 252, 20, 2000, 4, 1.15, 0.9),     # long rows, 14 segments per row, k > SEG
+])
+def test_foveal_matches_oracle(R, T, W, H, k, B, alpha, beta):
+    from conftest import assert_topk_close
+    ds, q = make_inputs(R, T, W, B, seed=900 + R)
+    emb = sb.Foveal(alpha, beta, W)
+    obj = sb.PathShadowing(emb, sb.RelativeMSE(), ds, sb.PredictionContext(H or None))
+    d, paths, idx = obj.shadow(q, k=k)
+    ex = emb(torch.tensor(q))[:, 0, :].numpy()
+    do, io = oracle.embed_topk(ds, emb.kernel.numpy()[:, 0, :], ex, k, H)
+    assert_topk_close(d, idx, do, io)
+    assert np.array_equal(paths, _gather_ref(ds, idx, W + H))
+    assert (np.diff(d, axis=1) >= 0).all()
+
+
+def test_generic_kernels_through_the_embedded_scan():
+    """Identity as a generic kernel (W one-tap runs) agrees with the exact Identity scan; a
+    piecewise-constant kernel with several runs per row and an all-zero row agrees with the oracle."""
+    from conftest import assert_topk_close
+    ds, q = make_inputs(40, 900, 24, 3, seed=61)
+    d0, _, i0 = _obj(ds, 24, 6).shadow(q, k=200)
+    gen = sb.PathEmbedding(torch.eye(24)[:, None, :].clone())
+    d1, _, i1 = sb.PathShadowing(gen, sb.RelativeMSE(), ds, sb.PredictionContext(6)).shadow(q, k=200)
+    assert_topk_close(d1, i1, d0, i0)
+    K = torch.zeros(4, 1, 24)
+    K[0, 0, 2:9] = 0.5; K[0, 0, 9:15] = -1.25; K[0, 0, 20:] = 2.0
+    K[2, 0, :] = 0.1
+    K[3, 0, ::2] = 1.0
+    emb = sb.PathEmbedding(K)
+    d2, _, i2 = sb.PathShadowing(emb, sb.RelativeMSE(), ds, sb.PredictionContext(6)).shadow(q, k=200)
+    ex = emb(torch.tensor(q))[:, 0, :].numpy()
+    do, io = oracle.embed_topk(ds, K.numpy()[:, 0, :], ex, 200, 6)
+    assert_topk_close(d2, i2, do, io)
+
+
+def test_testing_ipynb_foveal_self_consistency():
+    """testing.ipynb:62-78 'shadowing correctly selected paths': the returned paths, re-embedded and
+    re-distanced with the plugins' own forward, reproduce the returned distances (rtol 1e-2 there)."""
+    g = torch.Generator().manual_seed(5)
+    x_context = torch.randn(8, 1, 126, generator=g)
+    x_dataset = torch.randn(32, 1, 4096, generator=g)
+    embedding = sb.Foveal(1.15, 0.9, 126)
+    context = sb.PredictionContext(252)
+    obj = sb.PathShadowing(embedding, sb.RelativeMSE(), x_dataset, context)
+    distances, paths, _ = obj.shadow(x_context, k=1024, cuda=True)
+    x_emb = embedding(x_context)[:, 0, :]
+    p_in = context.select_in_context(torch.tensor(paths))
+    p_emb = torch.stack([embedding(p_in[b])[:, 0, :] for b in range(8)])
+    d_check = sb.RelativeMSE()(x_emb[:, None, :], p_emb).numpy()
+    assert np.allclose(d_check, distances, rtol=1e-5)
+
+
+def test_predict_with_foveal_end_to_end():
+    ds, q = make_inputs(300, 1500, 64, 6, seed=15)
+    emb = sb.Foveal(1.2, 0.8, 64)
+    obj = sb.PathShadowing(emb, sb.RelativeMSE(), ds, sb.PredictionContext(20))
+    rv = sb.RealizedVariance([5, 10, 20])
+    pred, std = obj.predict(q, k=256, to_predict=rv, eta=0.1, n_context_splits=2)
+    d, paths, _ = obj.shadow(q, k=256)
+    mo, so = oracle.predict_from_paths(d, paths, 20, [5, 10, 20], False, "softmax", 0.1)
+    assert np.allclose(pred, mo, rtol=1e-6) and np.allclose(std, so, rtol=1e-5)
+
+
+def test_unsupported_plugins_raise():
+    class Cosine(sb.PathDistance):
+        def forward(self, x, y):
+            return 1 - (x * y).sum(-1)
+    ds, q = make_inputs(4, 100, 8, 1)
+    with pytest.raises(NotImplementedError):
+        sb.PathShadowing(sb.Identity(8), Cosine(), ds, sb.PredictionContext(2)).shadow(q, k=3)
