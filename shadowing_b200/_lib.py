@@ -186,9 +186,10 @@ def scan_topk(ds: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int, row_off
 
 def scan_topk_embed(ds: torch.Tensor, T: int, ex: torch.Tensor, W: int, H: int, k: int, runs: torch.Tensor,
                     row_offset: int = 0, nosync: bool = False, workspace: torch.Tensor | None = None,
-                    out: tuple[torch.Tensor, torch.Tensor] | None = None):
+                    out: tuple[torch.Tensor, torch.Tensor] | None = None, rec: torch.Tensor | None = None):
     """Scan in embedded space: ex (B, d) f32 cuda embedded queries, runs (nruns, 4) 32-bit words cuda
-    [row, a, b, c] (path_embedding.kernel_runs) -> (dist (B,k) f32, idx (B,k,2) i32) cuda."""
+    [row, a, b, c] (path_embedding.kernel_runs) -> (dist (B,k) f32, idx (B,k,2) i32) cuda; with
+    `rec` (B,k,3) i32 the results are written there as packed [distance bits, r, t] records."""
     L = lib()
     assert ds.is_cuda and ex.is_cuda and runs.is_cuda and ex.dtype == torch.float32 and ex.is_contiguous()
     R, row_stride = ds.shape[0], ds.stride(0)
@@ -196,7 +197,9 @@ def scan_topk_embed(ds: torch.Tensor, T: int, ex: torch.Tensor, W: int, H: int, 
     need = L.psh_scan_workspace_bytes(R, T, B, W, H, k) or 256
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty(need, dtype=torch.uint8, device=ds.device)
-    if out is not None:
+    if rec is not None:
+        dist, idx = rec, None
+    elif out is not None:
         dist, idx = out
     else:
         dist = torch.empty((B, k), dtype=torch.float32, device=ds.device)
@@ -204,8 +207,8 @@ def scan_topk_embed(ds: torch.Tensor, T: int, ex: torch.Tensor, W: int, H: int, 
     with torch.cuda.device(ds.device):
         rc = L.psh_scan_topk_embed_f32(ds.data_ptr(), R, T, row_stride, ex.data_ptr(), B, d, W, H, k, row_offset,
                                        PSH_FLAG_NOSYNC if nosync else 0, runs.data_ptr(), runs.shape[0],
-                                       dist.data_ptr(), idx.data_ptr(), workspace.data_ptr(), workspace.numel(),
-                                       _stream(ds))
+                                       dist.data_ptr(), idx.data_ptr() if idx is not None else None,
+                                       workspace.data_ptr(), workspace.numel(), _stream(ds))
     _check(rc, "psh_scan_topk_embed_f32")
     return dist, idx, workspace
 

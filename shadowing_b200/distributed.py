@@ -27,11 +27,25 @@ def shard_bounds(R: int, world: int, rank: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def _local_records(ps, rows, T, q, H, k, rec, nosync: bool):
-    """This rank's k best windows as packed (B,k,3) int32 records [distance bits, r, t] in `rec`."""
-    B, W = q.shape
+def _local_records(ps, rows, T, q, H, k, rec, nosync: bool, W: int):
+    """This rank's k best windows as packed (B,k,3) int32 records [distance bits, r, t] in `rec`.
+    `q` holds the contexts (B, W) -- or, for a non-Identity embedding, the EMBEDDED contexts (B, d)."""
     n_local = rows.shape[0] * (T - W - H + 1)
     k_loc = min(k, n_local)
+    runs = ps._run_table(rows.device) if rows.is_cuda else None
+    if runs is not None:   # Foveal / PathEmbedding(kernel): the embedded scan
+        rec[..., 0] = 0x7F800000
+        rec[..., 1] = _PAD_ROW
+        rec[..., 2] = 0
+        if k_loc == k:
+            _, _, ps._workspace = _lib.scan_topk_embed(rows, T, q, W, H, k, runs, ps._row_offset, nosync,
+                                                       ps._workspace, rec=rec)
+        elif k_loc > 0:
+            d, i, ps._workspace = _lib.scan_topk_embed(rows, T, q, W, H, k_loc, runs, ps._row_offset, False,
+                                                       ps._workspace)
+            rec[:, :k_loc, 0] = d.view(torch.int32)
+            rec[:, :k_loc, 1:] = i
+        return
     if rows.is_cuda and k_loc == k:
         mode, aux = ps._mode_and_aux(rows, T, W, H)
         ps._workspace = _lib.scan_topk_packed(rows, T, q, H, k, ps._row_offset,
@@ -119,14 +133,15 @@ def _exchange_and_merge(ps, rows, rec, rec_all, Tp, flag):
     return _lib.merge_topk(rec_all[..., 0].contiguous().view(torch.float32), rec_all[..., 1:].contiguous(), Tp)
 
 
-def sharded_scan(ps, rows: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int):
+def sharded_scan(ps, rows: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int, W: int | None = None):
     """Local exact top-k on this rank's rows, all-gather, merge.  Every rank returns the global
     (dist (B,k), idx (B,k,2)) with GLOBAL trajectory indices.  On CUDA the scan, the all-gather
     and the merge are enqueued back to back without a host synchronisation; the candidate-buffer
     overflow flag travels inside the records and is read once per step by `finish_sharded`."""
     pg = ps._pg
     world = dist.get_world_size(pg)
-    B, W = q.shape
+    B = q.shape[0]
+    W = q.shape[1] if W is None else W
     Tp = T - W - H + 1
     if Tp <= 0:
         raise RuntimeError(f"context ({W}) + horizon ({H}) longer than the trajectories ({T})")
@@ -148,13 +163,13 @@ def sharded_scan(ps, rows: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int
                 torch.zeros(1, dtype=torch.int32, device=rows.device))
         ps._shard_bufs = bufs
     rec, rec_all, flag = bufs
-    _local_records(ps, rows, T, q, H, k, rec, nosync=True)
+    _local_records(ps, rows, T, q, H, k, rec, True, W)
     out = _exchange_and_merge(ps, rows, rec, rec_all, Tp, flag)
     ps._pending_flag = flag if rows.is_cuda else None
     return out
 
 
-def finish_sharded(ps, rows: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int, out):
+def finish_sharded(ps, rows: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int, out, W: int | None = None):
     """Second half of the sharded scan: the single host synchronisation of a step.  If a candidate
     buffer overflowed on ANY rank (adversarially ordered data; every rank reads the same flag from
     the gathered records) all ranks repeat the step together with synchronous scans, which re-run
@@ -169,9 +184,9 @@ def finish_sharded(ps, rows: torch.Tensor, T: int, q: torch.Tensor, H: int, k: i
     flag.zero_()
     if status & 2:
         raise RuntimeError("peer-memory all-gather: a rank did not deliver its records within the timeout")
-    B, W = q.shape
+    W = q.shape[1] if W is None else W
     rec, rec_all, _ = ps._shard_bufs
-    _local_records(ps, rows, T, q, H, k, rec, nosync=False)
+    _local_records(ps, rows, T, q, H, k, rec, False, W)
     return _exchange_and_merge(ps, rows, rec, rec_all, T - W - H + 1, None)
 
 

@@ -229,12 +229,24 @@ class PathShadowing:
         res = sharded_scan(self, rows, T, q, H, k)
         return res if nosync else finish_sharded(self, rows, T, q, H, k, res)
 
+    def _run_table(self, device: torch.device):
+        """Device run table of a non-Identity embedding kernel (None for Identity)."""
+        if type(self.embedding) is Identity:
+            return None
+        kernel = self.embedding.kernel
+        key = (kernel.data_ptr(), tuple(kernel.shape), kernel._version, str(device))
+        if self._runs is None or self._runs[0] != key:
+            runs = kernel_runs(kernel)
+            if runs.shape[0] == 0:
+                raise RuntimeError("the embedding kernel is identically zero")
+            words = torch.from_numpy(runs.view(np.int32).reshape(-1, 4).copy())
+            self._runs = (key, words.to(device))
+        return self._runs[1]
+
     def _scan_embedded(self, x: torch.Tensor, rows: torch.Tensor, T: int, k: int, H: int, out, nosync: bool):
         """Foveal / PathEmbedding(kernel): the few query windows are embedded on the host with the
         embedding's own forward -- the reference's `embedding(x)[:, 0, :]`, path_shadowing.py:138 --
         and the ensemble is scanned in embedded space from prefix sums (never materialised)."""
-        if self._pg is not None:
-            raise NotImplementedError("the sharded scan implements the Identity embedding")
         kernel = self.embedding.kernel
         W = int(kernel.shape[-1])
         if x.shape[-1] != W:
@@ -242,20 +254,17 @@ class PathShadowing:
         Tp = T - W - H + 1
         if Tp <= 0:
             raise RuntimeError(f"context ({W}) + horizon ({H}) longer than the trajectories ({T})")
-        if k > rows.shape[0] * Tp:
-            raise RuntimeError(f"selected index k out of range: k={k} > {rows.shape[0] * Tp} windows")
-        key = (kernel.data_ptr(), tuple(kernel.shape), kernel._version)
-        if self._runs is None or self._runs[0] != key:
-            runs = kernel_runs(kernel)
-            if runs.shape[0] == 0:
-                raise RuntimeError("the embedding kernel is identically zero")
-            words = torch.from_numpy(runs.view(np.int32).reshape(-1, 4).copy())
-            self._runs = (key, words.to(rows.device))
         with torch.no_grad():
             ex = self.embedding.to(x.device)(x)[:, 0, :]          # (B, d), as the reference embeds the context
         ex = ex.to(rows.device, non_blocking=True).contiguous()
-        dist, idx, self._workspace = _lib.scan_topk_embed(rows, T, ex, W, H, k, self._runs[1], self._row_offset,
-                                                          nosync, self._workspace, out)
+        if self._pg is not None:
+            from .distributed import finish_sharded, sharded_scan
+            res = sharded_scan(self, rows, T, ex, H, k, W)
+            return res if nosync else finish_sharded(self, rows, T, ex, H, k, res, W)
+        if k > rows.shape[0] * Tp:
+            raise RuntimeError(f"selected index k out of range: k={k} > {rows.shape[0] * Tp} windows")
+        dist, idx, self._workspace = _lib.scan_topk_embed(rows, T, ex, W, H, k, self._run_table(rows.device),
+                                                          self._row_offset, nosync, self._workspace, out)
         self._pipeline_B = ex.shape[0]
         return dist, idx
 

@@ -63,6 +63,28 @@ def main():
                 and np.array_equal(paths, po) and np.allclose(pred, mo, rtol=1e-6) and np.allclose(pstd, so, rtol=1e-5))
         print(f"rank {rank}/{world} R={R} T={T} W={W} k={k} B={B} adv={adversarial}: {'OK' if good else 'MISMATCH'}", flush=True)
         ok = ok and good
+    # Foveal embedding, sharded: every rank must return what ONE GPU holding all rows returns
+    # (bit-identical: same kernel, same per-window arithmetic, exact merge), and that agrees with the
+    # CPU oracle within the embedded scan's tolerance
+    from conftest import assert_topk_close
+    for (R, T, W, H, k, B) in [(301, 2000, 126, 50, 700, 4), (2, 900, 64, 0, 1200, 1)]:
+        ds, q = make_inputs(R, T, W, B, seed=600 + R)
+        emb = sb.Foveal(1.15, 0.9, W)
+        lo, hi = shard_bounds(R, world, rank)
+        obj = sb.PathShadowing(emb, sb.RelativeMSE(), ds[lo:hi], sb.PredictionContext(H or None), device=dev,
+                               row_offset=lo, process_group=dist.group.WORLD)
+        d, paths, idx = obj.shadow(q, k=k)
+        one = sb.PathShadowing(emb, sb.RelativeMSE(), ds, sb.PredictionContext(H or None), device=dev)
+        d1, p1, i1 = one.shadow(q, k=k)
+        good = np.array_equal(d.view(np.uint32), d1.view(np.uint32)) and np.array_equal(idx, i1) and np.array_equal(paths, p1)
+        ex = emb(torch.tensor(q))[:, 0, :].numpy()
+        do, io = oracle.embed_topk(ds, emb.kernel.numpy()[:, 0, :], ex, k, H)
+        try:
+            assert_topk_close(d, idx, do, io)
+        except AssertionError:
+            good = False
+        print(f"rank {rank}/{world} Foveal R={R} T={T} W={W} k={k} B={B}: {'OK' if good else 'MISMATCH'}", flush=True)
+        ok = ok and good
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
     dist.destroy_process_group()

@@ -148,3 +148,45 @@ def test_product_never_touches_the_oracle():
         text = f.read_text()
         assert "oracle" not in text.lower(), f"{f} mentions the oracle"
         assert "/root/reference" not in text, f"{f} reads the reference tree"
+
+
+def test_new_entry_points_validate_arguments():
+    from shadowing_b200 import _lib
+    L = _lib.lib()
+    # embedded scan: null run table / non-positive sizes / unknown flags are rejected before device work
+    assert L.psh_scan_topk_embed_f32(None, 1, 100, 100, None, 1, 4, 10, 0, 1, 0, 0, None, 0, None, None, None, 0, None) == -1
+    # exchange buffers: sizes scale with ranks, queries and k; more than 16 peers is not supported
+    a = L.psh_xchg_bytes(2, 1, 1024)
+    assert a >= 2 * (2 * 1024 * 12 + 2 * 4) and L.psh_xchg_bytes(8, 4, 1024) > 4 * a
+    assert L.psh_xchg_bytes(17, 1, 1024) == 0 and L.psh_xchg_bytes(0, 1, 1) == 0
+    assert L.psh_allgather_merge_packed(None, None, 2, 0, 1, 16, 100, 1, None, None, None, None) == -1
+    assert L.psh_xchg_open(None, None) == -1 and L.psh_xchg_close(None) == -1 and L.psh_xchg_destroy(None) == -1
+
+
+def test_foveal_matches_reference_fixture_and_kernel_runs():
+    """Foveal's kernel equals the live reference's (fixture) bit for bit; kernel_runs turns any
+    (d,1,W) kernel into runs that reconstruct it exactly."""
+    import shadowing_b200 as sb
+    from shadowing_b200.path_embedding import kernel_runs
+    g = load_golden("foveal_R32_T4096_W126")
+    a, b, w = g["foveal"]
+    f = sb.Foveal(float(a), float(b), int(w))
+    assert f.dim == 34 and f.alpha == float(a) and f.beta == float(b) and f.max_context == 126
+    assert torch.equal(f.kernel, torch.tensor(g["kernel"]))
+    assert [s.start for s in f.slices][:6] == [-1, -1, -1, -1, -2, -2] and f.slices[-1].start == -115
+    assert np.array_equal(f(torch.tensor(g["x_context"]))[:, 0, :].numpy(), g["ex"])   # same conv1d as the reference
+    runs = kernel_runs(f.kernel)
+    assert len(runs) == 34 and (runs["b"] == 126).all() and (np.diff(runs["row"]) == 1).all()
+    assert tuple(f.adjust_to_context(sb.PredictionContext(252)).kernel.shape) == (34, 1, 378)
+    rng = np.random.default_rng(0)
+    for K in (torch.eye(7)[:, None, :], torch.tensor(rng.integers(-2, 3, size=(5, 1, 40)).astype(np.float32)),
+              torch.tensor(g["kernel"]), torch.zeros(2, 1, 9)):
+        runs = kernel_runs(K)
+        rebuilt = np.zeros(tuple(K.shape), np.float32)
+        for r in runs:
+            assert 0 <= r["a"] < r["b"] <= K.shape[-1] and r["c"] != 0
+            assert (rebuilt[r["row"], 0, r["a"]:r["b"]] == 0).all()
+            rebuilt[r["row"], 0, r["a"]:r["b"]] = r["c"]
+        assert np.array_equal(rebuilt, K.numpy()) and (np.diff(runs["row"]) >= 0).all()
+    with pytest.raises(RuntimeError):
+        kernel_runs(torch.zeros(3, 2, 5))
