@@ -102,7 +102,21 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
 int psh_scan_topk_embed_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride,
                             const float *d_qemb, int B, int d, int W, int H, int64_t k,
                             int32_t row_offset, int flags, const void *d_runs, int nruns,
+                            const float *d_g, const void *d_aux, size_t aux_bytes,
                             float *d_out_dist, int32_t *d_out_idx, void *d_ws, size_t ws_bytes, void *stream);
+/*
+ * FFT flavour of the embedded scan (d_aux != NULL): ||ex - K y_t||^2 = ||ex||^2 - 2 g.y_t + ||K y_t||^2
+ * with g = K^T ex, so the cross term is one correlation per trajectory -- the Identity flavour's
+ * spectra and inverse FFT -- and the quadratic term is precomputed per dataset and kernel:
+ *   d_g     (B, W) fp32: g_b = K^T ex_b (the caller multiplies; B x d x W flops)
+ *   d_aux   buffer of psh_fft_aux_bytes(R, T, W, H) bytes filled by psh_fft_prepare_embed for this
+ *           dataset, kernel (runs), W and H.  NULL: every window is evaluated exactly.
+ * The filter is a rigorous lower bound; survivors are re-evaluated with the exact embedded
+ * arithmetic, so both flavours return the same windows (distances equal up to the last bit of
+ * a box sum).
+ */
+int psh_fft_prepare_embed(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride, int W, int H,
+                          const void *d_runs, int nruns, void *d_aux, size_t aux_bytes, void *stream);
 
 /* After one or more PSH_FLAG_NOSYNC scans on the same workspace (and whatever the caller enqueued
  * behind them): synchronise the stream and report PSH_OK, or PSH_E_OVERFLOW if a candidate buffer

@@ -49,7 +49,9 @@ def lib() -> ctypes.CDLL:
         L.psh_scan_topk_f32.argtypes = [vp, i64, i64, i64, vp, ci, ci, ci, i64, i32, ci, vp, vp, vp, sz, vp, sz, vp]
         L.psh_scan_topk_embed_f32.restype = ci
         L.psh_scan_topk_embed_f32.argtypes = [vp, i64, i64, i64, vp, ci, ci, ci, ci, i64, i32, ci, vp, ci,
-                                              vp, vp, vp, ctypes.c_size_t, vp]
+                                              vp, vp, ctypes.c_size_t, vp, vp, vp, ctypes.c_size_t, vp]
+        L.psh_fft_prepare_embed.restype = ci
+        L.psh_fft_prepare_embed.argtypes = [vp, i64, i64, i64, ci, ci, vp, ci, vp, ctypes.c_size_t, vp]
         L.psh_scan_overflowed.restype = ci
         L.psh_scan_overflowed.argtypes = [vp, ci, vp]
         L.psh_fft_aux_bytes.restype = sz
@@ -144,6 +146,21 @@ def fft_prepare(ds: torch.Tensor, T: int, W: int, H: int) -> torch.Tensor:
     return aux
 
 
+def fft_prepare_embed(ds: torch.Tensor, T: int, W: int, H: int, runs: torch.Tensor) -> torch.Tensor:
+    """Dataset- and kernel-side precomputation for the fft flavour of the embedded scan: spectra of
+    row pairs, EMBEDDED window energies sum_n e_n(t)^2, pair norms."""
+    L = lib()
+    need = L.psh_fft_aux_bytes(ds.shape[0], T, W, H)
+    if need == 0:
+        raise PshadowError(-5, "psh_fft_aux_bytes")
+    aux = torch.empty(need, dtype=torch.uint8, device=ds.device)
+    with torch.cuda.device(ds.device):
+        rc = L.psh_fft_prepare_embed(ds.data_ptr(), ds.shape[0], T, ds.stride(0), W, H, runs.data_ptr(),
+                                     runs.shape[0], aux.data_ptr(), aux.numel(), _stream(ds))
+    _check(rc, "psh_fft_prepare_embed")
+    return aux
+
+
 def debug_fft4096(x: torch.Tensor, direction: int, aux: torch.Tensor) -> torch.Tensor:
     """x (n, 4096) complex64 cuda -> unnormalised DFT (direction -1) / inverse (+1), test hook."""
     L = lib()
@@ -186,10 +203,12 @@ def scan_topk(ds: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int, row_off
 
 def scan_topk_embed(ds: torch.Tensor, T: int, ex: torch.Tensor, W: int, H: int, k: int, runs: torch.Tensor,
                     row_offset: int = 0, nosync: bool = False, workspace: torch.Tensor | None = None,
-                    out: tuple[torch.Tensor, torch.Tensor] | None = None, rec: torch.Tensor | None = None):
+                    out: tuple[torch.Tensor, torch.Tensor] | None = None, rec: torch.Tensor | None = None,
+                    g: torch.Tensor | None = None, aux: torch.Tensor | None = None):
     """Scan in embedded space: ex (B, d) f32 cuda embedded queries, runs (nruns, 4) 32-bit words cuda
     [row, a, b, c] (path_embedding.kernel_runs) -> (dist (B,k) f32, idx (B,k,2) i32) cuda; with
-    `rec` (B,k,3) i32 the results are written there as packed [distance bits, r, t] records."""
+    `rec` (B,k,3) i32 the results are written there as packed [distance bits, r, t] records.
+    fft flavour: `aux` from fft_prepare_embed, `g` (B, W) = ex @ K."""
     L = lib()
     assert ds.is_cuda and ex.is_cuda and runs.is_cuda and ex.dtype == torch.float32 and ex.is_contiguous()
     R, row_stride = ds.shape[0], ds.stride(0)
@@ -207,6 +226,9 @@ def scan_topk_embed(ds: torch.Tensor, T: int, ex: torch.Tensor, W: int, H: int, 
     with torch.cuda.device(ds.device):
         rc = L.psh_scan_topk_embed_f32(ds.data_ptr(), R, T, row_stride, ex.data_ptr(), B, d, W, H, k, row_offset,
                                        PSH_FLAG_NOSYNC if nosync else 0, runs.data_ptr(), runs.shape[0],
+                                       g.data_ptr() if aux is not None else None,
+                                       aux.data_ptr() if aux is not None else None,
+                                       aux.numel() if aux is not None else 0,
                                        dist.data_ptr(), idx.data_ptr() if idx is not None else None,
                                        workspace.data_ptr(), workspace.numel(), _stream(ds))
     _check(rc, "psh_scan_topk_embed_f32")

@@ -52,7 +52,8 @@ struct QState {
     float qmax;                  // max_k |FFT(q)_k| (fft flavour), rounded up
     unsigned int sticky;         // overflow of ANY scan since the last psh_scan_overflowed(): survives qprep,
     unsigned int magic;          // valid only while magic == QSTATE_MAGIC (the workspace starts as garbage)
-    unsigned int pad[3];
+    float gnorm;                 // ||g||_2 of the correlated vector (fft flavour of the embedded scan), rounded up
+    unsigned int pad[2];
 };
 constexpr unsigned int QSTATE_MAGIC = 0x50534831u;
 static_assert(sizeof(QState) == 64, "QState layout");
@@ -174,7 +175,8 @@ __global__ void __launch_bounds__(128) qprep_kernel(const float *__restrict__ q,
         z.thr_fast = __int_as_float(0x7f800000);
         z.q2 = (float)q2;
         z.qmax = 0.0f;
-        for (int i = 0; i < 3; ++i) z.pad[i] = 0;
+        z.gnorm = 0.0f;
+        for (int i = 0; i < 2; ++i) z.pad[i] = 0;
         st[b] = z;
     }
 }
@@ -636,6 +638,13 @@ __global__ void __launch_bounds__(4 * QFFT_K) qfft_kernel(const float *__restric
     const int b = blockIdx.y, tid = threadIdx.x;
     for (int j = tid; j < W; j += 4 * QFFT_K) qd[j] = (double)q[(size_t)b * W + j];
     __syncthreads();
+    if (blockIdx.x == 0 && tid < 32) {   // ||q||_2 of the correlated vector, rounded up
+        double s2 = 0.0;
+        for (int j = tid; j < W; j += 32) s2 += qd[j] * qd[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(FULL, s2, o);
+        if (tid == 0) st[b].gnorm = __double2float_ru(sqrt(s2) * (1.0 + 1e-7));
+    }
     const int k = blockIdx.x * QFFT_K + (tid >> 2), part = tid & 3;
     const int per = (W + 3) / 4;
     const int j0 = part * per, j1 = min(W, j0 + per);
@@ -693,6 +702,13 @@ struct FftScanParams {
     unsigned int k;
     float widen2;      // (1 + 2 (W+8) u)^2 (1 + 1e-6): exact-sequence rounding, both directions
     unsigned int *seed;  // (nq, SEED_STRIDE) seed histograms + ticket (seed launch only)
+    // embedded scan (pshadow_embed_fft.cuh); Identity: 8u, 1, 1
+    float slack_coef;    // coefficient of (Q2 + y2_scale ynorm^2) in the slack
+    float y2_scale;      // 1: the staged energies are window energies <= ynorm^2;  0: they carry their own
+                         // rounding allowance (stored scaled down), see ub_e2_coef
+    float g_coef;        // coefficient of ||g|| ynorm in the slack (rounding of the correlated vector g)
+    float ub_e2_coef;    // UB - LB grows by ub_e2_coef * (staged energy) per window
+    float thr_widen;     // thresholds read from the query state are widened by this factor
 };
 
 // One CTA per row pair: Z * conj(Q)/N -> inverse FFT -> (D_a[t], D_b[t]) for t = tid + 256 c.
@@ -736,7 +752,7 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
         mbar_fence_init();
     }
     if (tid < p.nq) {
-        const float t0 = ld_volatile_f32(&p.st[tid].thr_fast);
+        const float t0 = ld_volatile_f32(&p.st[tid].thr_fast) * p.thr_widen;
         s_thrq[tid] = t0;
         s_hscale[tid] = (!SEED && p.hist != nullptr && t0 > 0.0f && t0 < __int_as_float(0x7f800000)) ? (float)FFT_NB / t0 : 0.0f;
     }
@@ -765,7 +781,7 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
         for (int i = 0; i < 16; ++i) qreg[i] = __ldg(p.Qc + tid + 256 * i);
     }
     const fftx::TwSeeds seeds = fftx::load_seeds(p.tw, tid);
-    const float q2_0 = p.st[0].q2, qmax_0 = p.st[0].qmax;
+    const float q2_0 = p.st[0].q2, qmax_0 = p.st[0].qmax, gn_0 = p.st[0].gnorm;
     uint32_t phZ = 0, phY = 0;
     for (int iter = 0; slot < p.i1; slot += gridDim.x, ++iter) {
         const long long nslot = slot + gridDim.x;
@@ -793,19 +809,23 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
             if (b == 0) { mbar_wait(barY, phY); phY ^= 1; }  // the pair's window energies have landed
             const float q2 = SINGLEQ ? q2_0 : p.st[b].q2, qmax = SINGLEQ ? qmax_0 : p.st[b].qmax;
             const float thr = s_thrq[b];
-            const float slack = (2.0f * p.cf_u * qmax * yn + 4.76837158203125e-7f * (q2 + yn * yn)) * 1.0001f;
+            const float gn = SINGLEQ ? gn_0 : p.st[b].gnorm;
+            const float slack = (2.0f * p.cf_u * qmax * yn + p.slack_coef * (q2 + p.y2_scale * yn * yn)
+                                 + p.g_coef * gn * yn) * 1.0001f;
             const float base0 = q2 - slack;   // LB = (Y2 - 2 D^) + base0, kept iff LB <= thr
             if (SEED) {
                 // min over the thread's windows of (Y2 - 2 D^); adding the constants afterwards is
                 // the same as taking the min of the UBs (fp addition is monotone)
-                float mn = __int_as_float(0x7f800000);
+                float mn = __int_as_float(0x7f800000), e2m = 0.0f;   // the minimum and the energy it was taken at
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                     const int pos = tid + 256 * c;
-                    mn = fminf(mn, fmaf(-2.0f, v[c].x, Y2s[pos]));
-                    if (has_b) mn = fminf(mn, fmaf(-2.0f, v[c].y, Y2s[fftx::N + pos]));
+                    const float ea = Y2s[pos], eb = Y2s[fftx::N + pos];
+                    const float va = fmaf(-2.0f, v[c].x, ea), vb = fmaf(-2.0f, v[c].y, eb);
+                    if (va < mn) { mn = va; e2m = ea; }
+                    if (has_b && vb < mn) { mn = vb; e2m = eb; }
                 }
-                const float ub = fmaxf((mn + base0) + 2.0f * slack, 0.0f);
+                const float ub = fmaxf(((mn + base0) + 2.0f * slack) + p.ub_e2_coef * e2m, 0.0f);
                 const bool act = ub < __int_as_float(0x7f800000);   // false for +inf (no valid window) and NaN
                 int bin = (int)(__float_as_uint(ub) >> 16) - ((int)(__float_as_uint(q2) >> 16) - SEED_NB / 2);
                 bin = bin < 0 ? 0 : (bin > SEED_NB - 1 ? SEED_NB - 1 : bin);
@@ -858,7 +878,8 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
                         if (pos < p.cap) dst[pos] = fa + t;
                         ++pos;
                         if (hs > 0.0f) {  // upper bound of the window's exact squared distance
-                            const float ub = (fmaf(-2.0f, v[c].x, Y2s[tid + 256 * c]) + base0) + 2.0f * slack;
+                            const float ea = Y2s[tid + 256 * c];
+                            const float ub = ((fmaf(-2.0f, v[c].x, ea) + base0) + 2.0f * slack) + p.ub_e2_coef * ea;
                             const float fbin = ub * hs;
                             if (fbin < (float)FFT_NB) atomicAdd(&hq[fbin > 0.0f ? (int)fbin : 0], 1u);
                         }
@@ -867,7 +888,8 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
                         if (pos < p.cap) dst[pos] = fb + t;
                         ++pos;
                         if (hs > 0.0f) {
-                            const float ub = (fmaf(-2.0f, v[c].y, Y2s[fftx::N + tid + 256 * c]) + base0) + 2.0f * slack;
+                            const float eb = Y2s[fftx::N + tid + 256 * c];
+                            const float ub = ((fmaf(-2.0f, v[c].y, eb) + base0) + 2.0f * slack) + p.ub_e2_coef * eb;
                             const float fbin = ub * hs;
                             if (fbin < (float)FFT_NB) atomicAdd(&hq[fbin > 0.0f ? (int)fbin : 0], 1u);
                         }
@@ -968,6 +990,8 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
         }
     }
 }
+
+#include "pshadow_embed_fft.cuh"
 
 // ------------------------------------------------------------------------------------------
 // exact re-rank of the filter's candidates.  Each warp takes 32 candidates at a time: their
@@ -1943,9 +1967,12 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
     PSH_LAUNCHED();
 
     const bool filter = (mode == PSH_MODE_FILTER || (mode == PSH_MODE_FFT && !use_fft)) && !safe;
+    if (use_fft && emb && emb->g == nullptr) return PSH_E_ARG;
     if (use_fft) {
+        // spectrum of the vector the trajectories are correlated with: the context itself, or
+        // g = K^T ex for an embedded scan
         qfft_kernel<<<dim3(fftx::N / QFFT_K, nq), 4 * QFFT_K, (size_t)W * sizeof(double), stream>>>(
-            d_q, W, aux->tw64, qspec, st);
+            emb ? emb->g : d_q, W, aux->tw64, qspec, st);
         PSH_LAUNCHED();
     }
     ScanParams p;
@@ -2013,10 +2040,44 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
         fp.cf_u = 512.0f * 5.9604644775390625e-8f;
         fp.hist = fhist; fp.k = (unsigned int)k;
         {
-            const double w1 = 1.0 + 2.0 * (double)(W + 8) * 5.9604644775390625e-8;
-            fp.widen2 = (float)(w1 * w1 * (1.0 + 1e-6));
+            const double w1 = 1.0 + 2.0 * (double)((emb ? emb->d : W) + 8) * 5.9604644775390625e-8;
+            const double we = emb ? 1.0 + 1.0 / 512.0 : 1.0;   // the exact embedded evaluation vs the true S
+            fp.widen2 = (float)(w1 * w1 * we * we * (1.0 + 1e-6));
+            fp.thr_widen = (float)we;
+            // Identity: 8u (Q2 + ynorm^2) covers the roundings of Q2, Y2 and of the combination.
+            // Embedded: |2 D| <= Q2 + E2_t (Cauchy-Schwarz in embedded space), so every rounding is
+            // <= a few u (Q2 + E2_t): 16u Q2 in the slack, 16u E2_t taken out of the stored energies
+            // (fft_prep_e2_kernel) and given back twice in UB; 2u ||g|| ynorm for the rounding of g
+            fp.slack_coef = (emb ? 16.0f : 8.0f) * 5.9604644775390625e-8f;
+            fp.y2_scale = emb ? 0.0f : 1.0f;
+            fp.g_coef = emb ? 2.0f * 5.9604644775390625e-8f : 0.0f;
+            fp.ub_e2_coef = emb ? 2.0f * 16.0f * 5.9604644775390625e-8f * 1.001f : 0.0f;
         }
     }
+    // exact re-rank of the fft / fma filter's survivors (embedded scans: emb_rerank_kernel)
+    const size_t smem_er = emb ? (size_t)((emb->d + 3) & ~3) * sizeof(float) * (1 + ERR_WARPS) + (size_t)emb->nruns * sizeof(EmbRun)
+                                     + (size_t)ERR_WARPS * (W + 2) * sizeof(float2)
+                               : 0;
+    if (emb && smem_er > 48 * 1024)
+        PSH_CUDA(cudaFuncSetAttribute(emb_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_er));
+    auto launch_rerank = [&]() -> int {
+        ProfScope ps(stream, 1);
+        if (emb) {
+            unsigned int rb = (pl.cap + ERR_WARPS - 1) / ERR_WARPS;
+            const unsigned int rb_max = (unsigned int)sm_count() * 8u;
+            if (rb > rb_max) rb = rb_max;
+            emb_rerank_kernel<<<dim3(rb, nq), ERR_WARPS * 32, smem_er, stream>>>(
+                d_dataset, row_stride, (unsigned int)pl.Tp, W, emb->d, d_q, ep.runs, ep.nruns, st, cand, keys, pl.cap);
+        } else {
+            unsigned int rb = (pl.cap + RR_THREADS - 1) / RR_THREADS;
+            const unsigned int rb_max = (unsigned int)sm_count() * 2u;
+            if (rb > rb_max) rb = rb_max;
+            rerank_kernel<<<dim3(rb, nq), RR_THREADS, smem_rr, stream>>>(
+                d_dataset, row_stride, (unsigned int)pl.Tp, W, d_q, st, cand, keys, pl.cap);
+        }
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return (int)cudaGetLastError();
+    };
     const size_t smem_fft = use_fft ? sizeof(float2) * fftx::N + sizeof(float) * 2 * (size_t)aux->y2_stride
                                           + sizeof(float2) * fftx::EX2_FLOAT2 + 16
                                     : 0;
@@ -2055,15 +2116,7 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
                 else fft_scan_kernel<false, false><<<(unsigned int)ctas, fftx::THREADS, smem_fft, stream>>>(fp);
             }
             PSH_LAUNCHED();
-            unsigned int rb = (pl.cap + RR_THREADS - 1) / RR_THREADS;
-            const unsigned int rb_max = (unsigned int)sm_count() * 2u;
-            if (rb > rb_max) rb = rb_max;
-            {
-                ProfScope ps(stream, 1);
-                rerank_kernel<<<dim3(rb, nq), RR_THREADS, smem_rr, stream>>>(
-                    d_dataset, row_stride, (unsigned int)pl.Tp, W, d_q, st, cand, keys, pl.cap);
-            }
-            PSH_LAUNCHED();
+            { int rc_ = launch_rerank(); if (rc_ != 0) return rc_; }
             {
                 ProfScope ps(stream, 1);
                 select_kernel<<<nq, SEL_THREADS, 0, stream>>>(st, keys, pl.cap, (unsigned int)k, W, fuse_final ? 1 : 0,
@@ -2139,17 +2192,7 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
             }
             PSH_LAUNCHED();
         }
-        if (!exact_round) {
-            unsigned int rb = (pl.cap + RR_THREADS - 1) / RR_THREADS;
-            unsigned int rb_max = (unsigned int)sm_count() * 2u;
-            if (rb > rb_max) rb = rb_max;
-            {
-                ProfScope ps(stream, 1);
-                rerank_kernel<<<dim3(rb, nq), RR_THREADS, smem_rr, stream>>>(
-                    d_dataset, row_stride, (unsigned int)pl.Tp, W, d_q, st, cand, keys, pl.cap);
-            }
-            PSH_LAUNCHED();
-        }
+        if (!exact_round) { int rc_ = launch_rerank(); if (rc_ != 0) return rc_; }
         {
             ProfScope ps(stream, 1);
             const int fin = (fuse_final && next == nslots) ? 1 : 0;
@@ -2202,12 +2245,20 @@ static int scan_entry(const float *d_dataset, int64_t R, int64_t T, int64_t row_
         auxp = &aux;
     }
 
+    // per query group: the embedded scan's cross-term vectors advance with the group
+    auto group_emb = [&](int g0, EmbParams &eg) -> const EmbParams * {
+        if (!emb) return nullptr;
+        eg = *emb;
+        if (eg.g) eg.g += (size_t)g0 * W;
+        return &eg;
+    };
     for (int g0 = 0; g0 < B; g0 += QG_MAX) {
         int nq = B - g0 < QG_MAX ? B - g0 : QG_MAX;
+        EmbParams eg;
         int rc = run_scan_group(d_dataset, R, T, row_stride, d_queries + (size_t)g0 * qstride, nq, W, H, k, row_offset,
                                 pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap, qspec + (size_t)g0 * fftx::N, fhist_all + (size_t)g0 * FFT_NB, shist_all + (size_t)g0 * SEED_STRIDE, auxp, mode, false,
                                 d_out_dist + (size_t)g0 * k * (d_out_idx ? 1 : 3),
-                                d_out_idx ? d_out_idx + (size_t)g0 * k * 2 : nullptr, stream, emb);
+                                d_out_idx ? d_out_idx + (size_t)g0 * k * 2 : nullptr, stream, group_emb(g0, eg));
         if (rc != PSH_OK) return rc;
     }
     if (nosync) return PSH_OK;  // the caller checks psh_scan_overflowed() before trusting the results
@@ -2222,11 +2273,12 @@ static int scan_entry(const float *d_dataset, int64_t R, int64_t T, int64_t row_
         bool ovf = false;
         for (int i = 0; i < nq; ++i) ovf = ovf || hst[g0 + i].overflow != 0;
         if (ovf) {
+            EmbParams eg;
             int rc = run_scan_group(d_dataset, R, T, row_stride, d_queries + (size_t)g0 * qstride, nq, W, H, k, row_offset,
                                     pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap, qspec + (size_t)g0 * fftx::N, fhist_all + (size_t)g0 * FFT_NB, shist_all + (size_t)g0 * SEED_STRIDE, auxp, mode,
                                     true,
                                     d_out_dist + (size_t)g0 * k * (d_out_idx ? 1 : 3),
-                                d_out_idx ? d_out_idx + (size_t)g0 * k * 2 : nullptr, stream, emb);
+                                d_out_idx ? d_out_idx + (size_t)g0 * k * 2 : nullptr, stream, group_emb(g0, eg));
             if (rc != PSH_OK) return rc;
             redone = true;
         }
@@ -2251,15 +2303,37 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
 int psh_scan_topk_embed_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride,
                             const float *d_qemb, int B, int d, int W, int H, int64_t k,
                             int32_t row_offset, int flags, const void *d_runs, int nruns,
+                            const float *d_g, const void *d_aux, size_t aux_bytes,
                             float *d_out_dist, int32_t *d_out_idx, void *d_ws, size_t ws_bytes, void *stream_) {
     if (!d_runs || nruns <= 0 || d <= 0 || (flags & ~PSH_FLAG_NOSYNC) != 0) return PSH_E_ARG;
+    if (d_aux != nullptr && d_g == nullptr) return PSH_E_ARG;
     EmbParams ep;
     ep.runs = static_cast<const EmbRun *>(d_runs);
     ep.nruns = nruns;
     ep.d = d;
     ep.ps_n = 0;
-    return scan_entry(d_dataset, R, T, row_stride, d_qemb, B, W, H, k, row_offset, PSH_MODE_EXACT | flags, d_out_dist,
-                      d_out_idx, d_ws, ws_bytes, nullptr, 0, stream_, &ep);
+    ep.g = d_aux ? d_g : nullptr;
+    return scan_entry(d_dataset, R, T, row_stride, d_qemb, B, W, H, k, row_offset,
+                      (d_aux ? PSH_MODE_FFT : PSH_MODE_EXACT) | flags, d_out_dist,
+                      d_out_idx, d_ws, ws_bytes, d_aux, aux_bytes, stream_, &ep);
+}
+
+int psh_fft_prepare_embed(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride, int W, int H,
+                          const void *d_runs, int nruns, void *d_aux, size_t aux_bytes, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!d_runs || nruns <= 0) return PSH_E_ARG;
+    // spectra, pair norms and twiddles as for the Identity flavour; then the window energies are
+    // replaced by the embedded energies E2 = sum_n e_n(t)^2
+    int rc = psh_fft_prepare(d_dataset, R, T, row_stride, W, H, d_aux, aux_bytes, stream_);
+    if (rc != PSH_OK) return rc;
+    FftAux a;
+    if (!fft_aux_layout(R, T, W, H, static_cast<unsigned char *>(d_aux), a)) return PSH_E_ARG;
+    const size_t smem = (size_t)nruns * sizeof(EmbRun);
+    if (smem > 12 * 1024) return PSH_E_UNSUPPORTED;   // next to the 32 KiB fp64 prefix array
+    fft_prep_e2_kernel<<<(unsigned int)a.VR, fftx::THREADS, smem, stream>>>(
+        d_dataset, (int)T, row_stride, W, (int)(T - W - H + 1), a, static_cast<const EmbRun *>(d_runs), nruns);
+    PSH_LAUNCHED();
+    return PSH_OK;
 }
 
 int psh_scan_overflowed(const void *d_ws, int B, void *stream_) {

@@ -22,6 +22,8 @@ struct EmbParams {
     int nruns;
     int d;          // embedding dimension (queries are (nq, d), staged with stride sp.wpad)
     int ps_n;       // float2 entries of a warp's prefix array (>= SEG + W, even)
+    // fft flavour of the embedded scan (NULL / 0: exact flavour only), see pshadow_embed_fft.cuh
+    const float *g;   // (nq, W) cross-term vectors g = K^T ex
 };
 
 constexpr int EMB_QG = 3;   // queries evaluated per pass over a staged segment

@@ -37,12 +37,13 @@ def _local_records(ps, rows, T, q, H, k, rec, nosync: bool, W: int):
         rec[..., 0] = 0x7F800000
         rec[..., 1] = _PAD_ROW
         rec[..., 2] = 0
+        flavour = ps._embed_flavour(rows, T, W, H, ps._ex_host) if rows.shape[0] > 0 else {}
         if k_loc == k:
             _, _, ps._workspace = _lib.scan_topk_embed(rows, T, q, W, H, k, runs, ps._row_offset, nosync,
-                                                       ps._workspace, rec=rec)
+                                                       ps._workspace, rec=rec, **flavour)
         elif k_loc > 0:
             d, i, ps._workspace = _lib.scan_topk_embed(rows, T, q, W, H, k_loc, runs, ps._row_offset, False,
-                                                       ps._workspace)
+                                                       ps._workspace, **flavour)
             rec[:, :k_loc, 0] = d.view(torch.int32)
             rec[:, :k_loc, 1:] = i
         return

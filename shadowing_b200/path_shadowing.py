@@ -243,6 +243,25 @@ class PathShadowing:
             self._runs = (key, words.to(device))
         return self._runs[1]
 
+    def _embed_flavour(self, rows: torch.Tensor, T: int, W: int, H: int, ex: torch.Tensor) -> dict:
+        """Extra arguments of the embedded scan's fft flavour (empty: exact flavour).  The squared
+        embedded distance is ||ex||^2 - 2 g.y_t + ||K y_t||^2 with g = K^T ex: one correlation per
+        trajectory (the Identity flavour's spectra) plus a per-(dataset, kernel) energy table."""
+        mode = self._scan_mode
+        if mode == "auto":
+            mode = "fft" if (64 <= W <= 1024 and T >= 1024) else "exact"
+        if mode != "fft" or W > _lib.FFT_MAX_W:
+            return {}
+        kernel = self.embedding.kernel
+        runs = self._run_table(rows.device)
+        key = (rows.data_ptr(), tuple(rows.shape), T, W, H, kernel.data_ptr(), kernel._version)
+        if self._fft_aux is None or self._fft_aux[0] != key:
+            K = kernel.detach().cpu()[:, 0, :].double()
+            self._fft_aux = (key, _lib.fft_prepare_embed(rows, T, W, H, runs), K)
+        _, aux, K = self._fft_aux
+        g = (ex.detach().cpu().double() @ K).float().to(rows.device, non_blocking=True).contiguous()
+        return {"g": g, "aux": aux}
+
     def _scan_embedded(self, x: torch.Tensor, rows: torch.Tensor, T: int, k: int, H: int, out, nosync: bool):
         """Foveal / PathEmbedding(kernel): the few query windows are embedded on the host with the
         embedding's own forward -- the reference's `embedding(x)[:, 0, :]`, path_shadowing.py:138 --
@@ -255,16 +274,18 @@ class PathShadowing:
         if Tp <= 0:
             raise RuntimeError(f"context ({W}) + horizon ({H}) longer than the trajectories ({T})")
         with torch.no_grad():
-            ex = self.embedding.to(x.device)(x)[:, 0, :]          # (B, d), as the reference embeds the context
-        ex = ex.to(rows.device, non_blocking=True).contiguous()
+            ex_host = self.embedding.to(x.device)(x)[:, 0, :]     # (B, d), as the reference embeds the context
+        ex = ex_host.to(rows.device, non_blocking=True).contiguous()
         if self._pg is not None:
             from .distributed import finish_sharded, sharded_scan
+            self._ex_host = ex_host
             res = sharded_scan(self, rows, T, ex, H, k, W)
             return res if nosync else finish_sharded(self, rows, T, ex, H, k, res, W)
         if k > rows.shape[0] * Tp:
             raise RuntimeError(f"selected index k out of range: k={k} > {rows.shape[0] * Tp} windows")
         dist, idx, self._workspace = _lib.scan_topk_embed(rows, T, ex, W, H, k, self._run_table(rows.device),
-                                                          self._row_offset, nosync, self._workspace, out)
+                                                          self._row_offset, nosync, self._workspace, out,
+                                                          **self._embed_flavour(rows, T, W, H, ex_host))
         self._pipeline_B = ex.shape[0]
         return dist, idx
 

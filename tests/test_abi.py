@@ -154,7 +154,9 @@ def test_new_entry_points_validate_arguments():
     from shadowing_b200 import _lib
     L = _lib.lib()
     # embedded scan: null run table / non-positive sizes / unknown flags are rejected before device work
-    assert L.psh_scan_topk_embed_f32(None, 1, 100, 100, None, 1, 4, 10, 0, 1, 0, 0, None, 0, None, None, None, 0, None) == -1
+    assert L.psh_scan_topk_embed_f32(None, 1, 100, 100, None, 1, 4, 10, 0, 1, 0, 0, None, 0, None, None, 0,
+                                     None, None, None, 0, None) == -1
+    assert L.psh_fft_prepare_embed(None, 1, 100, 100, 10, 0, None, 0, None, 0, None) == -1
     # exchange buffers: sizes scale with ranks, queries and k; more than 16 peers is not supported
     a = L.psh_xchg_bytes(2, 1, 1024)
     assert a >= 2 * (2 * 1024 * 12 + 2 * 4) and L.psh_xchg_bytes(8, 4, 1024) > 4 * a

@@ -471,8 +471,9 @@ def _gather_ref(ds, idx, L):
     return np.stack([np.stack([ds[r, t:t + L] for r, t in row]) for row in idx])[:, :, None, :]
 
 
+@pytest.mark.parametrize("mode", ["exact", "fft"])
 @pytest.mark.parametrize("name", ["foveal_R32_T4096_W126", "dense_kernel_R16_T300_W16"])
-def test_embedded_scan_matches_reference_fixture(name):
+def test_embedded_scan_matches_reference_fixture(name, mode):
     """Live-reference fixtures (testing.ipynb:62-78's Foveal configuration; a dense random kernel):
     distances within 1e-6 relative, indices equal up to near-ties, paths = the indexed windows."""
     from conftest import assert_topk_close
@@ -483,7 +484,7 @@ def test_embedded_scan_matches_reference_fixture(name):
         assert torch.equal(emb.kernel, torch.tensor(g["kernel"]))
     else:
         emb = sb.PathEmbedding(torch.tensor(g["kernel"]))
-    obj = sb.PathShadowing(emb, sb.RelativeMSE(), g["dataset"], sb.PredictionContext(g["H"]))
+    obj = sb.PathShadowing(emb, sb.RelativeMSE(), g["dataset"], sb.PredictionContext(g["H"]), scan_mode=mode)
     d, paths, idx = obj.shadow(g["x_context"], k=g["k"], n_splits=g["n_splits"], cuda=True)
     assert d.dtype == np.float32 and idx.dtype == np.int32 and paths.shape == (g["B"], g["k"], 1, g["W"] + g["H"])
     assert_topk_close(d, idx, g["distances"], g["indices"])
@@ -492,22 +493,47 @@ def test_embedded_scan_matches_reference_fixture(name):
         assert np.array_equal(paths, g["paths"])
 
 
+@pytest.mark.parametrize("mode", ["exact", "fft"])
 @pytest.mark.parametrize("R,T,W,H,k,B,alpha,beta", [
     (512, 4096, 126, 252, 1024, 5, 1.15, 0.9),   # the reference benchmark's embedding, 3 + 2 query groups
     (700, 1000, 64, 0, 300, 1, 1.3, 0.5),        # no horizon, one query
-    (33, 5000, 252, 20, 2000, 4, 1.15, 0.9),     # long rows, 14 segments per row, k > SEG
+    (33, 5000, 252, 20, 2000, 4, 1.15, 0.9),     # long rows (fft: two overlapping pieces per row), k > SEG
+    (1024, 4096, 126, 252, 1024, 2, 1.15, 0.9),  # 512 row pairs: the fft flavour runs its seedless schedule
 ])
-def test_foveal_matches_oracle(R, T, W, H, k, B, alpha, beta):
+def test_foveal_matches_oracle(R, T, W, H, k, B, alpha, beta, mode):
     from conftest import assert_topk_close
     ds, q = make_inputs(R, T, W, B, seed=900 + R)
     emb = sb.Foveal(alpha, beta, W)
-    obj = sb.PathShadowing(emb, sb.RelativeMSE(), ds, sb.PredictionContext(H or None))
+    obj = sb.PathShadowing(emb, sb.RelativeMSE(), ds, sb.PredictionContext(H or None), scan_mode=mode)
+    n0 = _lib.launch_count()
     d, paths, idx = obj.shadow(q, k=k)
     ex = emb(torch.tensor(q))[:, 0, :].numpy()
     do, io = oracle.embed_topk(ds, emb.kernel.numpy()[:, 0, :], ex, k, H)
     assert_topk_close(d, idx, do, io)
     assert np.array_equal(paths, _gather_ref(ds, idx, W + H))
     assert (np.diff(d, axis=1) >= 0).all()
+    if mode == "fft" and R == 1024:
+        n1 = _lib.launch_count()
+        obj.shadow(q, k=k)   # second call: aux is cached; qprep, qfft, seed, scan, rerank, select + gather
+        assert _lib.launch_count() - n1 == 7, _lib.launch_count() - n1
+
+
+def test_foveal_fft_flavour_equals_exact_flavour_and_recovers():
+    """Both embedded flavours return the same windows; a query far off the data's scale leaves the
+    seed threshold at +inf, the candidate buffer overflows and the safe schedule still answers."""
+    from conftest import assert_topk_close
+    ds, q = make_inputs(1024, 2048, 100, 3, seed=71)
+    emb = sb.Foveal(1.2, 0.7, 100)
+    outs = {}
+    for mode in ("exact", "fft"):
+        obj = sb.PathShadowing(emb, sb.RelativeMSE(), ds, sb.PredictionContext(30), scan_mode=mode)
+        outs[mode] = obj.shadow(q, k=500)
+    assert_topk_close(outs["fft"][0], outs["fft"][2], outs["exact"][0], outs["exact"][2])
+    qs = q * np.float32(1e-3)
+    d, _, idx = sb.PathShadowing(emb, sb.RelativeMSE(), ds, sb.PredictionContext(30), scan_mode="fft").shadow(qs, k=500)
+    ex = emb(torch.tensor(qs))[:, 0, :].numpy()
+    do, io = oracle.embed_topk(ds, emb.kernel.numpy()[:, 0, :], ex, 500, 30)
+    assert_topk_close(d, idx, do, io)
 
 
 def test_generic_kernels_through_the_embedded_scan():
