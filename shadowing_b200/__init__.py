@@ -7,6 +7,7 @@ realized_variance, and (leaking through path_shadowing.py:9 in the reference) So
 Uniform, DiscreteProba.
 """
 from .averaging import DiscreteProba, Softmax, Uniform, softmax_weights
+from .dataset import TimeSeriesDataset
 from .path_distance import PathDistance, RelativeMSE
 from .path_embedding import ArrayType, ContextManagerBase, Foveal, Identity, PathEmbedding, PredictionContext
 from .path_shadowing import PathShadowing, select_cartesian_product
@@ -17,6 +18,6 @@ __version__ = "0.1.0"
 __all__ = [
     "PathShadowing", "PathEmbedding", "Identity", "Foveal", "PathDistance", "RelativeMSE",
     "ContextManagerBase", "PredictionContext", "ArrayType", "realized_variance",
-    "RealizedVariance", "Softmax", "Uniform", "DiscreteProba", "softmax_weights",
+    "RealizedVariance", "TimeSeriesDataset", "Softmax", "Uniform", "DiscreteProba", "softmax_weights",
     "select_cartesian_product",
 ]

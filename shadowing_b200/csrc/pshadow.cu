@@ -2097,7 +2097,9 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
     if (use_fft && seedless_enabled()) {
         long long nseed = (long long)sm_count() * 2;
         if (nseed > p.npairs / 8) nseed = p.npairs / 8;
-        if (nseed >= 1 && nseed * (long long)fftx::THREADS >= 8 * k) {
+        // (k-th smallest of nseed*256 per-thread minima: with k <= half of them the hidden second-smallest
+        // values of a thread cost a few per cent of threshold quality, no more)
+        if (nseed >= 1 && nseed * (long long)fftx::THREADS >= 2 * k) {
             fp.seed = shist;
             fp.i0 = 0; fp.i1 = nseed;
             {

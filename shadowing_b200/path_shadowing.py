@@ -26,6 +26,7 @@ import torch
 
 from . import _lib
 from .averaging import DiscreteProba, Softmax, Uniform
+from .dataset import TimeSeriesDataset
 from .path_distance import PathDistance, RelativeMSE
 from .path_embedding import (ArrayType, ContextManagerBase, Foveal, Identity, PathEmbedding, PredictionContext,
                              kernel_runs)
@@ -71,17 +72,6 @@ def select_cartesian_product(indices: torch.Tensor, tensors: list[torch.Tensor])
     return torch.stack([t[c] for t, c in zip(tensors, coords)], dim=-1)
 
 
-def _load_npy_dir(dpath: Path) -> np.ndarray:
-    """Dataset directory of .npy batches (scripts/batch_generations.py:28-40 writes
-    `batchNNNN.npy` arrays of shape (n, C, T)); stands in for scatspectra's
-    TimeSeriesDataset(dpath, R=None).load() (path_shadowing.py:84-85)."""
-    files = sorted(Path(dpath).glob("*.npy"))
-    if not files:
-        raise FileNotFoundError(f"no .npy batches under {dpath}")
-    arrs = [_dim_array(np.load(f)) for f in files]
-    return np.concatenate(arrs, axis=0)
-
-
 def _recycle(pool: list, outstanding: list, host_buf: torch.Tensor) -> None:
     """Finaliser of a result buffer handed out by `shadow`: every numpy view of it is gone."""
     outstanding[0] -= 1
@@ -110,9 +100,9 @@ class PathShadowing:
         scan_mode: str = "auto",
     ):
         if isinstance(dataset, (str, Path)):
-            dataset = _load_npy_dir(Path(dataset))
+            dataset = TimeSeriesDataset(dpath=dataset, R=None).load()   # path_shadowing.py:84-85
         elif hasattr(dataset, "load") and not isinstance(dataset, (np.ndarray, torch.Tensor)):
-            dataset = dataset.load()  # a TimeSeriesDataset-like object (path_shadowing.py:86-87)
+            dataset = dataset.load()  # a TimeSeriesDataset(-like) object (path_shadowing.py:86-87)
         self.dataset = dataset
         self.embedding = embedding
         self.distance = distance

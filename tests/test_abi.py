@@ -192,3 +192,27 @@ def test_foveal_matches_reference_fixture_and_kernel_runs():
         assert np.array_equal(rebuilt, K.numpy()) and (np.diff(runs["row"]) >= 0).all()
     with pytest.raises(RuntimeError):
         kernel_runs(torch.zeros(3, 2, 5))
+
+
+def test_time_series_dataset_reads_npy_batches(tmp_path):
+    """The on-disk format of scripts/batch_generations.py:28-40 (batchNNNN.npy) and of single
+    trajectory files, in file-name order, with the README's `R=` limit (README.md:41-42)."""
+    import shadowing_b200 as sb
+    rng = np.random.default_rng(1)
+    parts = [rng.standard_normal((5, 1, 64)).astype(np.float32), rng.standard_normal((3, 64)).astype(np.float32),
+             rng.standard_normal(64)]
+    for i, a in enumerate(parts):
+        np.save(tmp_path / f"batch{i + 1:04}.npy", a)
+    full = np.concatenate([parts[0], parts[1][:, None, :], parts[2][None, None, :].astype(np.float32)])
+    ds = sb.TimeSeriesDataset(tmp_path)
+    assert len(ds) == 9 and np.array_equal(ds.load(), full) and ds.load().dtype == np.float32
+    assert np.array_equal(sb.TimeSeriesDataset(tmp_path, R=6).load(), full[:6])
+    with pytest.raises(ValueError):
+        sb.TimeSeriesDataset(tmp_path, R=10).load()
+    with pytest.raises(FileNotFoundError):
+        sb.TimeSeriesDataset(tmp_path / "nothing").load()
+    # PathShadowing accepts the directory or the dataset object, as path_shadowing.py:84-88
+    obj = sb.PathShadowing(sb.Identity(8), sb.RelativeMSE(), tmp_path, sb.PredictionContext(2))
+    assert np.array_equal(obj.dataset, full)
+    obj = sb.PathShadowing(sb.Identity(8), sb.RelativeMSE(), sb.TimeSeriesDataset(tmp_path, R=4))
+    assert obj.dataset.shape == (4, 1, 64) and obj.context.get_out_times() == 0
