@@ -237,8 +237,10 @@ def run_ours(args):
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    th0 = time.perf_counter()
     for i in range(args.steps):
         step_device(args.warmup + i)
+    host_enqueue_ms = (time.perf_counter() - th0) * 1e3 / args.steps   # host time to enqueue one step
     obj._check_pipeline()
     e1.record()
     barrier()
@@ -312,6 +314,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(d_np.nbytes + p_np.nbytes + i_np.nbytes),
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
+            "host_enqueue_ms_per_step": host_enqueue_ms,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                          "traffic": traffic, "peak_kind": peak_kind,

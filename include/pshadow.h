@@ -179,6 +179,15 @@ int psh_xchg_destroy(void *d_buf);
 int psh_allgather_merge_packed(const int32_t *d_rec_local, void *const *bufs, int G, int rank, int B, int64_t k,
                                int64_t Tp, uint32_t epoch, float *d_out_dist, int32_t *d_out_idx,
                                int32_t *d_flag, void *stream);
+/* The same step in two launches -- psh_xchg_send (stores + flags, never waits) and psh_xchg_merge
+ * (wait for the G flags of the epoch, merge) -- so a pipeline of scans can enqueue
+ *     scan(i+1), send(i+1), merge(i)
+ * and a rank computes its next scan instead of idling until the slowest peer has delivered step i.
+ * The exchange buffers hold three epochs (epoch % 3), which this order needs. */
+int psh_xchg_send(const int32_t *d_rec_local, void *const *bufs, int G, int rank, int B, int64_t k,
+                  uint32_t epoch, void *stream);
+int psh_xchg_merge(void *const *bufs, int G, int rank, int B, int64_t k, int64_t Tp, uint32_t epoch,
+                   float *d_out_dist, int32_t *d_out_idx, int32_t *d_flag, void *stream);
 
 /*
  * Gather the winning paths with their out-context: replaces path_shadowing.py:210-216.

@@ -77,6 +77,10 @@ def lib() -> ctypes.CDLL:
         L.psh_allgather_merge_packed.restype = ci
         L.psh_allgather_merge_packed.argtypes = [vp, ctypes.POINTER(vp), ci, ci, ci, i64, i64, ctypes.c_uint32,
                                                  vp, vp, vp, vp]
+        L.psh_xchg_send.restype = ci
+        L.psh_xchg_send.argtypes = [vp, ctypes.POINTER(vp), ci, ci, ci, i64, ctypes.c_uint32, vp]
+        L.psh_xchg_merge.restype = ci
+        L.psh_xchg_merge.argtypes = [ctypes.POINTER(vp), ci, ci, ci, i64, i64, ctypes.c_uint32, vp, vp, vp, vp]
         L.psh_gather_paths.restype = ci
         L.psh_gather_paths.argtypes = [vp, i64, i64, i64, vp, i64, i32, ci, vp, vp]
         L.psh_rv_aggregate.restype = ci
@@ -351,3 +355,27 @@ def allgather_merge_packed(rec: torch.Tensor, bufs: list[int], rank: int, Tp: in
                                           _stream(rec))
     _check(rc, "psh_allgather_merge_packed")
     return dist, idx
+
+
+def xchg_send(rec: torch.Tensor, bufs: list[int], rank: int, epoch: int) -> None:
+    """First half of allgather_merge_packed: store this rank's records into every rank's buffer and
+    raise the flags; never waits."""
+    L = lib()
+    B, k, _ = rec.shape
+    G = len(bufs)
+    arr = (ctypes.c_void_p * G)(*bufs)
+    with torch.cuda.device(rec.device):
+        rc = L.psh_xchg_send(rec.data_ptr(), arr, G, rank, B, k, epoch, _stream(rec))
+    _check(rc, "psh_xchg_send")
+
+
+def xchg_merge(bufs: list[int], rank: int, B: int, k: int, Tp: int, epoch: int, dist: torch.Tensor,
+               idx: torch.Tensor, flag: torch.Tensor | None = None) -> None:
+    """Second half: wait for the epoch's records of all ranks, merge into dist (B,k) / idx (B,k,2)."""
+    L = lib()
+    G = len(bufs)
+    arr = (ctypes.c_void_p * G)(*bufs)
+    with torch.cuda.device(dist.device):
+        rc = L.psh_xchg_merge(arr, G, rank, B, k, Tp, epoch, dist.data_ptr(), idx.data_ptr(),
+                              flag.data_ptr() if flag is not None else None, _stream(dist))
+    _check(rc, "psh_xchg_merge")

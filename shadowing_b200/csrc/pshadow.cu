@@ -735,7 +735,10 @@ __device__ __forceinline__ long long fft_pair_of_slot(const FftScanParams &p, lo
 // minima lie -- k distinct windows whose exact squared distance is <= edge -- and publishes
 // thr_fast = edge * widen2: the threshold the main launch over ALL pairs starts from (and
 // tightens further by itself).  This replaces two exact seed rounds and two selects.
-template <bool SINGLEQ, bool SEED>
+// EMB = true: the embedded scan's flavour (pshadow_embed_fft.cuh) -- per-query ||g|| term in the slack,
+// energy-proportional UB term, widened thresholds.  Compile-time, so the Identity instantiation
+// carries none of it (measured: the run-time version cost the Identity scan 9 %).
+template <bool SINGLEQ, bool SEED, bool EMB>
 __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftScanParams p) {
     extern __shared__ __align__(128) unsigned char fsm[];
     float2 *Zs = reinterpret_cast<float2 *>(fsm);
@@ -752,7 +755,7 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
         mbar_fence_init();
     }
     if (tid < p.nq) {
-        const float t0 = ld_volatile_f32(&p.st[tid].thr_fast) * p.thr_widen;
+        const float t0 = EMB ? ld_volatile_f32(&p.st[tid].thr_fast) * p.thr_widen : ld_volatile_f32(&p.st[tid].thr_fast);
         s_thrq[tid] = t0;
         s_hscale[tid] = (!SEED && p.hist != nullptr && t0 > 0.0f && t0 < __int_as_float(0x7f800000)) ? (float)FFT_NB / t0 : 0.0f;
     }
@@ -781,7 +784,7 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
         for (int i = 0; i < 16; ++i) qreg[i] = __ldg(p.Qc + tid + 256 * i);
     }
     const fftx::TwSeeds seeds = fftx::load_seeds(p.tw, tid);
-    const float q2_0 = p.st[0].q2, qmax_0 = p.st[0].qmax, gn_0 = p.st[0].gnorm;
+    const float q2_0 = p.st[0].q2, qmax_0 = p.st[0].qmax, gn_0 = EMB ? p.st[0].gnorm : 0.0f;
     uint32_t phZ = 0, phY = 0;
     for (int iter = 0; slot < p.i1; slot += gridDim.x, ++iter) {
         const long long nslot = slot + gridDim.x;
@@ -809,23 +812,33 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
             if (b == 0) { mbar_wait(barY, phY); phY ^= 1; }  // the pair's window energies have landed
             const float q2 = SINGLEQ ? q2_0 : p.st[b].q2, qmax = SINGLEQ ? qmax_0 : p.st[b].qmax;
             const float thr = s_thrq[b];
-            const float gn = SINGLEQ ? gn_0 : p.st[b].gnorm;
-            const float slack = (2.0f * p.cf_u * qmax * yn + p.slack_coef * (q2 + p.y2_scale * yn * yn)
-                                 + p.g_coef * gn * yn) * 1.0001f;
+            float slack;
+            if (EMB) {
+                const float gn = SINGLEQ ? gn_0 : p.st[b].gnorm;
+                slack = (2.0f * p.cf_u * qmax * yn + p.slack_coef * q2 + p.g_coef * gn * yn) * 1.0001f;
+            } else {
+                slack = (2.0f * p.cf_u * qmax * yn + 4.76837158203125e-7f * (q2 + yn * yn)) * 1.0001f;
+            }
             const float base0 = q2 - slack;   // LB = (Y2 - 2 D^) + base0, kept iff LB <= thr
             if (SEED) {
                 // min over the thread's windows of (Y2 - 2 D^); adding the constants afterwards is
                 // the same as taking the min of the UBs (fp addition is monotone)
-                float mn = __int_as_float(0x7f800000), e2m = 0.0f;   // the minimum and the energy it was taken at
+                float mn = __int_as_float(0x7f800000), e2m = 0.0f;   // the minimum (EMB: and the energy it was taken at)
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                     const int pos = tid + 256 * c;
                     const float ea = Y2s[pos], eb = Y2s[fftx::N + pos];
                     const float va = fmaf(-2.0f, v[c].x, ea), vb = fmaf(-2.0f, v[c].y, eb);
-                    if (va < mn) { mn = va; e2m = ea; }
-                    if (has_b && vb < mn) { mn = vb; e2m = eb; }
+                    if (EMB) {
+                        if (va < mn) { mn = va; e2m = ea; }
+                        if (has_b && vb < mn) { mn = vb; e2m = eb; }
+                    } else {
+                        mn = fminf(mn, va);
+                        if (has_b) mn = fminf(mn, vb);
+                    }
                 }
-                const float ub = fmaxf(((mn + base0) + 2.0f * slack) + p.ub_e2_coef * e2m, 0.0f);
+                const float ub = fmaxf(EMB ? ((mn + base0) + 2.0f * slack) + p.ub_e2_coef * e2m
+                                           : (mn + base0) + 2.0f * slack, 0.0f);
                 const bool act = ub < __int_as_float(0x7f800000);   // false for +inf (no valid window) and NaN
                 int bin = (int)(__float_as_uint(ub) >> 16) - ((int)(__float_as_uint(q2) >> 16) - SEED_NB / 2);
                 bin = bin < 0 ? 0 : (bin > SEED_NB - 1 ? SEED_NB - 1 : bin);
@@ -879,7 +892,8 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
                         ++pos;
                         if (hs > 0.0f) {  // upper bound of the window's exact squared distance
                             const float ea = Y2s[tid + 256 * c];
-                            const float ub = ((fmaf(-2.0f, v[c].x, ea) + base0) + 2.0f * slack) + p.ub_e2_coef * ea;
+                            float ub = (fmaf(-2.0f, v[c].x, ea) + base0) + 2.0f * slack;
+                            if (EMB) ub += p.ub_e2_coef * ea;
                             const float fbin = ub * hs;
                             if (fbin < (float)FFT_NB) atomicAdd(&hq[fbin > 0.0f ? (int)fbin : 0], 1u);
                         }
@@ -889,7 +903,8 @@ __global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftSca
                         ++pos;
                         if (hs > 0.0f) {
                             const float eb = Y2s[fftx::N + tid + 256 * c];
-                            const float ub = ((fmaf(-2.0f, v[c].y, eb) + base0) + 2.0f * slack) + p.ub_e2_coef * eb;
+                            float ub = (fmaf(-2.0f, v[c].y, eb) + base0) + 2.0f * slack;
+                            if (EMB) ub += p.ub_e2_coef * eb;
                             const float fbin = ub * hs;
                             if (fbin < (float)FFT_NB) atomicAdd(&hq[fbin > 0.0f ? (int)fbin : 0], 1u);
                         }
@@ -1552,13 +1567,13 @@ __global__ void __launch_bounds__(SEL_THREADS) merge_kernel(const float *d_parts
 // ------------------------------------------------------------------------------------------
 // all-gather over NVLink peer memory fused with the merge (multi-GPU, one process per GPU).
 // Every rank owns an exchange buffer that all other ranks have mapped (CUDA IPC):
-//     [parity 0/1][ records (G, B, k, 3) int32 | flags (G, B) uint32 ]
+//     [epoch % 3][ records (G, B, k, 3) int32 | flags (G, B) uint32 ]
 // CTA b of rank r stores query b's k packed records into slot r of EVERY rank's buffer (plain
 // stores over NVLink), fences (system scope), then raises flag (r, b) on every rank with the
 // step's epoch; it then waits until the G flags of query b in its OWN buffer carry the epoch
 // and merges the G*k records exactly like merge_kernel.  One launch replaces ncclAllGather +
-// merge_kernel.  Parities alternate per step: a rank can be at most one step ahead of a peer
-// (its next merge waits for that peer's flag), so two buffers suffice.
+// merge_kernel.  Three buffers rotate with the epoch: in the split form (send of step i+1 enqueued
+// BEFORE the wait + merge of step i) a rank may be writing step i+2 while a peer still merges step i.
 // A peer that never arrives (crashed rank) raises bit 1 of `flag` after `timeout_ns` instead of
 // hanging the GPU.
 // ------------------------------------------------------------------------------------------
@@ -1589,19 +1604,26 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
 __global__ void __launch_bounds__(SEL_THREADS) xchg_merge_kernel(const XchgParams x, int B, unsigned int k,
                                                                   unsigned long long Tp, unsigned int npow2,
                                                                   unsigned long long *scratch, int use_smem,
-                                                                  float *out_d, int *out_idx, int *flag) {
+                                                                  float *out_d, int *out_idx, int *flag, int phases) {
+    // phases: bit 0 = send (stores + flags), bit 1 = wait + merge.  Split, the two halves of a step
+    // can be enqueued around the NEXT step's scan, so a rank never idles waiting for a slower peer.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x, tid = threadIdx.x;
     const unsigned int n3 = k * 3u;
-    const int *src = x.local_rec + (size_t)b * n3;
-    for (int g = 0; g < x.G; ++g) {
-        int *dst = x.rec[g] + ((size_t)x.rank * B + b) * n3;
-        for (unsigned int i = tid; i < n3; i += SEL_THREADS) dst[i] = src[i];
+    if (phases & 1) {
+        const int *src = x.local_rec + (size_t)b * n3;
+        for (int g = 0; g < x.G; ++g) {
+            int *dst = x.rec[g] + ((size_t)x.rank * B + b) * n3;
+            for (unsigned int i = tid; i < n3; i += SEL_THREADS) dst[i] = src[i];
+        }
+        __syncthreads();
+        if (tid < x.G) {
+            __threadfence_system();   // the CTA's record stores (ordered before by the barrier) precede the flag
+            st_release_sys(x.flags[tid] + (size_t)x.rank * B + b, x.epoch);
+        }
     }
-    __syncthreads();
+    if (!(phases & 2)) return;
     if (tid < x.G) {
-        __threadfence_system();   // the CTA's record stores (ordered before by the barrier) precede the flag
-        st_release_sys(x.flags[tid] + (size_t)x.rank * B + b, x.epoch);
         const unsigned int *mine = x.flags[x.rank] + (size_t)tid * B + b;
         const unsigned long long t0 = globaltimer_ns();
         while (ld_acquire_sys(mine) != x.epoch) {
@@ -2082,11 +2104,25 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
                                           + sizeof(float2) * fftx::EX2_FLOAT2 + 16
                                     : 0;
     if (use_fft) {
-        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
-        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
-        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
-        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
     }
+    // one launcher for the 8 instantiations (single query / seed launch / embedded flavour)
+    auto launch_fft = [&](bool seed, unsigned int grid) {
+        const bool sq = nq == 1, em = emb != nullptr;
+#define PSH_FFT_CASE(SQ, SD, EM) \
+        if (sq == SQ && seed == SD && em == EM) fft_scan_kernel<SQ, SD, EM><<<grid, fftx::THREADS, smem_fft, stream>>>(fp);
+        PSH_FFT_CASE(true, false, false) PSH_FFT_CASE(false, false, false) PSH_FFT_CASE(true, true, false)
+        PSH_FFT_CASE(false, true, false) PSH_FFT_CASE(true, false, true) PSH_FFT_CASE(false, false, true)
+        PSH_FFT_CASE(true, true, true) PSH_FFT_CASE(false, true, true)
+#undef PSH_FFT_CASE
+    };
     const bool fuse_final = k <= SEL_LIST;                  // last select also sorts and decodes
 
     // ---- seedless schedule (large ensembles): seed launch -> ONE launch over all pairs -> exact
@@ -2104,8 +2140,7 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
             fp.i0 = 0; fp.i1 = nseed;
             {
                 ProfScope ps(stream, 0);
-                if (nq == 1) fft_scan_kernel<true, true><<<(unsigned int)nseed, fftx::THREADS, smem_fft, stream>>>(fp);
-                else fft_scan_kernel<false, true><<<(unsigned int)nseed, fftx::THREADS, smem_fft, stream>>>(fp);
+                launch_fft(true, (unsigned int)nseed);
             }
             PSH_LAUNCHED();
             fp.i0 = 0; fp.i1 = p.npairs;
@@ -2114,8 +2149,7 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
             if (ctas > max_ctas) ctas = max_ctas;
             {
                 ProfScope ps(stream, 0);
-                if (nq == 1) fft_scan_kernel<true, false><<<(unsigned int)ctas, fftx::THREADS, smem_fft, stream>>>(fp);
-                else fft_scan_kernel<false, false><<<(unsigned int)ctas, fftx::THREADS, smem_fft, stream>>>(fp);
+                launch_fft(false, (unsigned int)ctas);
             }
             PSH_LAUNCHED();
             { int rc_ = launch_rerank(); if (rc_ != 0) return rc_; }
@@ -2166,8 +2200,7 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
             if (ctas > max_ctas) ctas = max_ctas;
             {
                 ProfScope ps(stream, 0);
-                if (nq == 1) fft_scan_kernel<true, false><<<(unsigned int)ctas, fftx::THREADS, smem_fft, stream>>>(fp);
-                else fft_scan_kernel<false, false><<<(unsigned int)ctas, fftx::THREADS, smem_fft, stream>>>(fp);
+                launch_fft(false, (unsigned int)ctas);
             }
             PSH_LAUNCHED();
         } else {
@@ -2397,7 +2430,7 @@ static size_t xchg_flag_bytes(int G, int B) { return align_up((size_t)G * B * si
 
 size_t psh_xchg_bytes(int G, int B, int64_t k) {
     if (G <= 0 || G > XCHG_MAX_PEERS || B <= 0 || k <= 0) return 0;
-    return 2 * (xchg_rec_bytes(G, B, k) + xchg_flag_bytes(G, B));
+    return 3 * (xchg_rec_bytes(G, B, k) + xchg_flag_bytes(G, B));
 }
 
 int psh_xchg_create(size_t bytes, void **d_buf, unsigned char *handle64) {
@@ -2435,18 +2468,17 @@ int psh_xchg_destroy(void *d_buf) {
     return PSH_OK;
 }
 
-int psh_allgather_merge_packed(const int32_t *d_rec_local, void *const *bufs, int G, int rank, int B, int64_t k,
-                               int64_t Tp, uint32_t epoch, float *d_out_dist, int32_t *d_out_idx,
-                               int32_t *d_flag, void *stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    if (!d_rec_local || !bufs || !d_out_dist || !d_out_idx || G <= 0 || G > XCHG_MAX_PEERS || rank < 0 || rank >= G ||
-        B <= 0 || k <= 0 || Tp <= 0 || epoch == 0)
-        return PSH_E_ARG;
+static int xchg_launch(const int32_t *d_rec_local, void *const *bufs, int G, int rank, int B, int64_t k,
+                       int64_t Tp, uint32_t epoch, float *d_out_dist, int32_t *d_out_idx,
+                       int32_t *d_flag, int phases, cudaStream_t stream) {
+    if (!bufs || G <= 0 || G > XCHG_MAX_PEERS || rank < 0 || rank >= G || B <= 0 || k <= 0 || epoch == 0) return PSH_E_ARG;
+    if ((phases & 1) && !d_rec_local) return PSH_E_ARG;
+    if ((phases & 2) && (!d_out_dist || !d_out_idx || Tp <= 0)) return PSH_E_ARG;
     unsigned long long n = (unsigned long long)G * (unsigned long long)k;
     if (n > 0x7fffffffull) return PSH_E_TOO_LARGE;
     XchgParams x;
     const size_t rb = xchg_rec_bytes(G, B, k), fb = xchg_flag_bytes(G, B);
-    const size_t par = (size_t)(epoch & 1u) * (rb + fb);
+    const size_t par = (size_t)(epoch % 3u) * (rb + fb);
     for (int g = 0; g < G; ++g) {
         if (!bufs[g]) return PSH_E_ARG;
         unsigned char *base = static_cast<unsigned char *>(bufs[g]) + par;
@@ -2459,16 +2491,37 @@ int psh_allgather_merge_packed(const int32_t *d_rec_local, void *const *bufs, in
     int use_smem = npow2 <= SORT_SMEM_MAX ? 1 : 0;
     size_t smem = use_smem ? (size_t)npow2 * sizeof(unsigned long long) : 0;
     if (n * 12ull <= MERGE_RANK_SMEM_MAX && !merge_sort_forced()) { use_smem = 2; smem = (size_t)n * 12; }  // merge by rank
+    if (!(phases & 2)) { use_smem = 1; smem = 0; }   // send only: nothing is merged
     unsigned long long *scratch = nullptr;
     if (!use_smem) PSH_CUDA(cudaMallocAsync(&scratch, (size_t)B * npow2 * sizeof(unsigned long long), stream));
     if (smem > 48 * 1024)
         PSH_CUDA(cudaFuncSetAttribute(xchg_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ProfScope ps_merge(stream, 2);
-    xchg_merge_kernel<<<B, SEL_THREADS, smem, stream>>>(x, B, (unsigned int)k, (unsigned long long)Tp, npow2, scratch,
-                                                        use_smem, d_out_dist, d_out_idx, d_flag);
+    {
+        ProfScope ps_merge(stream, 2);
+        xchg_merge_kernel<<<B, SEL_THREADS, smem, stream>>>(x, B, (unsigned int)k, (unsigned long long)Tp, npow2, scratch,
+                                                            use_smem, d_out_dist, d_out_idx, d_flag, phases);
+    }
     PSH_LAUNCHED();
     if (scratch) PSH_CUDA(cudaFreeAsync(scratch, stream));
     return PSH_OK;
+}
+
+int psh_allgather_merge_packed(const int32_t *d_rec_local, void *const *bufs, int G, int rank, int B, int64_t k,
+                               int64_t Tp, uint32_t epoch, float *d_out_dist, int32_t *d_out_idx,
+                               int32_t *d_flag, void *stream_) {
+    return xchg_launch(d_rec_local, bufs, G, rank, B, k, Tp, epoch, d_out_dist, d_out_idx, d_flag, 3,
+                       (cudaStream_t)stream_);
+}
+
+int psh_xchg_send(const int32_t *d_rec_local, void *const *bufs, int G, int rank, int B, int64_t k,
+                  uint32_t epoch, void *stream_) {
+    return xchg_launch(d_rec_local, bufs, G, rank, B, k, 1, epoch, nullptr, nullptr, nullptr, 1, (cudaStream_t)stream_);
+}
+
+int psh_xchg_merge(void *const *bufs, int G, int rank, int B, int64_t k, int64_t Tp, uint32_t epoch,
+                   float *d_out_dist, int32_t *d_out_idx, int32_t *d_flag, void *stream_) {
+    return xchg_launch(nullptr, bufs, G, rank, B, k, Tp, epoch, d_out_dist, d_out_idx, d_flag, 2,
+                       (cudaStream_t)stream_);
 }
 
 int psh_gather_paths(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride,

@@ -121,20 +121,46 @@ def _peer_exchange(ps, device, B, k):
     return ex if ex.ok else None
 
 
-def _exchange_and_merge(ps, rows, rec, rec_all, Tp, flag):
+def flush_deferred_merge(ps) -> None:
+    """Enqueue the wait + merge of the step whose records were sent last (pipelined scans)."""
+    pend = getattr(ps, "_pending_merge", None)
+    if pend is None:
+        return
+    ps._pending_merge = None
+    ex, epoch, B, k, Tp, dist_, idx_, flag = pend
+    _lib.xchg_merge(ex.bufs, ex.rank, B, k, Tp, epoch, dist_, idx_, flag)
+
+
+def _exchange_and_merge(ps, rows, rec, rec_all, Tp, flag, defer: bool = False):
+    """All-gather of the per-rank records + merge.  `defer` (pipelines of enqueue-only scans): only
+    the send half is enqueued now; the wait + merge follows the NEXT step's scan and send (or the
+    pipeline's final check), so no rank idles while a slower peer finishes the same step.  The
+    returned tensors are filled by then -- the caller must not read them before `_check_pipeline`."""
     pg = ps._pg
     if rows.is_cuda:
-        ex = _peer_exchange(ps, rows.device, rec.shape[0], rec.shape[1])
+        B, k = rec.shape[0], rec.shape[1]
+        pend = getattr(ps, "_pending_merge", None)
+        if pend is not None and (not defer or pend[2:4] != (B, k)):
+            flush_deferred_merge(ps)
+        ex = _peer_exchange(ps, rows.device, B, k)
         if ex is not None:
             ex.epoch += 1
-            return _lib.allgather_merge_packed(rec, ex.bufs, ex.rank, Tp, ex.epoch, flag)
+            if not defer or os.environ.get("PSH_DEFER", "1") == "0":
+                return _lib.allgather_merge_packed(rec, ex.bufs, ex.rank, Tp, ex.epoch, flag)
+            _lib.xchg_send(rec, ex.bufs, ex.rank, ex.epoch)
+            flush_deferred_merge(ps)     # the previous step's merge, behind this step's scan and send
+            dist_ = torch.empty((B, k), dtype=torch.float32, device=rows.device)
+            idx_ = torch.empty((B, k, 2), dtype=torch.int32, device=rows.device)
+            ps._pending_merge = (ex, ex.epoch, B, k, Tp, dist_, idx_, flag)
+            return dist_, idx_
         dist.all_gather_into_tensor(rec_all, rec, group=pg)          # one ncclAllGather, B*k*12 bytes per rank
         return _lib.merge_topk_packed(rec_all, Tp, flag)
     dist.all_gather(list(rec_all.unbind(0)), rec, group=pg)          # gloo (CPU tests) has no *_into_tensor
     return _lib.merge_topk(rec_all[..., 0].contiguous().view(torch.float32), rec_all[..., 1:].contiguous(), Tp)
 
 
-def sharded_scan(ps, rows: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int, W: int | None = None):
+def sharded_scan(ps, rows: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int, W: int | None = None,
+                 defer: bool = False):
     """Local exact top-k on this rank's rows, all-gather, merge.  Every rank returns the global
     (dist (B,k), idx (B,k,2)) with GLOBAL trajectory indices.  On CUDA the scan, the all-gather
     and the merge are enqueued back to back without a host synchronisation; the candidate-buffer
@@ -165,7 +191,7 @@ def sharded_scan(ps, rows: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int
         ps._shard_bufs = bufs
     rec, rec_all, flag = bufs
     _local_records(ps, rows, T, q, H, k, rec, True, W)
-    out = _exchange_and_merge(ps, rows, rec, rec_all, Tp, flag)
+    out = _exchange_and_merge(ps, rows, rec, rec_all, Tp, flag, defer)
     ps._pending_flag = flag if rows.is_cuda else None
     return out
 

@@ -216,7 +216,7 @@ class PathShadowing:
             self._pipeline_B = q.shape[0]
             return dist, idx
         from .distributed import finish_sharded, sharded_scan
-        res = sharded_scan(self, rows, T, q, H, k)
+        res = sharded_scan(self, rows, T, q, H, k, defer=nosync)
         return res if nosync else finish_sharded(self, rows, T, q, H, k, res)
 
     def _run_table(self, device: torch.device):
@@ -269,7 +269,7 @@ class PathShadowing:
         if self._pg is not None:
             from .distributed import finish_sharded, sharded_scan
             self._ex_host = ex_host
-            res = sharded_scan(self, rows, T, ex, H, k, W)
+            res = sharded_scan(self, rows, T, ex, H, k, W, defer=nosync)
             return res if nosync else finish_sharded(self, rows, T, ex, H, k, res, W)
         if k > rows.shape[0] * Tp:
             raise RuntimeError(f"selected index k out of range: k={k} > {rows.shape[0] * Tp} windows")
@@ -285,6 +285,8 @@ class PathShadowing:
         if self._pg is None:
             bad = _lib.scan_overflowed(self._workspace, self._pipeline_B)
         else:
+            from .distributed import flush_deferred_merge
+            flush_deferred_merge(self)
             flag = getattr(self, "_pending_flag", None)
             bad = flag is not None and int(flag.item()) != 0
             if bad:

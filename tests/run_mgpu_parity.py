@@ -63,6 +63,22 @@ def main():
                 and np.array_equal(paths, po) and np.allclose(pred, mo, rtol=1e-6) and np.allclose(pstd, so, rtol=1e-5))
         print(f"rank {rank}/{world} R={R} T={T} W={W} k={k} B={B} adv={adversarial}: {'OK' if good else 'MISMATCH'}", flush=True)
         ok = ok and good
+    # pipelined sharded scans (bench.py's device loop): scan(i+1), send(i+1), merge(i) -- every query's
+    # result must equal the synchronous sharded result once the pipeline has been checked
+    R, T, W, H, k = 700, 2048, 100, 10, 300
+    ds, q = make_inputs(R, T, W, 6, seed=640)
+    lo, hi = shard_bounds(R, world, rank)
+    obj = sb.PathShadowing(sb.Identity(W), sb.RelativeMSE(), ds[lo:hi], sb.PredictionContext(H), device=dev,
+                           row_offset=lo, process_group=dist.group.WORLD)
+    rows, T_ = obj._resident_rows()
+    qd = torch.tensor(q)
+    outs = [obj._scan_device(qd[i:i + 1], rows, T_, k, nosync=True) for i in range(6)]
+    obj._check_pipeline()
+    do, io = oracle.shadow_topk(ds, q, k, H)
+    good = all(np.array_equal(d_.cpu().numpy().view(np.uint32), do[i:i + 1].view(np.uint32))
+               and np.array_equal(i_.cpu().numpy(), io[i:i + 1]) for i, (d_, i_) in enumerate(outs))
+    print(f"rank {rank}/{world} pipelined sharded scans: {'OK' if good else 'MISMATCH'}", flush=True)
+    ok = ok and good
     # Foveal embedding, sharded: every rank must return what ONE GPU holding all rows returns
     # (bit-identical: same kernel, same per-window arithmetic, exact merge), and that agrees with the
     # CPU oracle within the embedded scan's tolerance
