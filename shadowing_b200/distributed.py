@@ -145,7 +145,9 @@ def _exchange_and_merge(ps, rows, rec, rec_all, Tp, flag, defer: bool = False):
         ex = _peer_exchange(ps, rows.device, B, k)
         if ex is not None:
             ex.epoch += 1
-            if not defer or os.environ.get("PSH_DEFER", "1") == "0":
+            # (measured at N = 2 and 4: the split form is no faster -- rank skew is not what the exchange
+            # costs -- so the single fused launch stays the default; PSH_DEFER=1 selects the split form)
+            if not defer or os.environ.get("PSH_DEFER", "0") != "1":
                 return _lib.allgather_merge_packed(rec, ex.bufs, ex.rank, Tp, ex.epoch, flag)
             _lib.xchg_send(rec, ex.bufs, ex.rank, ex.epoch)
             flush_deferred_merge(ps)     # the previous step's merge, behind this step's scan and send

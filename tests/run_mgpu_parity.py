@@ -72,13 +72,16 @@ def main():
                            row_offset=lo, process_group=dist.group.WORLD)
     rows, T_ = obj._resident_rows()
     qd = torch.tensor(q)
-    outs = [obj._scan_device(qd[i:i + 1], rows, T_, k, nosync=True) for i in range(6)]
-    obj._check_pipeline()
     do, io = oracle.shadow_topk(ds, q, k, H)
-    good = all(np.array_equal(d_.cpu().numpy().view(np.uint32), do[i:i + 1].view(np.uint32))
-               and np.array_equal(i_.cpu().numpy(), io[i:i + 1]) for i, (d_, i_) in enumerate(outs))
-    print(f"rank {rank}/{world} pipelined sharded scans: {'OK' if good else 'MISMATCH'}", flush=True)
-    ok = ok and good
+    for defer in ("0", "1"):   # fused exchange launch / split send + deferred merge (PSH_DEFER)
+        os.environ["PSH_DEFER"] = defer
+        outs = [obj._scan_device(qd[i:i + 1], rows, T_, k, nosync=True) for i in range(6)]
+        obj._check_pipeline()
+        good = all(np.array_equal(d_.cpu().numpy().view(np.uint32), do[i:i + 1].view(np.uint32))
+                   and np.array_equal(i_.cpu().numpy(), io[i:i + 1]) for i, (d_, i_) in enumerate(outs))
+        print(f"rank {rank}/{world} pipelined sharded scans (PSH_DEFER={defer}): {'OK' if good else 'MISMATCH'}", flush=True)
+        ok = ok and good
+    os.environ.pop("PSH_DEFER", None)
     # Foveal embedding, sharded: every rank must return what ONE GPU holding all rows returns
     # (bit-identical: same kernel, same per-window arithmetic, exact merge), and that agrees with the
     # CPU oracle within the embedded scan's tolerance
