@@ -6,15 +6,20 @@
   python bench.py --impl reference --gpus N --steps K ...  (CPU reference arm: oracle port)
 
 A "step" is one shadow scan of one query over the resident ensemble.  Prints ONE JSON line.
-  value   : windows/s with the query already in HBM (C-ABI psh_scan_topk_f32, CUDA events)
-  e2e     : windows/s through PathShadowing.shadow() with HOST numpy in/out (pinned H2D of the
-            query, scan, gather, D2H of distances+paths+indices inside the timed region)
-  roofline: the scan kernel against the measured HBM peak (MEASURED_PEAKS.json) -- plus the
-            FP32-issue roof that actually binds this kernel
+  value   : windows/s with the queries already in HBM: the K scans of the timed region are enqueued
+            back to back through the C ABI (psh_scan_topk_f32 | PSH_FLAG_NOSYNC) and verified by ONE
+            psh_scan_overflowed at the end -- no host round trip between queries (CUDA events)
+  e2e     : windows/s through PathShadowing.shadow() with HOST numpy in/out, one call per step (pinned
+            H2D of the query, scan, gather, D2H of distances+paths+indices, one synchronisation)
+  roofline: the scan kernels (seed + main launch) against the measured HBM peak
+            (MEASURED_PEAKS.json) -- plus the FP32-issue roof
   cpu_baseline: the C oracle (port of the reference algorithm) on this box's host cores,
             bounded row sample.
-N > 1: each rank holds its own 32768-row shard (weak scaling, ensemble = N*32768 rows), the
-per-rank top-k are merged with one NCCL all-gather + merge kernel per step.
+  host_enqueue_ms_per_step: host time to enqueue one step (the device loop is GPU-bound while this
+            stays below ms_per_step)
+N > 1: each rank holds its own 32768-row shard (weak scaling, ensemble = N*32768 rows); the per-rank
+top-k are exchanged over NVLink peer memory and merged by one kernel per step (NCCL all-gather +
+merge kernel if the peer mapping is unavailable).
 """
 from __future__ import annotations
 
@@ -309,7 +314,9 @@ def run_ours(args):
                        "rows_per_gpu": R_PER_GPU, "scan_mode": eff_mode,
                        "l2": "512 MiB shard per GPU > 126 MB L2 (inputs larger than L2)",
                        "dataset": "resident in HBM (uploaded once at construction)",
-                       "parallelism": f"rows sharded x{world}, all-gather + merge of per-GPU top-k"},
+                       "timing": "K enqueue-only scans pipelined on one stream + one overflow check (value); "
+                                 "one synchronous shadow() per step (e2e)",
+                       "parallelism": f"rows sharded x{world}, peer-memory all-gather fused with the merge of per-GPU top-k"},
             "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": W * 4,
                     "d2h_bytes_per_step": int(d_np.nbytes + p_np.nbytes + i_np.nbytes),
                     "ms_per_step": ms_e2e / args.steps},
