@@ -168,8 +168,10 @@ int psh_merge_topk_packed(const int32_t *d_rec_parts, int G, int B, int64_t k, i
  *               this process (bufs[rank] = the own buffer)
  *   d_flag      int32, zeroed by the caller: bit 0 = a shard's NOSYNC scan overflowed,
  *               bit 1 = a peer's records did not arrive within 30 s (results invalid)
- * Each CTA stores its query's records into every rank's buffer, raises a per-(rank, query) flag
- * (st.release.sys), waits for the G flags of its query and merges (same order as psh_merge_topk).
+ * Each CTA stores its query's records into every rank's buffer -- every datum in one 8-byte store
+ * together with the epoch, so the words validate themselves: no fence, no flag (fallback for
+ * G*k*12 bytes > 200 KB: plain stores, a system-scope fence and per-(rank, query) flags) --, polls
+ * the G record sets of its query and merges (same order as psh_merge_topk).
  */
 size_t psh_xchg_bytes(int G, int B, int64_t k);
 int psh_xchg_create(size_t bytes, void **d_buf, unsigned char *ipc_handle_64);

@@ -1638,6 +1638,86 @@ __global__ void __launch_bounds__(SEL_THREADS) xchg_merge_kernel(const XchgParam
 }
 
 // ------------------------------------------------------------------------------------------
+// The same exchange without fences or flags ("LL": every 4-byte datum travels in ONE 8-byte store
+// together with the step's epoch, so a word validates itself -- the receiver polls each word until
+// its upper half carries the epoch; 8-byte stores are single-copy atomic, also over NVLink).  The
+// system-scope fence + flag round trip of xchg_merge_kernel is what its 35-45 us were spent on.
+// Merge by rank straight out of the polled words: (distance bits, flat index) go to shared
+// memory, the output (r, t) is recovered from the flat index.  Needs G*k*12 bytes of shared memory
+// (else xchg_merge_kernel runs).  The record area of the exchange buffer is sized for this form.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEL_THREADS) xchg_ll_kernel(const XchgParams x, int B, unsigned int k,
+                                                               unsigned long long Tp, float *out_d, int *out_idx,
+                                                               int *flag, int phases) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const unsigned int n3 = k * 3u;
+    const unsigned long long tag = (unsigned long long)x.epoch << 32;
+    if (phases & 1) {
+        const int *src = x.local_rec + (size_t)b * n3;
+        for (int g = 0; g < x.G; ++g) {
+            volatile unsigned long long *dst =
+                reinterpret_cast<volatile unsigned long long *>(x.rec[g]) + ((size_t)x.rank * B + b) * n3;
+            for (unsigned int i = tid; i < n3; i += SEL_THREADS) dst[i] = tag | (unsigned int)src[i];
+        }
+    }
+    if (!(phases & 2)) return;
+    const unsigned int n = (unsigned int)x.G * k;
+    unsigned long long *fl = reinterpret_cast<unsigned long long *>(smem_raw);
+    unsigned int *db = reinterpret_cast<unsigned int *>(fl + n);
+    const volatile unsigned long long *mine = reinterpret_cast<const volatile unsigned long long *>(x.rec[x.rank]);
+    const unsigned long long t0 = globaltimer_ns();
+    bool timed_out = false;
+    for (unsigned int i = tid; i < n; i += SEL_THREADS) {
+        const unsigned int g = i / k, j = i - g * k;
+        const volatile unsigned long long *w = mine + (((size_t)g * B + b) * k + j) * 3;
+        unsigned int v[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            unsigned long long word = w[c];
+            while ((word >> 32) != x.epoch && !timed_out) {
+                if (globaltimer_ns() - t0 > x.timeout_ns) { timed_out = true; break; }
+                __nanosleep(64);
+                word = w[c];
+            }
+            v[c] = (unsigned int)word;
+        }
+        if (flag != nullptr && v[0] == 0xffffffffu) atomicOr(flag, 1);   // a shard overflowed
+        db[i] = v[0];
+        fl[i] = (unsigned long long)v[1] * Tp + (unsigned long long)v[2];
+    }
+    if (timed_out && flag != nullptr) atomicOr(flag, 2);
+    __syncthreads();
+    for (unsigned int i = tid; i < n; i += SEL_THREADS) {
+        const unsigned int g = i / k, j = i - g * k;
+        const unsigned int dk = db[i];
+        const unsigned long long fk = fl[i];
+        unsigned int rank = j;
+        for (unsigned int g2 = 0; g2 < (unsigned int)x.G && rank < k; ++g2) {
+            if (g2 == g) continue;
+            const unsigned int base = g2 * k;
+            unsigned int lo = 0, hi = k;
+            while (lo < hi) {
+                const unsigned int mid = (lo + hi) >> 1;
+                const unsigned int d2 = db[base + mid];
+                bool before = d2 < dk;
+                if (d2 == dk) {
+                    const unsigned long long f2 = fl[base + mid];
+                    before = f2 < fk || (f2 == fk && g2 < g);
+                }
+                if (before) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < k) {
+            out_d[(size_t)b * k + rank] = __uint_as_float(dk);
+            out_idx[((size_t)b * k + rank) * 2 + 0] = (int)(fk / Tp);
+            out_idx[((size_t)b * k + rank) * 2 + 1] = (int)(fk % Tp);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // gather: paths[i, :] = dataset[r, t : t+L]   (path_shadowing.py:210-216), one warp per path
 // ------------------------------------------------------------------------------------------
 __global__ void gather_kernel(const float *__restrict__ ds, long long R, long long row_stride,
@@ -2425,7 +2505,13 @@ int psh_merge_topk_packed(const int32_t *d_rec_parts, int G, int B, int64_t k, i
 }
 
 // ---- exchange buffers for the peer-memory all-gather (multi-GPU) ----
-static size_t xchg_rec_bytes(int G, int B, int64_t k) { return align_up((size_t)G * B * (size_t)k * 3 * sizeof(int), 256); }
+static size_t xchg_rec_bytes(int G, int B, int64_t k) {   // sized for the LL form: 8 bytes per 4-byte datum
+    return align_up((size_t)G * B * (size_t)k * 3 * sizeof(unsigned long long), 256);
+}
+static bool xchg_ll_enabled() {   // PSH_XCHG_LL=0: always the fence + flag form (A/B measurements)
+    const char *e = getenv("PSH_XCHG_LL");
+    return !(e != nullptr && e[0] == '0');
+}
 static size_t xchg_flag_bytes(int G, int B) { return align_up((size_t)G * B * sizeof(unsigned int), 256); }
 
 size_t psh_xchg_bytes(int G, int B, int64_t k) {
@@ -2492,6 +2578,19 @@ static int xchg_launch(const int32_t *d_rec_local, void *const *bufs, int G, int
     size_t smem = use_smem ? (size_t)npow2 * sizeof(unsigned long long) : 0;
     if (n * 12ull <= MERGE_RANK_SMEM_MAX && !merge_sort_forced()) { use_smem = 2; smem = (size_t)n * 12; }  // merge by rank
     if (!(phases & 2)) { use_smem = 1; smem = 0; }   // send only: nothing is merged
+    if (n * 12ull <= MERGE_RANK_SMEM_MAX && !merge_sort_forced() && xchg_ll_enabled()) {
+        // LL form: self-validating 8-byte words, no fence, no flags
+        const size_t smem_ll = (phases & 2) ? (size_t)n * 12 : 0;
+        if (smem_ll > 48 * 1024)
+            PSH_CUDA(cudaFuncSetAttribute(xchg_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ll));
+        {
+            ProfScope ps_merge(stream, 2);
+            xchg_ll_kernel<<<B, SEL_THREADS, smem_ll, stream>>>(x, B, (unsigned int)k, (unsigned long long)Tp, d_out_dist,
+                                                                d_out_idx, d_flag, phases);
+        }
+        PSH_LAUNCHED();
+        return PSH_OK;
+    }
     unsigned long long *scratch = nullptr;
     if (!use_smem) PSH_CUDA(cudaMallocAsync(&scratch, (size_t)B * npow2 * sizeof(unsigned long long), stream));
     if (smem > 48 * 1024)
