@@ -86,15 +86,14 @@ class Foveal(PathEmbedding):
     (`alpha`, `beta`, `max_context`, `dim`, `slices`) and kernel as path_embedding.py:142-172."""
 
     def __init__(self, alpha: float, beta: float, max_context: int, device: str = "cpu"):
-        self.alpha = alpha
-        self.beta = beta
-        self.max_context = max_context
+        self.alpha, self.beta, self.max_context = alpha, beta, max_context
         self.dim = int(np.floor(np.log(max_context) / np.log(alpha)))
-        lengths = [int(alpha ** n) for n in range(1, 1 + self.dim)]
-        self.slices = [slice(-le, None) for le in lengths]
-        kernel = torch.zeros(self.dim, 1, max_context, dtype=torch.float32, device=device)
-        for row, le in enumerate(lengths):
-            kernel[row, :, -le:] = le ** (-beta)
+        lengths = np.array([int(alpha ** n) for n in range(1, self.dim + 1)], dtype=np.int64)
+        self.slices = [slice(-int(le), None) for le in lengths]
+        # row n: weight length**-beta on the last `length` taps, zero before (one trailing box per row)
+        weights = np.array([int(le) ** (-beta) for le in lengths], dtype=np.float64)
+        trailing = np.arange(max_context)[None, :] >= (max_context - lengths)[:, None]
+        kernel = torch.tensor(np.where(trailing, weights[:, None], 0.0)[:, None, :], dtype=torch.float32, device=device)
         super().__init__(kernel)
 
 
