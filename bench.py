@@ -7,8 +7,11 @@
 
 A "step" is one shadow scan of one query over the resident ensemble.  Prints ONE JSON line.
   value   : windows/s with the queries already in HBM: the K scans of the timed region are enqueued
-            back to back through the C ABI (psh_scan_topk_f32 | PSH_FLAG_NOSYNC) and verified by ONE
-            psh_scan_overflowed at the end -- no host round trip between queries (CUDA events)
+            back to back through the C ABI (psh_scan_topk_f32 | PSH_FLAG_NOSYNC), alternating between
+            two streams with their own workspaces (query i+1's prologue and main launch overlap query
+            i's re-rank and select), and verified by ONE psh_scan_overflowed per workspace at the end
+            -- no host round trip between queries (CUDA events on the caller's stream, which joins
+            both streams before the closing event)
   e2e     : windows/s through PathShadowing.shadow() with HOST numpy in/out, one call per step (pinned
             H2D of the query, scan, gather, D2H of distances+paths+indices, one synchronisation)
   roofline: the scan kernels (seed + main launch) against the measured HBM peak
@@ -214,6 +217,7 @@ def run_ours(args):
     obj = sb.PathShadowing(sb.Identity(W), sb.RelativeMSE(), ds_host, sb.PredictionContext(H), device=dev,
                            row_offset=rank * R_PER_GPU, process_group=pg, scan_mode=args.mode)
     rows, _ = obj._resident_rows()
+    obj._pipe_streams = max(1, args.streams) if world == 1 else 1
     qs_dev = qs_host.to(dev)
     torch.cuda.synchronize()
 
@@ -266,6 +270,10 @@ def run_ours(args):
     clocks = sampler.stop()
 
     # ---------------- per-kernel timing (roofline) ----------------
+    # one stream: the roofline wants each kernel's own duration, not its duration next to the
+    # neighbouring query's kernels
+    pipe_streams = obj._pipe_streams
+    obj._pipe_streams = 1
     L = _lib.lib()
     L.psh_profile_begin()
     for i in range(args.steps):
@@ -314,7 +322,7 @@ def run_ours(args):
                        "rows_per_gpu": R_PER_GPU, "scan_mode": eff_mode,
                        "l2": "512 MiB shard per GPU > 126 MB L2 (inputs larger than L2)",
                        "dataset": "resident in HBM (uploaded once at construction)",
-                       "timing": "K enqueue-only scans pipelined on one stream + one overflow check (value); "
+                       "timing": f"K enqueue-only scans pipelined on {pipe_streams} stream(s) + one overflow check (value); "
                                  "one synchronous shadow() per step (e2e)",
                        "parallelism": f"rows sharded x{world}, peer-memory all-gather fused with the merge of per-GPU top-k"},
             "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": W * 4,
@@ -350,6 +358,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="auto", choices=["auto", "fft", "filter", "exact"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("PSH_STREAMS", "2")),
+                    help="streams the pipelined device loop alternates between (N = 1 only; 1: the caller's stream)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -17,6 +17,7 @@ raises NotImplementedError (no silent fallback).
 """
 from __future__ import annotations
 
+import os
 import weakref
 from pathlib import Path
 from typing import Callable
@@ -124,6 +125,9 @@ class PathShadowing:
         self._fft_aux = None   # (key, aux buffer) for (resident rows, W, H)
         self._staging = None   # pinned host buffers for the results of shadow()
         self._runs = None      # (key, device run table) of a non-Identity embedding kernel
+        self._pipeline_B = 0   # queries of the last enqueue-only scan on the main workspace
+        self._side = None      # side streams [stream, workspace, B] of pipelined enqueue-only scans
+        self._pipe_streams = max(1, int(os.environ.get("PSH_STREAMS", "1")))
 
     # ------------------------------------------------------------------ device residency
     def _dev(self) -> torch.device:
@@ -210,6 +214,8 @@ class PathShadowing:
             if k > n_windows:
                 raise RuntimeError(f"selected index k out of range: k={k} > {n_windows} windows")
             mode, aux = self._mode_and_aux(rows, T, W, H)
+            if nosync and out is None and self._pipe_streams > 1:   # (shadow() brings its own `out`: one stream)
+                return self._scan_on_side_stream(rows, T, q, H, k, mode, aux)
             dist, idx, self._workspace = _lib.scan_topk(
                 rows, T, q, H, k, self._row_offset, mode | (_lib.PSH_FLAG_NOSYNC if nosync else 0),
                 self._workspace, aux, out)
@@ -218,6 +224,28 @@ class PathShadowing:
         from .distributed import finish_sharded, sharded_scan
         res = sharded_scan(self, rows, T, q, H, k, defer=nosync)
         return res if nosync else finish_sharded(self, rows, T, q, H, k, res)
+
+    def _scan_on_side_stream(self, rows, T, q, H, k, mode, aux):
+        """Pipelines of enqueue-only scans, `pipeline_streams` > 1: consecutive queries alternate
+        between side streams, each with its own workspace, so that query i+1's prologue and main
+        launch overlap query i's re-rank and select (two tiny grids that leave the GPU idle).
+        `_check_pipeline` joins the side streams back into the caller's stream."""
+        dev = rows.device
+        if self._side is None or len(self._side) != self._pipe_streams:
+            self._side = [[torch.cuda.Stream(device=dev), None, 0] for _ in range(self._pipe_streams)]
+            self._side_i = 0
+        slot = self._side[self._side_i % self._pipe_streams]
+        self._side_i += 1
+        side, cur = slot[0], torch.cuda.current_stream(dev)
+        side.wait_stream(cur)                      # the query comes from `cur`
+        q.record_stream(side)
+        with torch.cuda.stream(side):
+            dist, idx, slot[1] = _lib.scan_topk(rows, T, q, H, k, self._row_offset, mode | _lib.PSH_FLAG_NOSYNC,
+                                                slot[1], aux)
+        slot[2] = q.shape[0]
+        dist.record_stream(cur)                    # the results are consumed on `cur` after the join
+        idx.record_stream(cur)
+        return dist, idx
 
     def _run_table(self, device: torch.device):
         """Device run table of a non-Identity embedding kernel (None for Identity)."""
@@ -283,7 +311,16 @@ class PathShadowing:
         """Synchronise behind a pipeline of `nosync` scans; raises if any of them overflowed a
         candidate buffer (adversarially ordered data: those scans must be repeated synchronously)."""
         if self._pg is None:
-            bad = _lib.scan_overflowed(self._workspace, self._pipeline_B)
+            bad = False
+            if self._side is not None:
+                cur = torch.cuda.current_stream(self._dev())
+                for slot in self._side:
+                    if slot[1] is not None and slot[2] > 0:
+                        cur.wait_stream(slot[0])
+                        bad = _lib.scan_overflowed(slot[1], slot[2]) or bad
+                        slot[2] = 0
+            if self._pipeline_B:
+                bad = _lib.scan_overflowed(self._workspace, self._pipeline_B) or bad
         else:
             from .distributed import flush_deferred_merge
             flush_deferred_merge(self)

@@ -591,3 +591,27 @@ def test_unsupported_plugins_raise():
     ds, q = make_inputs(4, 100, 8, 1)
     with pytest.raises(NotImplementedError):
         sb.PathShadowing(sb.Identity(8), Cosine(), ds, sb.PredictionContext(2)).shadow(q, k=3)
+
+
+def test_two_stream_pipeline_matches_single_stream():
+    """`_pipe_streams = 2`: consecutive enqueue-only scans alternate between two side streams with
+    their own workspaces; results are those of the one-stream pipeline, overflow is still caught."""
+    R, T, W, H, k = 2048, 2048, 64, 4, 128
+    ds, q = make_inputs(R, T, W, 6, seed=93)
+    obj = _obj(ds, W, H, scan_mode="fft")
+    rows, T_ = obj._resident_rows()
+    qd = torch.tensor(q).cuda()
+    do, io = oracle.shadow_topk(ds, q, k, H)
+    obj._pipe_streams = 2
+    outs = [obj._scan_device(qd[i:i + 1], rows, T_, k, nosync=True) for i in range(6)]
+    obj._check_pipeline()
+    for i, (d, idx) in enumerate(outs):
+        assert_topk_equal(d.cpu().numpy(), idx.cpu().numpy(), do[i:i + 1], io[i:i + 1])
+    obj._scan_device(qd[:1] * 1e-3, rows, T_, k, nosync=True)     # overflows (seed threshold +inf)
+    obj._scan_device(qd[1:2], rows, T_, k, nosync=True)
+    with pytest.raises(_lib.PshadowError):
+        obj._check_pipeline()
+    obj._scan_device(qd[1:2], rows, T_, k, nosync=True)
+    obj._check_pipeline()
+    d, _, idx = obj.shadow(q[:2], k=k)                              # shadow() keeps to one stream
+    assert_topk_equal(d, idx, do[:2], io[:2])
