@@ -141,18 +141,27 @@ def make_queries(n: int):
     return torch.randn(n, 1, W, generator=g, dtype=torch.float32) * 0.01
 
 
+def host_cores() -> int:
+    """Host threads this process may use (torchrun exports OMP_NUM_THREADS=1: the oracle is told the
+    thread count explicitly, so the CPU arm always runs on all the cores it can use)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline_run(ds_np: np.ndarray, q_np: np.ndarray, target_s: float = 12.0):
     """C oracle (all host threads) on a bounded sample of rows of the same workload."""
     from oracle import oracle
-    cores = oracle.num_threads()
+    cores = host_cores()
     rows = min(256 * max(cores // 8, 1), ds_np.shape[0])
     t0 = time.perf_counter()
-    oracle.shadow_topk(ds_np[:rows], q_np, K_NEIGH, H)
+    oracle.shadow_topk(ds_np[:rows], q_np, K_NEIGH, H, nthreads=cores)
     dt = time.perf_counter() - t0
     rate = rows * TP / dt
     rows2 = int(min(ds_np.shape[0], max(rows, rate * target_s / TP)))
     t0 = time.perf_counter()
-    oracle.shadow_topk(ds_np[:rows2], q_np, K_NEIGH, H)
+    oracle.shadow_topk(ds_np[:rows2], q_np, K_NEIGH, H, nthreads=cores)
     dt = time.perf_counter() - t0
     return {"value": rows2 * TP / dt, "unit": "windows/s", "cores": cores, "kind": "port",
             "sample": f"first {rows2} of {ds_np.shape[0]} rows x T={T}, one query, W={W}, k={K_NEIGH}: "
@@ -164,20 +173,20 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle
-    cores = oracle.num_threads()
+    cores = host_cores()
     ds = make_shard(0).numpy()
     qs = make_queries(args.steps + args.warmup).numpy()
     # bounded sample per step: ~2 s of CPU work, fixed across steps
     rows = min(256 * max(cores // 8, 1), R_PER_GPU)
     t0 = time.perf_counter()
-    oracle.shadow_topk(ds[:rows], qs[0], K_NEIGH, H)
+    oracle.shadow_topk(ds[:rows], qs[0], K_NEIGH, H, nthreads=cores)
     rate = rows * TP / (time.perf_counter() - t0)
     rows = int(min(R_PER_GPU, max(rows, rate * 2.0 / TP)))
     for i in range(args.warmup):
-        oracle.shadow_topk(ds[:rows], qs[i], K_NEIGH, H)
+        oracle.shadow_topk(ds[:rows], qs[i], K_NEIGH, H, nthreads=cores)
     t0 = time.perf_counter()
     for i in range(args.steps):
-        oracle.shadow_topk(ds[:rows], qs[args.warmup + i], K_NEIGH, H)
+        oracle.shadow_topk(ds[:rows], qs[args.warmup + i], K_NEIGH, H, nthreads=cores)
     dt = time.perf_counter() - t0
     val = rows * TP * args.steps / dt
     sample = (f"each step = first {rows} of {R_PER_GPU} rows x T={T}, one query (oracle/shadow_oracle.c port of "
