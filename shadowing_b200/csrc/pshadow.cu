@@ -2512,6 +2512,12 @@ static bool xchg_ll_enabled() {   // PSH_XCHG_LL=0: always the fence + flag form
     const char *e = getenv("PSH_XCHG_LL");
     return !(e != nullptr && e[0] == '0');
 }
+static unsigned long long xchg_timeout_ns() {   // PSH_XCHG_TIMEOUT_MS: how long a rank waits for its peers (default 30 s)
+    const char *e = getenv("PSH_XCHG_TIMEOUT_MS");
+    long long ms = e != nullptr ? atoll(e) : 0;
+    if (ms <= 0) ms = 30000;
+    return (unsigned long long)ms * 1000000ull;
+}
 static size_t xchg_flag_bytes(int G, int B) { return align_up((size_t)G * B * sizeof(unsigned int), 256); }
 
 size_t psh_xchg_bytes(int G, int B, int64_t k) {
@@ -2572,7 +2578,7 @@ static int xchg_launch(const int32_t *d_rec_local, void *const *bufs, int G, int
         x.flags[g] = reinterpret_cast<unsigned int *>(base + rb);
     }
     x.local_rec = d_rec_local; x.G = G; x.rank = rank; x.epoch = epoch;
-    x.timeout_ns = 30ull * 1000ull * 1000ull * 1000ull;
+    x.timeout_ns = xchg_timeout_ns();
     unsigned int npow2 = 1; while (npow2 < n) npow2 <<= 1;
     int use_smem = npow2 <= SORT_SMEM_MAX ? 1 : 0;
     size_t smem = use_smem ? (size_t)npow2 * sizeof(unsigned long long) : 0;

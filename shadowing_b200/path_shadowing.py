@@ -186,9 +186,14 @@ class PathShadowing:
             return _lib.PSH_MODE_EXACT, None
         if mode == "filter" or W > _lib.FFT_MAX_W:
             return _lib.PSH_MODE_FILTER, None
-        key = (rows.data_ptr(), tuple(rows.shape), T, W, H)
-        if self._fft_aux is None or self._fft_aux[0] != key:
-            self._fft_aux = (key, _lib.fft_prepare(rows, T, W, H))
+        # the spectra / window energies are cached for the RESIDENT rows only, and the cache entry holds
+        # the rows tensor itself (compared with `is`): a foreign `y` of batched_distance gets a throwaway
+        # aux -- a data_ptr() key could be recycled by the caching allocator for the next same-shaped y
+        if self._resident is None or rows is not self._resident[1]:
+            return _lib.PSH_MODE_FFT, _lib.fft_prepare(rows, T, W, H)
+        key = (T, W, H)
+        if self._fft_aux is None or self._fft_aux[0] != key or self._fft_aux[2] is not rows:
+            self._fft_aux = (key, _lib.fft_prepare(rows, T, W, H), rows)
         return _lib.PSH_MODE_FFT, self._fft_aux[1]
 
     # ------------------------------------------------------------------ scan
@@ -272,11 +277,17 @@ class PathShadowing:
             return {}
         kernel = self.embedding.kernel
         runs = self._run_table(rows.device)
-        key = (rows.data_ptr(), tuple(rows.shape), T, W, H, kernel.data_ptr(), kernel._version)
-        if self._fft_aux is None or self._fft_aux[0] != key:
+        key = (T, W, H, kernel.data_ptr(), kernel._version)
+        resident = self._resident is not None and rows is self._resident[1]
+        if not resident:   # a foreign `y`: throwaway aux (see _mode_and_aux)
             K = kernel.detach().cpu()[:, 0, :].double()
-            self._fft_aux = (key, _lib.fft_prepare_embed(rows, T, W, H, runs), K)
-        _, aux, K = self._fft_aux
+            aux = _lib.fft_prepare_embed(rows, T, W, H, runs)
+        else:
+            if (self._fft_aux is None or self._fft_aux[0] != key or len(self._fft_aux) != 4
+                    or self._fft_aux[2] is not rows):
+                K = kernel.detach().cpu()[:, 0, :].double()
+                self._fft_aux = (key, _lib.fft_prepare_embed(rows, T, W, H, runs), rows, K)
+            _, aux, _, K = self._fft_aux
         g = (ex.detach().cpu().double() @ K).float().to(rows.device, non_blocking=True).contiguous()
         return {"g": g, "aux": aux}
 

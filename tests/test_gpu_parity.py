@@ -231,6 +231,24 @@ def test_batched_distance_contract():
     assert_topk_equal(d.numpy(), i.numpy(), do, io)
 
 
+def test_batched_distance_foreign_y_never_reuses_stale_spectra():
+    """batched_distance(x, y) with a `y` that is not the resident dataset, twice, same shapes, fft
+    flavour: the second call must not filter with the first y's spectra / window energies (the
+    caching allocator hands the second upload the first one's address)."""
+    R, T, W, H, k = 64, 2048, 64, 4, 50
+    obj = _obj(make_inputs(R, T, W, 1, seed=41)[0], W, H, scan_mode="fft")
+    for seed in (42, 43, 44):
+        y, q = make_inputs(R, T, W, 2, seed=seed)
+        d, idx = obj.batched_distance(torch.tensor(q), torch.tensor(y), k, 1, False)
+        do, io = oracle.shadow_topk(y, q, k, H)
+        assert_topk_equal(d.numpy(), idx.numpy(), do, io)
+    # and the resident dataset's own cache is still valid afterwards
+    q = make_inputs(R, T, W, 2, seed=41)[1]
+    d, _, idx = obj.shadow(q, k=k)
+    do, io = oracle.shadow_topk(obj.dataset, q, k, H)
+    assert_topk_equal(d, idx, do, io)
+
+
 def test_testing_ipynb_self_consistency():
     """testing.ipynb:62-78 re-expressed for Identity: re-embedding the returned paths and
     re-computing the distance reproduces the returned distances (their rtol 1e-2; here 1e-6)."""
