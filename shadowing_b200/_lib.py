@@ -8,7 +8,8 @@ from pathlib import Path
 import torch
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libpshadow.so"
+import os as _os
+LIB_PATH = _PKG / _os.environ.get("PSH_LIB", "libpshadow.so")   # (A/B builds: PSH_LIB=libpshadow_<variant>.so)
 
 PSH_MODE_EXACT = 0
 PSH_MODE_FILTER = 1

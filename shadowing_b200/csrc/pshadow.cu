@@ -12,6 +12,7 @@
 // which a radix select keeps the k best.  The distance arithmetic reproduces the reference's
 // CPU bit pattern (sequential, non-fused fp32), so indices and distances are bit-identical.
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <math.h>
 #include <string.h>
@@ -121,6 +122,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const float *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src) {   // L2 only (.cg): never a stale L1 line
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ float ld_volatile_f32(const float *p) {
     return *reinterpret_cast<const volatile float *>(p);
 }
@@ -132,22 +147,17 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
 __device__ __forceinline__ float dist_from_s(float s, float qn) { return __fdiv_rn(__fsqrt_rn(s), qn); }
 
 #include "pshadow_fft.cuh"
+#include "pshadow_fft2.cuh"
 
 // ------------------------------------------------------------------------------------------
 // query preparation: ||q|| in torch's contiguous-reduction order (8 interleaved partial sums,
 // lanes added 0..7, scalar tail), state reset.  path_distance.py:65 `x.norm(dim=-1)`.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) qprep_kernel(const float *__restrict__ q, int W, int nq, QState *st,
-                                                    uint4 *zero_a, int zero_a_vec4, uint4 *zero_b, int zero_b_vec4) {
+__global__ void __launch_bounds__(128) qprep_kernel(const float *__restrict__ q, int W, int nq, QState *st) {
     // one warp per query; lanes 0..7 own torch's 8 interleaved partial sums
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (b >= nq) return;
-    // fft flavour: this query's in-launch threshold histogram and seed histogram + ticket start at zero
-    if (zero_a != nullptr)
-        for (int i = lane; i < zero_a_vec4; i += 32) zero_a[(size_t)b * zero_a_vec4 + i] = make_uint4(0u, 0u, 0u, 0u);
-    if (zero_b != nullptr)
-        for (int i = lane; i < zero_b_vec4; i += 32) zero_b[(size_t)b * zero_b_vec4 + i] = make_uint4(0u, 0u, 0u, 0u);
     const float *x = q + (size_t)b * W;
     const int n8 = (W / 8) * 8;
     float acc = 0.0f;
@@ -493,518 +503,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, EXACT ? 2 : 3) scan_kernel(const
 // ------------------------------------------------------------------------------------------
 // FFT flavour: preparation kernels, query spectrum, scan
 // ------------------------------------------------------------------------------------------
-struct FftAux {            // device pointers into the caller's aux buffer
-    float2 *tw32;          // exp(+2 pi i m / 4096), m < 4096
-    double2 *tw64;
-    float *ynorm;          // (npairs) sqrt(|y_a|^2 + |y_b|^2), rounded up
-    float2 *Z;             // (npairs, 4096) spectra of y_a + i y_b
-    float *Y2;             // (R, y2_stride) window energies sum_{j<W} y_{t+j}^2
-    long long npairs;
-    int y2_stride;
-    int nsegv, hop, span;  // virtual rows, see ScanParams
-    long long VR;
-    size_t total;
-};
-
-inline bool fft_aux_layout(long long R, long long T, int W, int H, unsigned char *base, FftAux &a) {
-    if (R <= 0 || T <= 0 || W <= 0 || W > fftx::N / 2 || H < 0 || T - W - H + 1 <= 0) return false;
-    const long long Tp = T - W - H + 1;
-    if (T <= fftx::N) { a.nsegv = 1; a.hop = fftx::N; a.span = (int)Tp; }
-    else {
-        a.hop = (fftx::N - W + 1) & ~3;                   // windows per piece (multiple of 4: TMA alignment)
-        a.span = a.hop;
-        a.nsegv = (int)((Tp + a.hop - 1) / a.hop);
-    }
-    a.VR = R * (long long)a.nsegv;
-    if (a.VR > 0x7fffffffLL) return false;
-    a.npairs = (a.VR + 1) / 2;
-    a.y2_stride = fftx::N;  // padded with +inf beyond the piece's windows: the scan epilogue needs no range checks
-    size_t off = 0;
-    a.tw32 = reinterpret_cast<float2 *>(base + off); off += sizeof(float2) * fftx::N;
-    a.tw64 = reinterpret_cast<double2 *>(base + off); off += sizeof(double2) * fftx::N;
-    a.ynorm = reinterpret_cast<float *>(base + off); off += (sizeof(float) * (size_t)a.npairs + 255) / 256 * 256;
-    a.Z = reinterpret_cast<float2 *>(base + off); off += sizeof(float2) * fftx::N * (size_t)a.npairs;
-    a.Y2 = reinterpret_cast<float *>(base + off); off += (sizeof(float) * (size_t)a.VR * (size_t)a.y2_stride + 255) / 256 * 256;
-    a.total = off;
-    return true;
-}
-
-// debug / test entry: batched 4096-point transform of n independent signals
-__global__ void __launch_bounds__(fftx::THREADS) fft_debug_kernel(const float2 *__restrict__ in, float2 *out,
-                                                                  const float2 *__restrict__ tw, int dir) {
-    __shared__ float2 ex[fftx::EX_FLOAT2];
-    const int tid = threadIdx.x;
-    const float2 *x = in + (size_t)blockIdx.x * fftx::N;
-    float2 v[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = x[tid + 256 * i];
-    const fftx::TwSeeds seeds = fftx::load_seeds(tw, tid);
-    if (dir > 0) fftx::fft4096<1, true>(v, ex, tw, tid, seeds);
-    else if (dir < -1) fftx::fft4096<1, false>(v, ex, tw, tid, seeds);   // dir = -2 / +2: seed-twiddle flavour
-    else fftx::fft4096<-1, true>(v, ex, tw, tid, seeds);
-    float2 *y = out + (size_t)blockIdx.x * fftx::N;
-#pragma unroll
-    for (int c = 0; c < 16; ++c) y[tid + 256 * c] = v[c];
-}
-
-// spectra of row pairs + pair norms: one CTA per pair
-__global__ void __launch_bounds__(fftx::THREADS) fft_prep_spectra_kernel(const float *__restrict__ ds, long long R, int T,
-                                                                         long long row_stride, FftAux a) {
-    __shared__ float2 ex[fftx::EX_FLOAT2];
-    __shared__ double red[fftx::THREADS / 32];
-    const int tid = threadIdx.x;
-    (void)R;
-    const long long pair = blockIdx.x;
-    const long long va = 2 * pair, vb = va + 1;
-    const bool has_b = vb < a.VR;
-    const long long rowa = va / a.nsegv, rowb = (has_b ? vb : va) / a.nsegv;
-    const int oa = (int)(va - rowa * a.nsegv) * a.hop, ob = (int)((has_b ? vb : va) - rowb * a.nsegv) * a.hop;
-    const float *ya = ds + rowa * row_stride + oa;
-    const float *yb = ds + rowb * row_stride + ob;
-    float2 v[16];
-    double e = 0.0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const int n = tid + 256 * i;
-        const float xa = oa + n < T ? ya[n] : 0.0f;
-        const float xb = (ob + n < T && has_b) ? yb[n] : 0.0f;
-        v[i] = make_float2(xa, xb);
-        e += (double)xa * (double)xa + (double)xb * (double)xb;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(FULL, e, o);
-    if ((tid & 31) == 0) red[tid >> 5] = e;
-    fftx::fft4096<-1, true>(v, ex, a.tw32, tid, fftx::load_seeds(a.tw32, tid));  // (its barriers also order the writes to red)
-    float2 *z = a.Z + (size_t)pair * fftx::N;
-#pragma unroll
-    for (int c = 0; c < 16; ++c) z[tid + 256 * c] = v[c];
-    if (tid == 0) {
-        double s = 0.0;
-        for (int i = 0; i < fftx::THREADS / 32; ++i) s += red[i];
-        a.ynorm[pair] = __double2float_ru(sqrt(s) * (1.0 + 1e-7));
-    }
-}
-
-// window energies Y2[r][t] = sum_{j<W} y_{t+j}^2 from an fp64 prefix sum, rounded once: one CTA per row
-__global__ void __launch_bounds__(fftx::THREADS) fft_prep_y2_kernel(const float *__restrict__ ds, int T,
-                                                                    long long row_stride, int W, int Tp, FftAux a) {
-    __shared__ double pfx[fftx::N + 1];
-    __shared__ double wsum[fftx::THREADS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long row = (long long)blockIdx.x / a.nsegv;
-    const int piece = (int)((long long)blockIdx.x - row * a.nsegv);
-    const int o0 = piece * a.hop;                     // first sample / window of this virtual row
-    const float *y = ds + row * row_stride + o0;
-    double loc[16];
-    double run = 0.0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const int n = 16 * tid + i;
-        const double x = o0 + n < T ? (double)y[n] : 0.0;
-        run += x * x;
-        loc[i] = run;
-    }
-    double incl = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const double u = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += u;
-    }
-    if (lane == 31) wsum[warp] = incl;
-    __syncthreads();
-    double off = incl - run;
-    for (int w = 0; w < warp; ++w) off += wsum[w];
-    if (tid == 0) pfx[0] = 0.0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) pfx[16 * tid + i + 1] = off + loc[i];
-    __syncthreads();
-    float *o = a.Y2 + (size_t)blockIdx.x * a.y2_stride;
-    // stored at position p = 256 c + 16 a + b for window t = 256 c + 16 b + a (the scan's output order)
-    for (int pos = tid; pos < a.y2_stride; pos += fftx::THREADS) {
-        const int t = (pos & ~255) | ((pos & 15) << 4) | ((pos >> 4) & 15);
-        const bool mine = t < a.span && o0 + t < Tp;   // the windows this virtual row owns
-        o[pos] = mine ? (float)(pfx[t + W] - pfx[t]) : __int_as_float(0x7f800000);
-    }
-}
-
-// conj(FFT_4096(q padded))/4096 per query (direct fp64 DFT on the exact twiddle table) and
-// max_k |Q_k|.  grid = (4096/64, nq): 64 frequencies per CTA, 4 threads share one frequency.
-constexpr int QFFT_K = 64;
-
-__global__ void __launch_bounds__(4 * QFFT_K) qfft_kernel(const float *__restrict__ q, int W,
-                                                          const double2 *__restrict__ tw64, float2 *Qc, QState *st) {
-    extern __shared__ double qd[];
-    __shared__ double red[4 * QFFT_K / 32];
-    const int b = blockIdx.y, tid = threadIdx.x;
-    for (int j = tid; j < W; j += 4 * QFFT_K) qd[j] = (double)q[(size_t)b * W + j];
-    __syncthreads();
-    if (blockIdx.x == 0 && tid < 32) {   // ||q||_2 of the correlated vector, rounded up
-        double s2 = 0.0;
-        for (int j = tid; j < W; j += 32) s2 += qd[j] * qd[j];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(FULL, s2, o);
-        if (tid == 0) st[b].gnorm = __double2float_ru(sqrt(s2) * (1.0 + 1e-7));
-    }
-    const int k = blockIdx.x * QFFT_K + (tid >> 2), part = tid & 3;
-    const int per = (W + 3) / 4;
-    const int j0 = part * per, j1 = min(W, j0 + per);
-    double re = 0.0, im = 0.0;
-#pragma unroll 8
-    for (int j = j0; j < j1; ++j) {
-        const double2 w = __ldg(tw64 + ((j * k) & (fftx::N - 1)));  // exp(+i theta): Q_k = sum q_j exp(-i theta)
-        re += qd[j] * w.x;
-        im -= qd[j] * w.y;
-    }
-    re += __shfl_xor_sync(FULL, re, 1); im += __shfl_xor_sync(FULL, im, 1);
-    re += __shfl_xor_sync(FULL, re, 2); im += __shfl_xor_sync(FULL, im, 2);
-    if (part == 0) Qc[(size_t)b * fftx::N + k] = make_float2((float)(re / fftx::N), (float)(-im / fftx::N));
-    double mx = re * re + im * im;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
-    if ((tid & 31) == 0) red[tid >> 5] = mx;
-    __syncthreads();
-    if (tid == 0) {
-        for (int i = 1; i < 4 * QFFT_K / 32; ++i) mx = fmax(mx, red[i]);
-        const float m = __double2float_ru(sqrt(mx) * (1.0 + 1e-7));
-        atomicMax(reinterpret_cast<unsigned int *>(&st[b].qmax), __float_as_uint(m));  // positive floats order as uints
-    }
-}
-
-constexpr int FFT_NB = 2048;      // bins of the in-launch threshold histogram
-constexpr int FFT_REFRESH = 4;    // pairs between two threshold refreshes of a CTA
-// seed launch (fft_scan_kernel<.., SEED = true>): histogram of per-thread minima of the upper bound
-// over one wave of row pairs.  Bins are logarithmic -- the upper 16 bits of the float (8 exponent +
-// 7 mantissa bits: 0.8 % wide), SEED_NB of them centred on Q2, i.e. 16 binades either side -- so no
-// range estimate is needed before the first window has been looked at.
-constexpr int SEED_NB = 4096;
-constexpr int SEED_STRIDE = SEED_NB + 32;   // uints per query: bins, then the launch's CTA ticket
-
-struct FftScanParams {
-    const float2 *Z;
-    const float *Y2;
-    const float *ynorm;
-    const float2 *tw;
-    const float2 *Qc;  // (nq, 4096)
-    int Tp, y2_stride, nq;
-    int nsegv, hop;
-    long long npairs, VR;
-    long long i0, i1;  // pair slots of this launch
-    long long perm;
-    double inv_np;
-    QState *st;
-    unsigned int *cand;
-    unsigned int cap;
-    float cf_u;        // CF * 2^-24: |c^_t - c_t| <= cf_u * Qmax * ynorm  (CF = 512, theory ~165)
-    // in-launch threshold tightening: per query a histogram (FFT_NB linear bins over [0, thr at
-    // launch)) of UPPER bounds UB = LB + 2 slack of the windows that passed; the bin edge below
-    // which k upper bounds lie is a valid, tighter threshold (NULL: thresholds stay fixed)
-    unsigned int *hist;
-    unsigned int k;
-    float widen2;      // (1 + 2 (W+8) u)^2 (1 + 1e-6): exact-sequence rounding, both directions
-    unsigned int *seed;  // (nq, SEED_STRIDE) seed histograms + ticket (seed launch only)
-    // embedded scan (pshadow_embed_fft.cuh); Identity: 8u, 1, 1
-    float slack_coef;    // coefficient of (Q2 + y2_scale ynorm^2) in the slack
-    float y2_scale;      // 1: the staged energies are window energies <= ynorm^2;  0: they carry their own
-                         // rounding allowance (stored scaled down), see ub_e2_coef
-    float g_coef;        // coefficient of ||g|| ynorm in the slack (rounding of the correlated vector g)
-    float ub_e2_coef;    // UB - LB grows by ub_e2_coef * (staged energy) per window
-    float thr_widen;     // thresholds read from the query state are widened by this factor
-};
-
-// One CTA per row pair: Z * conj(Q)/N -> inverse FFT -> (D_a[t], D_b[t]) for t = tid + 256 c.
-// Lower bound LB = Q2 + Y2 - 2 D^ - slack,
-//   slack = 2 cf_u Qmax ynorm + 8u (Q2 + ynorm^2)   (FFT error; Y2, Q2 roundings and the combination)
-// Staging: the pair's spectrum (32 KiB) and its two window-energy rows arrive by TMA bulk copies
-// issued one pair ahead -- the spectrum buffer is free as soon as it has been multiplied into
-// registers, the energy buffer as soon as the epilogue has read it -- so HBM latency hides
-// behind the transform of the current pair.  With a single query its spectrum stays in
-// registers (16 values per thread, a function of tid only).
-__device__ __forceinline__ long long fft_pair_of_slot(const FftScanParams &p, long long slot) {
-    const unsigned long long prod = (unsigned long long)slot * (unsigned long long)p.perm;
-    const unsigned long long qq = __double2ull_rz(__ull2double_rz(prod) * p.inv_np);
-    long long pair = (long long)(prod - qq * (unsigned long long)p.npairs);
-    if (pair < 0) pair += p.npairs;
-    else if (pair >= p.npairs) pair -= p.npairs;
-    return pair;
-}
-
-//
-// SEED = true (the seed launch of the seedless schedule): no window is appended.  Every thread
-// folds the upper bounds UB = LB + 2 slack of its 32 windows into their minimum and adds it to the
-// query's logarithmic seed histogram; the last CTA to finish finds the bin edge below which k
-// minima lie -- k distinct windows whose exact squared distance is <= edge -- and publishes
-// thr_fast = edge * widen2: the threshold the main launch over ALL pairs starts from (and
-// tightens further by itself).  This replaces two exact seed rounds and two selects.
-// EMB = true: the embedded scan's flavour (pshadow_embed_fft.cuh) -- per-query ||g|| term in the slack,
-// energy-proportional UB term, widened thresholds.  Compile-time, so the Identity instantiation
-// carries none of it (measured: the run-time version cost the Identity scan 9 %).
-template <bool SINGLEQ, bool SEED, bool EMB>
-__global__ void __launch_bounds__(fftx::THREADS, 2) fft_scan_kernel(const FftScanParams p) {
-    extern __shared__ __align__(128) unsigned char fsm[];
-    float2 *Zs = reinterpret_cast<float2 *>(fsm);
-    float *Y2s = reinterpret_cast<float *>(fsm + sizeof(float2) * fftx::N);
-    float2 *ex = reinterpret_cast<float2 *>(fsm + sizeof(float2) * fftx::N + sizeof(float) * 2 * p.y2_stride);
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(ex + fftx::EX2_FLOAT2);
-    __shared__ float s_thrq[QG_MAX], s_hscale[QG_MAX];
-    __shared__ unsigned int s_wsum[fftx::THREADS / 32], s_edge;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const uint32_t barZ = smem_u32(&bars[0]), barY = smem_u32(&bars[1]);
-    if (tid == 0) {
-        mbar_init(barZ, 1);
-        mbar_init(barY, 1);
-        mbar_fence_init();
-    }
-    if (tid < p.nq) {
-        const float t0 = EMB ? ld_volatile_f32(&p.st[tid].thr_fast) * p.thr_widen : ld_volatile_f32(&p.st[tid].thr_fast);
-        s_thrq[tid] = t0;
-        s_hscale[tid] = (!SEED && p.hist != nullptr && t0 > 0.0f && t0 < __int_as_float(0x7f800000)) ? (float)FFT_NB / t0 : 0.0f;
-    }
-    __syncthreads();
-
-    auto issue_z = [&](long long pair) {  // thread 0
-        mbar_expect_tx(barZ, (uint32_t)(sizeof(float2) * fftx::N));
-        bulk_g2s(smem_u32(Zs), p.Z + (size_t)pair * fftx::N, (uint32_t)(sizeof(float2) * fftx::N), barZ);
-    };
-    auto issue_y = [&](long long pair) {  // thread 0
-        const long long ra = 2 * pair, rb = (ra + 1 < p.VR) ? ra + 1 : ra;
-        const uint32_t bytes = (uint32_t)(sizeof(float) * p.y2_stride);
-        mbar_expect_tx(barY, 2 * bytes);
-        bulk_g2s(smem_u32(Y2s), p.Y2 + (size_t)ra * p.y2_stride, bytes, barY);
-        bulk_g2s(smem_u32(Y2s + p.y2_stride), p.Y2 + (size_t)rb * p.y2_stride, bytes, barY);
-    };
-
-    long long slot = p.i0 + blockIdx.x;
-    if (!SEED && slot >= p.i1) return;   // (a seed launch has one CTA per slot; all of them take a ticket)
-    long long pair = fft_pair_of_slot(p, slot);
-    if (tid == 0) { issue_z(pair); issue_y(pair); }
-
-    float2 qreg[16];
-    if (SINGLEQ) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) qreg[i] = __ldg(p.Qc + tid + 256 * i);
-    }
-    const fftx::TwSeeds seeds = fftx::load_seeds(p.tw, tid);
-    const float q2_0 = p.st[0].q2, qmax_0 = p.st[0].qmax, gn_0 = EMB ? p.st[0].gnorm : 0.0f;
-    uint32_t phZ = 0, phY = 0;
-    for (int iter = 0; slot < p.i1; slot += gridDim.x, ++iter) {
-        const long long nslot = slot + gridDim.x;
-        const long long npair = nslot < p.i1 ? fft_pair_of_slot(p, nslot) : -1;
-        const long long ra = 2 * pair, rb = ra + 1;   // virtual rows
-        const bool has_b = rb < p.VR;
-        const float yn = p.ynorm[pair];
-        mbar_wait(barZ, phZ); phZ ^= 1;
-        for (int b = 0; b < p.nq; ++b) {
-            float2 v[16];
-            if (SINGLEQ) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = fftx::cmul(Zs[tid + 256 * i], qreg[i]);
-            } else {
-                const float2 *Qb = p.Qc + (size_t)b * fftx::N;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = fftx::cmul(Zs[tid + 256 * i], __ldg(Qb + tid + 256 * i));
-            }
-            // behind the transform's only CTA barrier every thread has consumed the staged
-            // spectrum: the next pair's copy is issued there (last query of the group)
-            const bool last_q = b == p.nq - 1;
-            fftx::ifft4096_scan(v, ex, tid, seeds, [&]() {
-                if (last_q && tid == 0 && npair >= 0) issue_z(npair);
-            });
-            if (b == 0) { mbar_wait(barY, phY); phY ^= 1; }  // the pair's window energies have landed
-            const float q2 = SINGLEQ ? q2_0 : p.st[b].q2, qmax = SINGLEQ ? qmax_0 : p.st[b].qmax;
-            const float thr = s_thrq[b];
-            float slack;
-            if (EMB) {
-                const float gn = SINGLEQ ? gn_0 : p.st[b].gnorm;
-                slack = (2.0f * p.cf_u * qmax * yn + p.slack_coef * q2 + p.g_coef * gn * yn) * 1.0001f;
-            } else {
-                slack = (2.0f * p.cf_u * qmax * yn + 4.76837158203125e-7f * (q2 + yn * yn)) * 1.0001f;
-            }
-            const float base0 = q2 - slack;   // LB = (Y2 - 2 D^) + base0, kept iff LB <= thr
-            if (SEED) {
-                // min over the thread's windows of (Y2 - 2 D^); adding the constants afterwards is
-                // the same as taking the min of the UBs (fp addition is monotone)
-                float mn = __int_as_float(0x7f800000), e2m = 0.0f;   // the minimum (EMB: and the energy it was taken at)
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const int pos = tid + 256 * c;
-                    const float ea = Y2s[pos], eb = Y2s[fftx::N + pos];
-                    const float va = fmaf(-2.0f, v[c].x, ea), vb = fmaf(-2.0f, v[c].y, eb);
-                    if (EMB) {
-                        if (va < mn) { mn = va; e2m = ea; }
-                        if (has_b && vb < mn) { mn = vb; e2m = eb; }
-                    } else {
-                        mn = fminf(mn, va);
-                        if (has_b) mn = fminf(mn, vb);
-                    }
-                }
-                const float ub = fmaxf(EMB ? ((mn + base0) + 2.0f * slack) + p.ub_e2_coef * e2m
-                                           : (mn + base0) + 2.0f * slack, 0.0f);
-                const bool act = ub < __int_as_float(0x7f800000);   // false for +inf (no valid window) and NaN
-                int bin = (int)(__float_as_uint(ub) >> 16) - ((int)(__float_as_uint(q2) >> 16) - SEED_NB / 2);
-                bin = bin < 0 ? 0 : (bin > SEED_NB - 1 ? SEED_NB - 1 : bin);
-                const unsigned int am = __ballot_sync(FULL, act);
-                if (act) {
-                    const unsigned int peers = __match_any_sync(am, bin);
-                    if (lane == __ffs(peers) - 1)
-                        atomicAdd(&p.seed[(size_t)b * SEED_STRIDE + bin], (unsigned int)__popc(peers));
-                }
-                __syncthreads();  // ex (and, after the last query, the energy rows) may be overwritten
-                continue;
-            }
-            unsigned int mask = 0;
-            // v[c] belongs to window t = (tid>>4) + 16 (tid&15) + 256 c; the energy rows are stored
-            // in that order (position tid + 256 c) and padded with +inf beyond T': no range checks
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                const int pos = tid + 256 * c;
-                const float va = fmaf(-2.0f, v[c].x, Y2s[pos]) + base0;
-                if (!(va > thr)) mask |= 1u << c;
-                const float vb = fmaf(-2.0f, v[c].y, Y2s[fftx::N + pos]) + base0;
-                if (!(vb > thr)) mask |= 1u << (16 + c);
-            }
-            if (!has_b) mask &= 0xffffu;
-            if (__any_sync(FULL, mask != 0)) {
-                const int cnt = __popc(mask);
-                int incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int u = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += u;
-                }
-                const int total = __shfl_sync(FULL, incl, 31);
-                unsigned int basepos = 0;
-                if (lane == 31) basepos = atomicAdd(&p.st[b].ccount, (unsigned int)total);
-                basepos = __shfl_sync(FULL, basepos, 31);
-                unsigned int pos = basepos + (unsigned int)(incl - cnt);
-                unsigned int *dst = p.cand + (size_t)b * p.cap;
-                // flat window index of local window 0 of each virtual row: row * T' + piece * hop
-                const unsigned int fa = (unsigned int)((unsigned long long)(ra / p.nsegv) * (unsigned long long)p.Tp
-                                                       + (unsigned long long)(ra % p.nsegv) * (unsigned long long)p.hop);
-                const unsigned int fb = (unsigned int)((unsigned long long)(rb / p.nsegv) * (unsigned long long)p.Tp
-                                                       + (unsigned long long)(rb % p.nsegv) * (unsigned long long)p.hop);
-                const float hs = s_hscale[b];
-                unsigned int *hq = p.hist + (size_t)b * FFT_NB;
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const unsigned int t = (unsigned int)((tid >> 4) + 16 * (tid & 15) + 256 * c);
-                    if (mask & (1u << c)) {
-                        if (pos < p.cap) dst[pos] = fa + t;
-                        ++pos;
-                        if (hs > 0.0f) {  // upper bound of the window's exact squared distance
-                            const float ea = Y2s[tid + 256 * c];
-                            float ub = (fmaf(-2.0f, v[c].x, ea) + base0) + 2.0f * slack;
-                            if (EMB) ub += p.ub_e2_coef * ea;
-                            const float fbin = ub * hs;
-                            if (fbin < (float)FFT_NB) atomicAdd(&hq[fbin > 0.0f ? (int)fbin : 0], 1u);
-                        }
-                    }
-                    if (mask & (1u << (16 + c))) {
-                        if (pos < p.cap) dst[pos] = fb + t;
-                        ++pos;
-                        if (hs > 0.0f) {
-                            const float eb = Y2s[fftx::N + tid + 256 * c];
-                            float ub = (fmaf(-2.0f, v[c].y, eb) + base0) + 2.0f * slack;
-                            if (EMB) ub += p.ub_e2_coef * eb;
-                            const float fbin = ub * hs;
-                            if (fbin < (float)FFT_NB) atomicAdd(&hq[fbin > 0.0f ? (int)fbin : 0], 1u);
-                        }
-                    }
-                }
-            }
-            __syncthreads();  // ex (and, after the last query, the energy rows) may be overwritten
-        }
-        if (tid == 0 && npair >= 0) issue_y(npair);
-        // threshold refresh: k windows with UB <= edge exist  =>  the k-th exact distance of the whole
-        // ensemble is <= edge (1+gamma)  =>  filtering with edge * widen2 loses nothing
-        if (!SEED && p.hist != nullptr && (iter < 2 || (iter % FFT_REFRESH) == FFT_REFRESH - 1) && npair >= 0) {
-            for (int b = 0; b < p.nq; ++b) {
-                const float hs = s_hscale[b];
-                if (!(hs > 0.0f)) continue;  // CTA-uniform
-                const uint4 *h4 = reinterpret_cast<const uint4 *>(p.hist + (size_t)b * FFT_NB) + tid * (FFT_NB / fftx::THREADS / 4);
-                unsigned int loc[FFT_NB / fftx::THREADS];
-#pragma unroll
-                for (int i = 0; i < FFT_NB / fftx::THREADS / 4; ++i) {
-                    const uint4 x = __ldcg(h4 + i);
-                    loc[4 * i] = x.x; loc[4 * i + 1] = x.y; loc[4 * i + 2] = x.z; loc[4 * i + 3] = x.w;
-                }
-                unsigned int sum = 0;
-#pragma unroll
-                for (int i = 0; i < FFT_NB / fftx::THREADS; ++i) sum += loc[i];
-                unsigned int incl = sum;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned int u = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += u;
-                }
-                if (lane == 31) s_wsum[tid >> 5] = incl;
-                if (tid == 0) s_edge = 0xffffffffu;
-                __syncthreads();
-                unsigned int cum = incl - sum;
-                for (int w = 0; w < (tid >> 5); ++w) cum += s_wsum[w];
-                if (cum < p.k && p.k <= cum + sum) {  // exactly one thread
-#pragma unroll
-                    for (int i = 0; i < FFT_NB / fftx::THREADS; ++i) {
-                        if (cum < p.k && p.k <= cum + loc[i]) s_edge = (unsigned int)(tid * (FFT_NB / fftx::THREADS) + i + 1);
-                        cum += loc[i];
-                    }
-                }
-                __syncthreads();
-                if (tid == 0 && s_edge != 0xffffffffu) {
-                    const float tn = ((float)s_edge / hs) * p.widen2;
-                    if (tn < s_thrq[b]) s_thrq[b] = tn;
-                }
-                __syncthreads();
-            }
-        }
-        pair = npair;
-    }
-    if (SEED) {
-        // last CTA done: every other CTA's histogram increments are visible behind its fence + ticket
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) s_edge = atomicAdd(&p.seed[SEED_NB], 1u);
-        __syncthreads();
-        if (s_edge != gridDim.x - 1) return;
-        __threadfence();
-        constexpr int PER = SEED_NB / fftx::THREADS;
-        for (int b = 0; b < p.nq; ++b) {
-            __syncthreads();
-            const uint4 *h4 = reinterpret_cast<const uint4 *>(p.seed + (size_t)b * SEED_STRIDE) + tid * (PER / 4);
-            unsigned int loc[PER];
-#pragma unroll
-            for (int i = 0; i < PER / 4; ++i) {
-                const uint4 x = __ldcg(h4 + i);
-                loc[4 * i] = x.x; loc[4 * i + 1] = x.y; loc[4 * i + 2] = x.z; loc[4 * i + 3] = x.w;
-            }
-            unsigned int sum = 0;
-#pragma unroll
-            for (int i = 0; i < PER; ++i) sum += loc[i];
-            unsigned int incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned int u = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += u;
-            }
-            if (lane == 31) s_wsum[tid >> 5] = incl;
-            __syncthreads();
-            unsigned int cum = incl - sum;
-            for (int w = 0; w < (tid >> 5); ++w) cum += s_wsum[w];
-            if (cum < p.k && p.k <= cum + sum) {  // at most one thread; none: fewer than k minima -> thr stays +inf
-                int bin = 0;
-#pragma unroll
-                for (int i = 0; i < PER; ++i) {
-                    if (cum < p.k && p.k <= cum + loc[i]) bin = tid * PER + i;
-                    cum += loc[i];
-                }
-                // upper edge of the bin (exclusive); the clamped top bin has no finite edge
-                const int eb = (int)(__float_as_uint(p.st[b].q2) >> 16) - SEED_NB / 2 + bin + 1;
-                float thr = __int_as_float(0x7f800000);
-                if (bin < SEED_NB - 1 && eb > 0 && eb < 0x7f80) thr = __uint_as_float((unsigned int)eb << 16) * p.widen2;
-                p.st[b].thr_fast = thr;
-            }
-        }
-    }
-}
+#include "pshadow_fftscan.cuh"
 
 #include "pshadow_embed_fft.cuh"
 
@@ -1020,12 +519,6 @@ constexpr int RR_THREADS = RR_WARPS * 32;
 constexpr int RR_JC = 256;          // reduction steps staged per pass
 constexpr int RR_WP = RR_JC + 1;    // tile row stride (floats)
 
-__device__ __forceinline__ void cp_async_4(uint32_t dst, const float *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.wait_all;" ::: "memory");
-}
 
 __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(const float *__restrict__ ds, long long row_stride,
                                                              unsigned int Tp, int W,
@@ -1229,7 +722,8 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(QState *st_all, uns
                                                               int *out_idx, unsigned int *fft_hist) {
     __shared__ unsigned int hist[SEL_BINS];
     if (fft_hist != nullptr)  // fresh in-launch threshold histogram for the next FFT round
-        for (int i = threadIdx.x; i < FFT_NB; i += SEL_THREADS) fft_hist[(size_t)blockIdx.x * FFT_NB + i] = 0u;
+        for (int i = threadIdx.x; i < HB + HC; i += SEL_THREADS) fft_hist[(size_t)blockIdx.x * HSTRIDE + i] = 0u;
+    if (fft_hist != nullptr && threadIdx.x == 0) fft_hist[(size_t)blockIdx.x * HSTRIDE + H_SLOT] = 0u;   // the next launch's pair slots
     __shared__ unsigned long long list[SEL_LIST];
     __shared__ unsigned long long s_prefix;
     __shared__ unsigned int s_need, s_done, s_out, s_min, s_max, s_bin, s_below, s_nlist, s_fast;
@@ -1587,11 +1081,6 @@ struct XchgParams {
     unsigned long long timeout_ns;
 };
 
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 __device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -1841,7 +1330,7 @@ struct Plan {
     unsigned int cap;
     long long n0;      // rows of the seeding chunk
     int growth;
-    size_t off_state, off_keys, off_cand, off_qspec, off_hist, off_seed, total;
+    size_t off_state, off_keys, off_cand, off_qspec, off_hist, off_qmaxp, total;
 };
 
 constexpr int SEED_FACTOR = 16;  // seeding chunk holds ~16 k windows
@@ -1871,8 +1360,8 @@ bool make_plan(long long R, long long T, int B, int W, int H, long long k, Plan 
     pl.off_cand = pl.off_keys + (size_t)B * 2 * (size_t)pl.cap * sizeof(unsigned long long);
     pl.off_qspec = pl.off_cand + align_up((size_t)B * (size_t)pl.cap * sizeof(unsigned int), 256);
     pl.off_hist = pl.off_qspec + (size_t)B * fftx::N * sizeof(float2);  // query spectra (fft flavour)
-    pl.off_seed = pl.off_hist + (size_t)B * FFT_NB * sizeof(unsigned int);  // in-launch threshold histograms
-    pl.total = pl.off_seed + (size_t)B * SEED_STRIDE * sizeof(unsigned int);  // seed histograms + tickets
+    pl.off_qmaxp = pl.off_hist + (size_t)B * HSTRIDE * sizeof(unsigned int);  // threshold histograms + published thresholds
+    pl.total = pl.off_qmaxp + align_up((size_t)B * QMAXP * sizeof(float), 256);  // partial maxima of the query spectra
     return true;
 }
 
@@ -1995,20 +1484,22 @@ size_t psh_fft_aux_bytes(int64_t R, int64_t T, int W, int H) {
     return a.total;
 }
 
-int psh_fft_prepare(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride, int W, int H,
-                    void *d_aux, size_t aux_bytes, void *stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+// spectra + pair statistics, then the energy table: window energies (Identity) or, with a run table, the
+// embedded energies E2 = sum_n e_n(t)^2
+static int fft_prepare_impl(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride, int W, int H,
+                            void *d_aux, size_t aux_bytes, const EmbRun *d_runs, int nruns, cudaStream_t stream) {
     if (!d_dataset || !d_aux || row_stride < T) return PSH_E_ARG;
     FftAux a;
     if (!fft_aux_layout(R, T, W, H, static_cast<unsigned char *>(d_aux), a)) return W > fftx::N / 2 ? PSH_E_UNSUPPORTED : PSH_E_ARG;
     if (aux_bytes < a.total || (reinterpret_cast<uintptr_t>(d_aux) & 255u)) return PSH_E_WORKSPACE;
+    const size_t smem = (size_t)nruns * sizeof(EmbRun);
+    if (smem > 12 * 1024) return PSH_E_UNSUPPORTED;   // next to the 32 KiB fp64 prefix array
     // twiddle tables: exp(+2 pi i m / 4096) in fp64, rounded once for the fp32 copy
     static std::vector<double2> h64;
     static std::vector<float2> h32;
     if (h64.empty()) {
         h64.resize(fftx::N); h32.resize(fftx::N);
         for (int m = 0; m < fftx::N; ++m) {
-            // exact symmetries from the first octant keep the table accurate to the last bit
             const double ang = 6.283185307179586476925286766559 * (double)m / (double)fftx::N;
             h64[m].x = cos(ang); h64[m].y = sin(ang);
             h32[m].x = (float)h64[m].x; h32[m].y = (float)h64[m].y;
@@ -2016,19 +1507,35 @@ int psh_fft_prepare(const float *d_dataset, int64_t R, int64_t T, int64_t row_st
     }
     PSH_CUDA(cudaMemcpyAsync(a.tw64, h64.data(), sizeof(double2) * fftx::N, cudaMemcpyHostToDevice, stream));
     PSH_CUDA(cudaMemcpyAsync(a.tw32, h32.data(), sizeof(float2) * fftx::N, cudaMemcpyHostToDevice, stream));
-    fft_prep_spectra_kernel<<<(unsigned int)a.npairs, fftx::THREADS, 0, stream>>>(d_dataset, R, (int)T, row_stride, a);
+    fft_prep_spectra_kernel<<<(unsigned int)a.npairs, fftx::THREADS, 0, stream>>>(d_dataset, (int)T, row_stride, a);
     PSH_LAUNCHED();
-    fft_prep_y2_kernel<<<(unsigned int)a.VR, fftx::THREADS, 0, stream>>>(d_dataset, (int)T, row_stride, W,
-                                                                     (int)(T - W - H + 1), a);
+    if (d_runs != nullptr)
+        fft_prep_energy_kernel<true><<<(unsigned int)a.npairs, fftx::THREADS, smem, stream>>>(
+            d_dataset, (int)T, row_stride, W, (int)(T - W - H + 1), a, d_runs, nruns);
+    else
+        fft_prep_energy_kernel<false><<<(unsigned int)a.npairs, fftx::THREADS, 0, stream>>>(
+            d_dataset, (int)T, row_stride, W, (int)(T - W - H + 1), a, nullptr, 0);
     PSH_LAUNCHED();
     return PSH_OK;
+}
+
+int psh_fft_prepare(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride, int W, int H,
+                    void *d_aux, size_t aux_bytes, void *stream_) {
+    return fft_prepare_impl(d_dataset, R, T, row_stride, W, H, d_aux, aux_bytes, nullptr, 0, (cudaStream_t)stream_);
 }
 
 int psh_debug_fft4096(const void *d_in, void *d_out, int n, int dir, const void *d_aux, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!d_in || !d_out || !d_aux || n <= 0) return PSH_E_ARG;
-    fft_debug_kernel<<<n, fftx::THREADS, 0, stream>>>(static_cast<const float2 *>(d_in), static_cast<float2 *>(d_out),
-                                                      static_cast<const float2 *>(d_aux), dir);
+    if (dir >= 3) {
+        const size_t smem_dbg = sizeof(float2) * (fx2::EX1_FLOAT2 + fx2::EX2_FLOAT2);
+        PSH_CUDA(cudaFuncSetAttribute(fft_debug_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dbg));
+        fft_debug_scan_kernel<<<n, fx2::THREADS, smem_dbg, stream>>>(
+            static_cast<const float2 *>(d_in), static_cast<float2 *>(d_out), static_cast<const float2 *>(d_aux));
+    } else {
+        fft_debug_kernel<<<n, fftx::THREADS, 0, stream>>>(static_cast<const float2 *>(d_in), static_cast<float2 *>(d_out),
+                                                          static_cast<const float2 *>(d_aux), dir);
+    }
     PSH_LAUNCHED();
     return PSH_OK;
 }
@@ -2044,8 +1551,6 @@ static int launch_finalize(const Plan &pl, QState *st, unsigned long long *keys,
     unsigned int npow2 = 1; while (npow2 < (unsigned int)k) npow2 <<= 1;
     int use_smem = npow2 <= SORT_SMEM_MAX ? 1 : 0;
     size_t fsmem = use_smem ? (size_t)npow2 * sizeof(unsigned long long) : 0;
-    if (fsmem > 48 * 1024)
-        PSH_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
     {
         ProfScope ps(stream, 1);
         finalize_kernel<<<nq, SEL_THREADS, fsmem, stream>>>(st, keys, pl.cap, (unsigned int)k, npow2, use_smem,
@@ -2055,28 +1560,118 @@ static int launch_finalize(const Plan &pl, QState *st, unsigned long long *keys,
     return PSH_OK;
 }
 
+// ---- one-time per-device setup: dynamic shared-memory limits, resident CTAs of the fft scan ----
+constexpr size_t SMEM_BIG = 200 * 1024;          // budget of the kernels whose shared memory grows with W / k
+constexpr size_t SMEM_FFT = sizeof(__half2) * 2 * fx2::N + sizeof(float2) * (fx2::EX1_FLOAT2 + fx2::EX2_FLOAT2) + sizeof(float4) + 16;
+typedef void (*FftScanFn)(const FftScanParams);
+struct FftVariant { FftScanFn fn; int ctas_per_sm; };
+constexpr int FFT_VARIANTS = 4;                  // [query spectrum in registers][emb]
+struct DevSetup { bool done = false; FftVariant fft[FFT_VARIANTS]; };
+static DevSetup g_dev[64];
+
+static FftScanFn fft_variant_fn(int sq, int em) {
+    if (sq && em) return fft_scan_kernel<true, true>;
+    if (sq) return fft_scan_kernel<true, false>;
+    if (em) return fft_scan_kernel<false, true>;
+    return fft_scan_kernel<false, false>;
+}
+
+#define big_smem(kernel, bytes) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
+
+static int device_setup(DevSetup **out) {
+    int dev = 0;
+    PSH_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return PSH_E_ARG;
+    DevSetup &d = g_dev[dev];
+    *out = &d;
+    if (d.done) return PSH_OK;
+    PSH_CUDA(big_smem(scan_kernel<true>, SMEM_BIG));
+    PSH_CUDA(big_smem(scan_kernel<false>, SMEM_BIG));
+    PSH_CUDA(big_smem(emb_scan_kernel<1>, SMEM_BIG));
+    PSH_CUDA(big_smem(emb_scan_kernel<EMB_QG>, SMEM_BIG));
+    PSH_CUDA(big_smem(rerank_kernel, SMEM_BIG));
+    PSH_CUDA(big_smem(emb_rerank_kernel, SMEM_BIG));
+    PSH_CUDA(big_smem(finalize_kernel, SMEM_BIG));
+    PSH_CUDA(big_smem(merge_kernel, SMEM_BIG));
+    PSH_CUDA(big_smem(xchg_merge_kernel, SMEM_BIG));
+    PSH_CUDA(big_smem(xchg_ll_kernel, SMEM_BIG));
+    for (int i = 0; i < FFT_VARIANTS; ++i) {
+        FftScanFn fn = fft_variant_fn((i >> 1) & 1, i & 1);
+        PSH_CUDA(big_smem(fn, SMEM_FFT));
+        int nb = 0;
+        PSH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, fx2::THREADS, SMEM_FFT));
+        d.fft[i].fn = fn;
+        d.fft[i].ctas_per_sm = nb > 0 ? nb : 1;
+    }
+    d.done = true;
+    return PSH_OK;
+}
+
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return (e != nullptr && e[0] != 0) ? atoi(e) : dflt;
+}
+
+// shared memory of the direct-evaluation kernels for a group of nq queries
+struct DirectSmem { int epl, pfx_floats, buf_floats, wpad; size_t exact, filter; };
+static DirectSmem direct_smem(int W, int qlen, int nq) {
+    DirectSmem m;
+    const int need = SEG + W - 1;
+    int epl4 = ((need + 31) / 32 + 3) / 4;
+    if ((epl4 & 1) == 0) ++epl4;  // odd multiple of 4 floats per lane: conflict-free LDS.128/STS.128
+    m.epl = 4 * epl4;
+    m.pfx_floats = 4 + 32 * m.epl + 4;
+    m.buf_floats = (int)align_up((size_t)need + RING + 4, 4);
+    if (m.buf_floats < 32 * m.epl + 4) m.buf_floats = 32 * m.epl + 4;
+    m.wpad = (int)align_up((size_t)qlen + 4, 4);
+    m.exact = ((size_t)nq * m.wpad + (size_t)SCAN_WARPS * 2 * m.buf_floats) * sizeof(float)
+              + (size_t)SCAN_WARPS * 2 * sizeof(unsigned long long);
+    m.filter = m.exact + (size_t)SCAN_WARPS * m.pfx_floats * sizeof(float);
+    return m;
+}
+static size_t emb_smem(int W, int d, int nruns, int nq) {
+    const DirectSmem m = direct_smem(W, d, nq);
+    const int ps_n = (int)align_up((size_t)SEG + W + 1, 2);
+    return (size_t)nq * m.wpad * sizeof(float) + (size_t)nruns * sizeof(EmbRun) + (size_t)SCAN_WARPS * ps_n * sizeof(float2)
+           + (size_t)SCAN_WARPS * 2 * m.buf_floats * sizeof(float) + (size_t)SCAN_WARPS * 2 * sizeof(unsigned long long);
+}
+// queries per scan group: as many (<= QG_MAX) as the shared memory of the kernels this call may launch
+// holds; 0: not even one query fits (context too long for the staging buffers)
+static int query_group_size(int W, int mode, bool has_aux, const EmbParams *emb) {
+    for (int nq = QG_MAX; nq >= 1; --nq) {
+        if (emb) {
+            if (emb_smem(W, emb->d, emb->nruns, nq) <= SMEM_BIG) return nq;
+            continue;
+        }
+        const DirectSmem m = direct_smem(W, W, nq);
+        const bool filter_used = mode == PSH_MODE_FILTER || (mode == PSH_MODE_FFT && !has_aux);
+        if ((filter_used ? m.filter : m.exact) <= SMEM_BIG) return nq;
+    }
+    return 0;
+}
+
 static int run_scan_group(const float *d_dataset, long long R, long long T, long long row_stride,
                           const float *d_q, int nq, int W, int H, long long k, int row_offset,
                           const Plan &pl, QState *st, unsigned long long *keys, unsigned int *cand, float2 *qspec,
-                          unsigned int *fhist, unsigned int *shist, const FftAux *aux, int mode, bool safe,
+                          unsigned int *fhist, float *qmaxp, const FftAux *aux, int mode, bool safe,
                           float *d_out_dist, int *d_out_idx, cudaStream_t stream, const EmbParams *emb = nullptr) {
     (void)H;
+    DevSetup *dv = nullptr;
+    { int rc_ = device_setup(&dv); if (rc_ != PSH_OK) return rc_; }
     const bool use_fft = (mode == PSH_MODE_FFT) && !safe && aux != nullptr;
-    // embedded scan: d_q holds the EMBEDDED queries (nq, d); ||ex|| in torch's order comes from the same kernel
-    qprep_kernel<<<(nq + 3) / 4, 128, 0, stream>>>(d_q, emb ? emb->d : W, nq, st,
-                                                   use_fft ? reinterpret_cast<uint4 *>(fhist) : nullptr, FFT_NB / 4,
-                                                   use_fft ? reinterpret_cast<uint4 *>(shist) : nullptr, SEED_STRIDE / 4);
-    PSH_LAUNCHED();
-
     const bool filter = (mode == PSH_MODE_FILTER || (mode == PSH_MODE_FFT && !use_fft)) && !safe;
     if (use_fft && emb && emb->g == nullptr) return PSH_E_ARG;
+    const int qlen = emb ? emb->d : W;   // embedded scan: d_q holds the EMBEDDED queries (nq, d)
     if (use_fft) {
-        // spectrum of the vector the trajectories are correlated with: the context itself, or
-        // g = K^T ex for an embedded scan
+        // query state + spectrum of the vector the trajectories are correlated with (the context itself,
+        // or g = K^T ex for an embedded scan) + a clean threshold histogram: ONE launch
         qfft_kernel<<<dim3(fftx::N / QFFT_K, nq), 4 * QFFT_K, (size_t)W * sizeof(double), stream>>>(
-            emb ? emb->g : d_q, W, aux->tw64, qspec, st);
-        PSH_LAUNCHED();
+            d_q, qlen, emb ? emb->g : d_q, W, aux->tw64, qspec, st, fhist, qmaxp);
+    } else {
+        qprep_kernel<<<(nq + 3) / 4, 128, 0, stream>>>(d_q, qlen, nq, st);
     }
+    PSH_LAUNCHED();
+
     ScanParams p;
     p.ds = d_dataset; p.row_stride = row_stride; p.T = (int)T; p.Tp = (int)pl.Tp; p.W = W;
     // tasks per row; in the fft flavour per VIRTUAL row (a piece of `span` windows of a long trajectory)
@@ -2088,35 +1683,22 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
     p.R = R; p.perm = perm_stride(R);
     p.queries = d_q; p.nq = nq; p.st = st; p.keys = keys; p.cand = cand; p.cap = pl.cap;
     p.bulk_ok = ((reinterpret_cast<uintptr_t>(d_dataset) & 15u) == 0 && (row_stride & 3) == 0) ? 1 : 0;
-    const int need = SEG + W - 1;
-    int epl4 = ((need + 31) / 32 + 3) / 4;
-    if ((epl4 & 1) == 0) ++epl4;  // odd multiple of 4 floats per lane: conflict-free LDS.128/STS.128
-    p.epl = 4 * epl4;
-    p.pfx_floats = 4 + 32 * p.epl + 4;
+    const DirectSmem dm = direct_smem(W, qlen, nq);
+    p.epl = dm.epl; p.pfx_floats = dm.pfx_floats; p.buf_floats = dm.buf_floats; p.wpad = dm.wpad;
     p.cw = (float)(W + 256) * 5.9604644775390625e-8f;
-    p.buf_floats = (int)align_up((size_t)need + RING + 4, 4);
-    if (p.buf_floats < 32 * p.epl + 4) p.buf_floats = 32 * p.epl + 4;
-    p.wpad = (int)align_up((size_t)(emb ? emb->d : W) + 4, 4);
     EmbParams ep;
     size_t smem_emb = 0;
     if (emb) {
         ep = *emb;
         ep.ps_n = (int)align_up((size_t)SEG + W + 1, 2);
-        smem_emb = (size_t)nq * p.wpad * sizeof(float) + (size_t)ep.nruns * sizeof(EmbRun)
-                   + (size_t)SCAN_WARPS * ep.ps_n * sizeof(float2)
-                   + (size_t)SCAN_WARPS * 2 * p.buf_floats * sizeof(float) + (size_t)SCAN_WARPS * 2 * sizeof(unsigned long long);
-        if (smem_emb > 200 * 1024) return PSH_E_UNSUPPORTED;
-        PSH_CUDA(cudaFuncSetAttribute(emb_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_emb));
-        PSH_CUDA(cudaFuncSetAttribute(emb_scan_kernel<EMB_QG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_emb));
+        smem_emb = emb_smem(W, emb->d, emb->nruns, nq);
+        if (smem_emb > SMEM_BIG) return PSH_E_UNSUPPORTED;
     }
-    const size_t smem_exact = ((size_t)nq * p.wpad + (size_t)SCAN_WARPS * 2 * p.buf_floats) * sizeof(float)
-                              + (size_t)SCAN_WARPS * 2 * sizeof(unsigned long long);
-    const size_t smem_filter = smem_exact + (size_t)SCAN_WARPS * p.pfx_floats * sizeof(float);
-    if (smem_filter > 200 * 1024) return PSH_E_UNSUPPORTED;
-    PSH_CUDA(cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_exact));
-    PSH_CUDA(cudaFuncSetAttribute(scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_filter));
+    const size_t smem_exact = dm.exact, smem_filter = dm.filter;
+    // (scan_entry sized the query group for the kernels this call can launch)
+    if (!emb && (filter ? smem_filter : smem_exact) > SMEM_BIG) return PSH_E_UNSUPPORTED;
     const size_t smem_rr = ((size_t)((W + 3) & ~3) + (size_t)RR_WARPS * 32 * RR_WP) * sizeof(float);
-    PSH_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rr));
+    if (smem_rr > SMEM_BIG) return PSH_E_UNSUPPORTED;
     auto ctas_per_sm = [](size_t smem, int lim) {
         int c = (int)((224 * 1024) / (smem + 1024));
         return c > lim ? lim : (c < 1 ? 1 : c);
@@ -2133,35 +1715,42 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
     p.inv_np = 1.0 / (double)p.npairs;
     if (use_fft) p.perm = perm_stride(p.npairs);
     FftScanParams fp;
+    FftVariant fv = {nullptr, 1};
     if (use_fft) {
-        fp.Z = aux->Z; fp.Y2 = aux->Y2; fp.ynorm = aux->ynorm; fp.tw = aux->tw32; fp.Qc = qspec;
-        fp.Tp = (int)pl.Tp; fp.y2_stride = aux->y2_stride; fp.nq = nq;
-        fp.npairs = p.npairs; fp.VR = aux->VR; fp.nsegv = aux->nsegv; fp.hop = aux->hop;
+        fp.Z = aux->Z; fp.Y2 = aux->Y2; fp.pinfo = aux->pinfo; fp.tw = aux->tw32; fp.Qc = qspec; fp.qmaxp = qmaxp;
+        fp.Tp = (int)pl.Tp; fp.nq = nq;
+        fp.npairs = (int)p.npairs; fp.VR = aux->VR; fp.nsegv = aux->nsegv; fp.hop = aux->hop;
         fp.perm = p.perm; fp.inv_np = p.inv_np;
         fp.st = st; fp.cand = cand; fp.cap = pl.cap;
         fp.cf_u = 512.0f * 5.9604644775390625e-8f;
         fp.hist = fhist; fp.k = (unsigned int)k;
+        fp.seed = 0; fp.seed_need = 1;
+        fp.dbg = nullptr;
+        { const char *e_ = getenv("PSH_FFT_DBG"); if (e_ != nullptr && e_[0] != 0) fp.dbg = reinterpret_cast<unsigned long long *>(strtoull(e_, nullptr, 0)); }
+        fp.refresh_mask = (unsigned int)env_int("PSH_FFT_REFRESH", 7);
         {
-            const double w1 = 1.0 + 2.0 * (double)((emb ? emb->d : W) + 8) * 5.9604644775390625e-8;
+            const double w1 = 1.0 + 2.0 * (double)(qlen + 8) * 5.9604644775390625e-8;
             const double we = emb ? 1.0 + 1.0 / 512.0 : 1.0;   // the exact embedded evaluation vs the true S
             fp.widen2 = (float)(w1 * w1 * we * we * (1.0 + 1e-6));
             fp.thr_widen = (float)we;
-            // Identity: 8u (Q2 + ynorm^2) covers the roundings of Q2, Y2 and of the combination.
+            // Identity: 12u (Q2 + ynorm^2) covers the roundings of Q2, Y2 and of the combination (in the kernel).
             // Embedded: |2 D| <= Q2 + E2_t (Cauchy-Schwarz in embedded space), so every rounding is
-            // <= a few u (Q2 + E2_t): 16u Q2 in the slack, 16u E2_t taken out of the stored energies
-            // (fft_prep_e2_kernel) and given back twice in UB; 2u ||g|| ynorm for the rounding of g
-            fp.slack_coef = (emb ? 16.0f : 8.0f) * 5.9604644775390625e-8f;
-            fp.y2_scale = emb ? 0.0f : 1.0f;
+            // <= a few u (Q2 + E2_t): 20u Q2 in the slack, 16u E2_t taken out of the stored energies
+            // (fft_prep_energy_kernel<true>) and given back twice in UB; 2u ||g|| ynorm for the rounding of g
+            fp.slack_coef = (emb ? 20.0f : 12.0f) * 5.9604644775390625e-8f;
             fp.g_coef = emb ? 2.0f * 5.9604644775390625e-8f : 0.0f;
-            fp.ub_e2_coef = emb ? 2.0f * 16.0f * 5.9604644775390625e-8f * 1.001f : 0.0f;
+            // UB - LB: the fp16 floor of the staged energies (2^-10) + the embedded scan's 2 x 16u
+            fp.ub_y_coef = 9.765625e-4f * 1.01f + (emb ? 2.0f * 16.0f * 5.9604644775390625e-8f * 1.001f : 0.0f);
         }
+        // one query: its spectrum in registers (16 per thread) or streamed from L1/L2 like a group's
+        const int qreg = nq == 1 && env_int("PSH_FFT_QREG", 1) != 0;
+        fv = dv->fft[(qreg << 1) | (emb != nullptr ? 1 : 0)];
     }
     // exact re-rank of the fft / fma filter's survivors (embedded scans: emb_rerank_kernel)
     const size_t smem_er = emb ? (size_t)((emb->d + 3) & ~3) * sizeof(float) * (1 + ERR_WARPS) + (size_t)emb->nruns * sizeof(EmbRun)
                                      + (size_t)ERR_WARPS * (W + 2) * sizeof(float2)
                                : 0;
-    if (emb && smem_er > 48 * 1024)
-        PSH_CUDA(cudaFuncSetAttribute(emb_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_er));
+    if (smem_er > SMEM_BIG) return PSH_E_UNSUPPORTED;
     auto launch_rerank = [&]() -> int {
         ProfScope ps(stream, 1);
         if (emb) {
@@ -2180,62 +1769,36 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return (int)cudaGetLastError();
     };
-    const size_t smem_fft = use_fft ? sizeof(float2) * fftx::N + sizeof(float) * 2 * (size_t)aux->y2_stride
-                                          + sizeof(float2) * fftx::EX2_FLOAT2 + 16
-                                    : 0;
-    if (use_fft) {
-        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
-        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
-        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
-        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
-        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
-        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
-        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
-        PSH_CUDA(cudaFuncSetAttribute(fft_scan_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
-    }
-    // one launcher for the 8 instantiations (single query / seed launch / embedded flavour)
-    auto launch_fft = [&](bool seed, unsigned int grid) {
-        const bool sq = nq == 1, em = emb != nullptr;
-#define PSH_FFT_CASE(SQ, SD, EM) \
-        if (sq == SQ && seed == SD && em == EM) fft_scan_kernel<SQ, SD, EM><<<grid, fftx::THREADS, smem_fft, stream>>>(fp);
-        PSH_FFT_CASE(true, false, false) PSH_FFT_CASE(false, false, false) PSH_FFT_CASE(true, true, false)
-        PSH_FFT_CASE(false, true, false) PSH_FFT_CASE(true, false, true) PSH_FFT_CASE(false, false, true)
-        PSH_FFT_CASE(true, true, true) PSH_FFT_CASE(false, true, true)
-#undef PSH_FFT_CASE
+    auto launch_fft = [&](unsigned int grid) {
+        ProfScope ps(stream, 0);
+        fv.fn<<<grid, fx2::THREADS, SMEM_FFT, stream>>>(fp);
     };
+    const long long fft_grid_max = (long long)sm_count() * fv.ctas_per_sm;
     const bool fuse_final = k <= SEL_LIST;                  // last select also sorts and decodes
 
-    // ---- seedless schedule (large ensembles): seed launch -> ONE launch over all pairs -> exact
-    // re-rank of the survivors -> select.  The seed launch turns one wave of row pairs into a
-    // valid starting threshold (see fft_scan_kernel<.., SEED>), so no exact seed round, no
-    // intermediate select and no exact threshold exist before the final select: the re-rank keeps
-    // every survivor (s_thr = +inf, tau = ~0 from qprep) and the select picks the k best keys.
+    // ---- seedless schedule: ONE launch over all pairs that seeds its own threshold from every CTA's
+    // first pair (fft_scan_kernel, p.seed) -> exact re-rank of the survivors -> select.  No exact seed
+    // round, no intermediate select and no exact threshold exist before the final select: the re-rank
+    // keeps every survivor (s_thr = +inf, tau = ~0 from the query preparation) and the select picks the
+    // k best keys.  4 launches per query.
     if (use_fft && seedless_enabled()) {
-        long long nseed = (long long)sm_count() * 2;
-        if (nseed > p.npairs / 8) nseed = p.npairs / 8;
-        // (k-th smallest of nseed*256 per-thread minima: with k <= half of them the hidden second-smallest
+        long long ctas = p.npairs < fft_grid_max ? p.npairs : fft_grid_max;
+        // (k-th smallest of ctas*256 per-thread minima: with k <= half of them the hidden second-smallest
         // values of a thread cost a few per cent of threshold quality, no more)
-        if (nseed >= 1 && nseed * (long long)fftx::THREADS >= 2 * k) {
-            fp.seed = shist;
-            fp.i0 = 0; fp.i1 = nseed;
-            {
-                ProfScope ps(stream, 0);
-                launch_fft(true, (unsigned int)nseed);
-            }
-            PSH_LAUNCHED();
-            fp.i0 = 0; fp.i1 = p.npairs;
-            long long ctas = p.npairs;
-            const long long max_ctas = (long long)sm_count() * 2;
-            if (ctas > max_ctas) ctas = max_ctas;
-            {
-                ProfScope ps(stream, 0);
-                launch_fft(false, (unsigned int)ctas);
-            }
+        if (ctas >= 1 && ctas * (long long)fx2::THREADS >= 2 * k) {
+            long long need = ctas / 4, kq = (2 * k + fx2::THREADS - 1) / fx2::THREADS;
+            if (need < kq) need = kq;
+            if (need > ctas) need = ctas;
+            if (need < 1) need = 1;
+            { const int e_ = env_int("PSH_FFT_SEEDNEED", 0); if (e_ > 0 && e_ <= ctas) need = e_; }
+            fp.seed = 1; fp.seed_need = (unsigned int)need;
+            fp.i0 = 0; fp.i1 = (int)p.npairs;
+            launch_fft((unsigned int)ctas);
             PSH_LAUNCHED();
             { int rc_ = launch_rerank(); if (rc_ != 0) return rc_; }
             {
                 ProfScope ps(stream, 1);
-                select_kernel<<<nq, SEL_THREADS, 0, stream>>>(st, keys, pl.cap, (unsigned int)k, W, fuse_final ? 1 : 0,
+                select_kernel<<<nq, SEL_THREADS, 0, stream>>>(st, keys, pl.cap, (unsigned int)k, qlen, fuse_final ? 1 : 0,
                                                               (unsigned int)pl.Tp, row_offset, d_out_dist, d_out_idx, nullptr);
             }
             PSH_LAUNCHED();
@@ -2274,14 +1837,10 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
         // small rounds are cheaper on the exact kernel (no re-rank, fills the GPU with fewer rows)
         const bool exact_round = first || safe || (!use_fft && !filter) || (use_fft && (next - done) < 64);
         if (use_fft && !exact_round) {
-            fp.i0 = done; fp.i1 = next;
+            fp.i0 = (int)done; fp.i1 = (int)next;
             long long ctas = next - done;
-            const long long max_ctas = (long long)sm_count() * 2;
-            if (ctas > max_ctas) ctas = max_ctas;
-            {
-                ProfScope ps(stream, 0);
-                launch_fft(false, (unsigned int)ctas);
-            }
+            if (ctas > fft_grid_max) ctas = fft_grid_max;
+            launch_fft((unsigned int)ctas);
             PSH_LAUNCHED();
         } else {
             p.i0 = done * unit; p.i1 = next * unit;
@@ -2311,7 +1870,7 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
         {
             ProfScope ps(stream, 1);
             const int fin = (fuse_final && next == nslots) ? 1 : 0;
-            select_kernel<<<nq, SEL_THREADS, 0, stream>>>(st, keys, pl.cap, (unsigned int)k, W, fin,
+            select_kernel<<<nq, SEL_THREADS, 0, stream>>>(st, keys, pl.cap, (unsigned int)k, qlen, fin,
                                                           (unsigned int)pl.Tp, row_offset, d_out_dist, d_out_idx,
                                                           use_fft ? fhist : nullptr);
         }
@@ -2350,7 +1909,7 @@ static int scan_entry(const float *d_dataset, int64_t R, int64_t T, int64_t row_
     unsigned int *cand = reinterpret_cast<unsigned int *>(ws + pl.off_cand);
     float2 *qspec = reinterpret_cast<float2 *>(ws + pl.off_qspec);
     unsigned int *fhist_all = reinterpret_cast<unsigned int *>(ws + pl.off_hist);
-    unsigned int *shist_all = reinterpret_cast<unsigned int *>(ws + pl.off_seed);
+    float *qmaxp_all = reinterpret_cast<float *>(ws + pl.off_qmaxp);
     FftAux aux;
     const FftAux *auxp = nullptr;
     if (mode == PSH_MODE_FFT && d_aux != nullptr) {
@@ -2359,6 +1918,10 @@ static int scan_entry(const float *d_dataset, int64_t R, int64_t T, int64_t row_
             return PSH_E_WORKSPACE;
         auxp = &aux;
     }
+    // queries per group: what the shared memory of the direct-evaluation kernels holds at this context
+    // length (long contexts: fewer queries per pass instead of an error)
+    const int QG = query_group_size(W, mode, auxp != nullptr, emb);
+    if (QG == 0) return PSH_E_UNSUPPORTED;
 
     // per query group: the embedded scan's cross-term vectors advance with the group
     auto group_emb = [&](int g0, EmbParams &eg) -> const EmbParams * {
@@ -2367,13 +1930,16 @@ static int scan_entry(const float *d_dataset, int64_t R, int64_t T, int64_t row_
         if (eg.g) eg.g += (size_t)g0 * W;
         return &eg;
     };
-    for (int g0 = 0; g0 < B; g0 += QG_MAX) {
-        int nq = B - g0 < QG_MAX ? B - g0 : QG_MAX;
+    auto run_group = [&](int g0, int nq, bool safe) -> int {
         EmbParams eg;
-        int rc = run_scan_group(d_dataset, R, T, row_stride, d_queries + (size_t)g0 * qstride, nq, W, H, k, row_offset,
-                                pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap, qspec + (size_t)g0 * fftx::N, fhist_all + (size_t)g0 * FFT_NB, shist_all + (size_t)g0 * SEED_STRIDE, auxp, mode, false,
-                                d_out_dist + (size_t)g0 * k * (d_out_idx ? 1 : 3),
-                                d_out_idx ? d_out_idx + (size_t)g0 * k * 2 : nullptr, stream, group_emb(g0, eg));
+        return run_scan_group(d_dataset, R, T, row_stride, d_queries + (size_t)g0 * qstride, nq, W, H, k, row_offset,
+                              pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap,
+                              qspec + (size_t)g0 * fftx::N, fhist_all + (size_t)g0 * HSTRIDE, qmaxp_all + (size_t)g0 * QMAXP,
+                              auxp, mode, safe, d_out_dist + (size_t)g0 * k * (d_out_idx ? 1 : 3),
+                              d_out_idx ? d_out_idx + (size_t)g0 * k * 2 : nullptr, stream, group_emb(g0, eg));
+    };
+    for (int g0 = 0; g0 < B; g0 += QG) {
+        int rc = run_group(g0, B - g0 < QG ? B - g0 : QG, false);
         if (rc != PSH_OK) return rc;
     }
     if (nosync) return PSH_OK;  // the caller checks psh_scan_overflowed() before trusting the results
@@ -2383,17 +1949,12 @@ static int scan_entry(const float *d_dataset, int64_t R, int64_t T, int64_t row_
     PSH_CUDA(cudaMemcpyAsync(hst, st, sizeof(QState) * B, cudaMemcpyDeviceToHost, stream));
     PSH_CUDA(cudaStreamSynchronize(stream));
     bool redone = false;
-    for (int g0 = 0; g0 < B; g0 += QG_MAX) {
-        int nq = B - g0 < QG_MAX ? B - g0 : QG_MAX;
+    for (int g0 = 0; g0 < B; g0 += QG) {
+        int nq = B - g0 < QG ? B - g0 : QG;
         bool ovf = false;
         for (int i = 0; i < nq; ++i) ovf = ovf || hst[g0 + i].overflow != 0;
         if (ovf) {
-            EmbParams eg;
-            int rc = run_scan_group(d_dataset, R, T, row_stride, d_queries + (size_t)g0 * qstride, nq, W, H, k, row_offset,
-                                    pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap, qspec + (size_t)g0 * fftx::N, fhist_all + (size_t)g0 * FFT_NB, shist_all + (size_t)g0 * SEED_STRIDE, auxp, mode,
-                                    true,
-                                    d_out_dist + (size_t)g0 * k * (d_out_idx ? 1 : 3),
-                                d_out_idx ? d_out_idx + (size_t)g0 * k * 2 : nullptr, stream, group_emb(g0, eg));
+            int rc = run_group(g0, nq, true);
             if (rc != PSH_OK) return rc;
             redone = true;
         }
@@ -2435,20 +1996,11 @@ int psh_scan_topk_embed_f32(const float *d_dataset, int64_t R, int64_t T, int64_
 
 int psh_fft_prepare_embed(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride, int W, int H,
                           const void *d_runs, int nruns, void *d_aux, size_t aux_bytes, void *stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
     if (!d_runs || nruns <= 0) return PSH_E_ARG;
-    // spectra, pair norms and twiddles as for the Identity flavour; then the window energies are
-    // replaced by the embedded energies E2 = sum_n e_n(t)^2
-    int rc = psh_fft_prepare(d_dataset, R, T, row_stride, W, H, d_aux, aux_bytes, stream_);
-    if (rc != PSH_OK) return rc;
-    FftAux a;
-    if (!fft_aux_layout(R, T, W, H, static_cast<unsigned char *>(d_aux), a)) return PSH_E_ARG;
-    const size_t smem = (size_t)nruns * sizeof(EmbRun);
-    if (smem > 12 * 1024) return PSH_E_UNSUPPORTED;   // next to the 32 KiB fp64 prefix array
-    fft_prep_e2_kernel<<<(unsigned int)a.VR, fftx::THREADS, smem, stream>>>(
-        d_dataset, (int)T, row_stride, W, (int)(T - W - H + 1), a, static_cast<const EmbRun *>(d_runs), nruns);
-    PSH_LAUNCHED();
-    return PSH_OK;
+    // spectra, pair norms and twiddles as for the Identity flavour; the energy table holds the embedded
+    // energies E2 = sum_n e_n(t)^2 instead of the window energies
+    return fft_prepare_impl(d_dataset, R, T, row_stride, W, H, d_aux, aux_bytes, static_cast<const EmbRun *>(d_runs), nruns,
+                            (cudaStream_t)stream_);
 }
 
 int psh_scan_overflowed(const void *d_ws, int B, void *stream_) {
@@ -2480,8 +2032,7 @@ static int merge_impl(const float *d_parts, const int *i_parts, int dstride, int
     if (n * 12ull <= MERGE_RANK_SMEM_MAX && !merge_sort_forced()) { use_smem = 2; smem = (size_t)n * 12; }  // merge by rank
     unsigned long long *scratch = nullptr;
     if (!use_smem) PSH_CUDA(cudaMallocAsync(&scratch, (size_t)B * npow2 * sizeof(unsigned long long), stream));
-    if (smem > 48 * 1024)
-        PSH_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { DevSetup *dv_ = nullptr; int rc_ = device_setup(&dv_); if (rc_ != PSH_OK) return rc_; }
     ProfScope ps_merge(stream, 2);
     merge_kernel<<<B, SEL_THREADS, smem, stream>>>(d_parts, i_parts, dstride, istride, G, B, (unsigned int)k,
                                                    (unsigned long long)Tp, npow2, scratch, use_smem, d_out_dist,
@@ -2577,6 +2128,7 @@ static int xchg_launch(const int32_t *d_rec_local, void *const *bufs, int G, int
         x.rec[g] = reinterpret_cast<int *>(base);
         x.flags[g] = reinterpret_cast<unsigned int *>(base + rb);
     }
+    { DevSetup *dv_ = nullptr; int rc_ = device_setup(&dv_); if (rc_ != PSH_OK) return rc_; }
     x.local_rec = d_rec_local; x.G = G; x.rank = rank; x.epoch = epoch;
     x.timeout_ns = xchg_timeout_ns();
     unsigned int npow2 = 1; while (npow2 < n) npow2 <<= 1;
@@ -2587,8 +2139,6 @@ static int xchg_launch(const int32_t *d_rec_local, void *const *bufs, int G, int
     if (n * 12ull <= MERGE_RANK_SMEM_MAX && !merge_sort_forced() && xchg_ll_enabled()) {
         // LL form: self-validating 8-byte words, no fence, no flags
         const size_t smem_ll = (phases & 2) ? (size_t)n * 12 : 0;
-        if (smem_ll > 48 * 1024)
-            PSH_CUDA(cudaFuncSetAttribute(xchg_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ll));
         {
             ProfScope ps_merge(stream, 2);
             xchg_ll_kernel<<<B, SEL_THREADS, smem_ll, stream>>>(x, B, (unsigned int)k, (unsigned long long)Tp, d_out_dist,
@@ -2599,8 +2149,6 @@ static int xchg_launch(const int32_t *d_rec_local, void *const *bufs, int G, int
     }
     unsigned long long *scratch = nullptr;
     if (!use_smem) PSH_CUDA(cudaMallocAsync(&scratch, (size_t)B * npow2 * sizeof(unsigned long long), stream));
-    if (smem > 48 * 1024)
-        PSH_CUDA(cudaFuncSetAttribute(xchg_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         ProfScope ps_merge(stream, 2);
         xchg_merge_kernel<<<B, SEL_THREADS, smem, stream>>>(x, B, (unsigned int)k, (unsigned long long)Tp, npow2, scratch,

@@ -20,59 +20,8 @@
 // bit of a box sum.
 #pragma once
 
-// E2[v][pos] for every virtual row v (one CTA each), in the scan's output order, +inf beyond the
-// row's windows -- the layout of fft_prep_y2_kernel.  fp64 prefix sums, fp64 box sums, rounded once.
-__global__ void __launch_bounds__(fftx::THREADS) fft_prep_e2_kernel(const float *__restrict__ ds, int T,
-                                                                    long long row_stride, int W, int Tp, FftAux a,
-                                                                    const EmbRun *__restrict__ runs, int nruns) {
-    __shared__ double pfx[fftx::N + 1];
-    __shared__ double wsum[fftx::THREADS / 32];
-    extern __shared__ EmbRun runs_s[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < nruns; i += fftx::THREADS) runs_s[i] = runs[i];
-    const long long row = (long long)blockIdx.x / a.nsegv;
-    const int piece = (int)((long long)blockIdx.x - row * a.nsegv);
-    const int o0 = piece * a.hop;
-    const float *y = ds + row * row_stride + o0;
-    double loc[16];
-    double run = 0.0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const int n = 16 * tid + i;
-        run += o0 + n < T ? (double)y[n] : 0.0;
-        loc[i] = run;
-    }
-    double incl = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const double u = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += u;
-    }
-    if (lane == 31) wsum[warp] = incl;
-    __syncthreads();
-    double off = incl - run;
-    for (int w = 0; w < warp; ++w) off += wsum[w];
-    if (tid == 0) pfx[0] = 0.0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) pfx[16 * tid + i + 1] = off + loc[i];
-    __syncthreads();
-    float *o = a.Y2 + (size_t)blockIdx.x * a.y2_stride;
-    for (int pos = tid; pos < a.y2_stride; pos += fftx::THREADS) {
-        const int t = (pos & ~255) | ((pos & 15) << 4) | ((pos >> 4) & 15);
-        const bool mine = t < a.span && o0 + t < Tp;
-        float out = __int_as_float(0x7f800000);
-        if (mine) {
-            double e2 = 0.0, e = 0.0;
-            for (int r = 0; r < nruns; ++r) {
-                const EmbRun rn = runs_s[r];
-                e += (double)rn.c * (pfx[t + rn.b] - pfx[t + rn.a]);
-                if (r + 1 == nruns || runs_s[r + 1].row != rn.row) { e2 += e * e; e = 0.0; }
-            }
-            out = __double2float_rd(e2 * (1.0 - 16.0 * 5.9604644775390625e-8));   // 16u E2 rounding allowance
-        }
-        o[pos] = out;
-    }
-}
+// The E2 table is written by fft_prep_energy_kernel<true> (pshadow_fftscan.cuh): fp64 prefix sums, fp64
+// box sums, (1 - 16u), scaled by the pair's power of two and rounded DOWN to fp16.
 
 // exact embedded re-rank of the fft filter's candidates: one WARP per candidate window.
 // The warp builds the double-float prefix of the window's W samples (lane chunks + fp64 scan of

@@ -1,14 +1,6 @@
-// pshadow_fft.cuh -- FFT flavour of the filter scan (PSH_MODE_FFT), included by pshadow.cu.
-//
-// The cross term D_t = sum_j q_j y_{t+j} of ||q - y_t||^2 = Q2 + Y2_t - 2 D_t is a correlation:
-// for a whole trajectory it costs O(log N) per window through the FFT instead of W FMAs.  Two
-// trajectories share one complex transform (z = y_a + i y_b; q is real, so the correlation of z
-// with q is corr(y_a) + i corr(y_b)).  What is W- and query-independent is computed once per
-// dataset (psh_fft_prepare): the spectra Z = FFT_4096(z) of all row pairs, the window energies
-// Y2[r][t] (fp64 prefix sums, rounded once) and the pair norms.  Per query the scan then streams
-// Z and Y2 once (2 x the raw bytes), multiplies by conj(FFT(q))/N, runs ONE inverse 4096-point
-// FFT per row pair in registers/shared memory and tests the same rigorous lower bound as the
-// FMA filter; survivors go through the exact re-rank, so results stay bit-identical.
+// pshadow_fft.cuh -- table-twiddle 4096-point transform (forward: dataset spectra in psh_fft_prepare;
+// both directions: test hook), included by pshadow.cu.  The scan's own inverse transform (packed fp32
+// arithmetic) and the data formats live in pshadow_fft2.cuh.
 //
 // FFT: N = 4096 = 16 x 16 x 16, 256 threads, 16 complex values per thread, three radix-16
 // passes in registers with two padded shared-memory exchanges.  Input index n = tid + 256 i,
@@ -155,50 +147,5 @@ __device__ __forceinline__ void fft4096(float2 (&v)[16], float2 *ex, const float
     fft16<DIR>(v);  // over tau1 -> c
 }
 
-
-// Scan flavour of the inverse transform: same three radix-16 passes, but
-//  * the second exchange is a 16 x 16 transpose INSIDE each half-warp (thread (a, t1) hands its
-//    value b to thread (a, b)), so it needs __syncwarp() only -- one CTA barrier per transform;
-//  * `after_first_barrier()` runs right behind that barrier: every thread has consumed the
-//    staged spectrum by then, so the caller issues the next TMA there instead of paying a
-//    barrier of its own.
-// Output: v[c] = X[k], k = (tid >> 4) + 16 (tid & 15) + 256 c  (the two low hex digits of the
-// natural position tid + 256 c swapped; the window energies are stored in the same order).
-constexpr int EX2_STRIDE = 272;                   // 16 x 17 float2 per row: conflict-free transposes
-constexpr int EX2_FLOAT2 = 16 * EX2_STRIDE;
-
-template <typename F>
-__device__ __forceinline__ void ifft4096_scan(float2 (&v)[16], float2 *ex, int tid, const TwSeeds &seeds,
-                                              F after_first_barrier) {
-    fft16<1>(v);  // over i -> a
-    {
-        float2 w[16];
-        unit_powers(seeds.a1, seeds.a4, w);
-#pragma unroll
-        for (int a = 1; a < 16; ++a) v[a] = cmul(v[a], w[a]);
-    }
-#pragma unroll
-    for (int a = 0; a < 16; ++a) ex[a * EX2_STRIDE + tid] = v[a];
-    __syncthreads();
-    after_first_barrier();
-    const int a2 = tid >> 4, t1 = tid & 15;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = ex[a2 * EX2_STRIDE + t1 + 16 * i];
-    fft16<1>(v);  // over tau2 -> b
-    {
-        float2 w[16];
-        unit_powers(seeds.b1, seeds.b4, w);
-#pragma unroll
-        for (int b = 1; b < 16; ++b) v[b] = cmul(v[b], w[b]);
-    }
-    // row a2 of ex is read (above) and rewritten (below) by the 16 threads of this half-warp only
-    __syncwarp();
-#pragma unroll
-    for (int b = 0; b < 16; ++b) ex[a2 * EX2_STRIDE + b * 17 + t1] = v[b];
-    __syncwarp();
-#pragma unroll
-    for (int t = 0; t < 16; ++t) v[t] = ex[a2 * EX2_STRIDE + t1 * 17 + t];
-    fft16<1>(v);  // over tau1 -> c : X[a2 + 16 t1 + 256 c]
-}
 
 }  // namespace fftx
