@@ -24,22 +24,25 @@
 // Arithmetic: Blackwell's packed fp32 pipe (add/mul/fma.rn.f32x2 -> SASS FADD2 / FMUL2 / FFMA2).  A
 // complex value lives in one 64-bit register pair; a complex add is ONE instruction, a multiplication
 // by +-i folds into an FFMA2 with a swapped / half-negated operand, a complex multiplication is two
-// (FMUL2 with a broadcast operand + FFMA2): the radix-8 butterfly issues 28 instructions instead of
-// 56.  Each lane is an IEEE fp32 operation, so the error analysis of round 1 is unchanged.
+// (FMUL2 with a broadcast operand + FFMA2): the radix-16 butterfly issues 81 instructions instead of
+// 160.  Each lane is an IEEE fp32 operation, so the error analysis of round 1 is unchanged.
 //
-// FFT: N = 4096 = 8 x 8 x 8 x 8, 512 threads, 8 complex values per thread, four radix-8 passes in
-// registers (64 registers per thread: 32 resident warps per SM -- the radix-16 / 256-thread version of
-// round 1 ran 16 warps per SM at 128 registers and was latency-bound at 36-64 % issue utilisation).
-// Exchange 1 goes through shared memory behind the transform's only CTA barrier, exchange 2 stays inside
-// groups of 64 threads (named barriers), exchange 3 is an 8 x 8 transpose inside 8 lanes.  Input index
-// n = tid + 512 i; output v[d] = X[kb(tid) + 512 d] (the energies are stored in that order).
+// FFT: N = 4096 = 16 x 16 x 16, 256 threads, 16 complex values per thread, three radix-16 passes in
+// registers; exchange 1 through padded shared memory (the transform's only CTA barrier), exchange 2 is
+// a 16 x 16 transpose inside each half-warp.  Input index n = tid + 256 i; output v[c] = X[k],
+// k = (tid >> 4) + 16 (tid & 15) + 256 c (the energies are stored in that order).
+// (Measured and rejected this round: four radix-8 passes with 512 threads -- 64 registers per thread, 32
+// resident warps per SM -- spilled ~200 bytes per thread and added a third exchange: 0.33 ms against
+// 0.23 ms; pass-B twiddles from a shared table and 3 CTAs per SM at 80 registers were slower as well.)
 #pragma once
 // (pshadow.cu includes <cuda_fp16.h> at file scope)
 
 namespace fx2 {
 
 constexpr int N = 4096;
-constexpr int THREADS = 512;
+constexpr int THREADS = 256;
+constexpr int EX_STRIDE = 272;                    // 16 x 17 float2 per row: conflict-free transposes
+constexpr int EX_FLOAT2 = 16 * EX_STRIDE;
 
 #ifndef PSH_SCALAR_FFT
 #define PSH_PK2(name, op)                                                                              \
@@ -93,90 +96,93 @@ __device__ __forceinline__ void ifft4_a2i(float2 &a0, float2 &a1, float2 &a2, fl
     a3 = sub_i(t1, t3);
 }
 
-// inverse 8-point DFT of v[0..7], natural order in and out; 28 packed instructions.
-//   X[2m]   = IDFT4(x_j + x_{j+4})_m,   X[2m+1] = IDFT4((x_j - x_{j+4}) w8^j)_m   (w8^2 = i folded into the butterfly)
-__device__ __forceinline__ void ifft8(float2 (&v)[8]) {
-    const float r = 0.70710678118654752f;
-    float2 s0 = add2(v[0], v[4]), d0 = sub2(v[0], v[4]);
-    float2 s1 = add2(v[1], v[5]), d1 = sub2(v[1], v[5]);
-    float2 s2 = add2(v[2], v[6]), d2 = sub2(v[2], v[6]);
-    float2 s3 = add2(v[3], v[7]), d3 = sub2(v[3], v[7]);
-    d1 = cmul(d1, make_float2(r, r));      // w8^1
-    d3 = cmul(d3, make_float2(-r, r));     // w8^3
-    ifft4(s0, s1, s2, s3);                 // X0, X2, X4, X6
-    ifft4_a2i(d0, d1, d2, d3);             // X1, X3, X5, X7
-    v[0] = s0; v[2] = s1; v[4] = s2; v[6] = s3;
-    v[1] = d0; v[3] = d1; v[5] = d2; v[7] = d3;
+// inverse 16-point DFT of v[0..15], natural order in and out; 81 packed instructions
+__device__ __forceinline__ void ifft16(float2 (&v)[16]) {
+#pragma unroll
+    for (int n1 = 0; n1 < 4; ++n1) ifft4(v[n1], v[n1 + 4], v[n1 + 8], v[n1 + 12]);
+    const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, r = 0.70710678118654752f;
+    v[1 + 4 * 1] = cmul(v[1 + 4 * 1], make_float2(c1, s1));     // w^1
+    v[2 + 4 * 1] = cmul(v[2 + 4 * 1], make_float2(r, r));       // w^2
+    v[3 + 4 * 1] = cmul(v[3 + 4 * 1], make_float2(s1, c1));     // w^3
+    v[1 + 4 * 2] = cmul(v[1 + 4 * 2], make_float2(r, r));       // w^2
+    //  v[2 + 4 * 2] *= w^4 = i : folded into the k2 = 2 butterfly below
+    v[3 + 4 * 2] = cmul(v[3 + 4 * 2], make_float2(-r, r));      // w^6
+    v[1 + 4 * 3] = cmul(v[1 + 4 * 3], make_float2(s1, c1));     // w^3
+    v[2 + 4 * 3] = cmul(v[2 + 4 * 3], make_float2(-r, r));      // w^6
+    v[3 + 4 * 3] = cmul(v[3 + 4 * 3], make_float2(-c1, -s1));   // w^9
+    ifft4(v[0], v[1], v[2], v[3]);
+    ifft4(v[4], v[5], v[6], v[7]);
+    ifft4_a2i(v[8], v[9], v[10], v[11]);
+    ifft4(v[12], v[13], v[14], v[15]);
+    // natural order: X[4 k1 + k2] = v[k1 + 4 k2]  (a register renaming under full unrolling)
+    float2 w[16];
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1)
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) w[4 * k1 + k2] = v[k1 + 4 * k2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = w[i];
 }
 
-// v[j] *= w^j, j = 1..7, the powers built from the table-exact w^1 (every power is a product of at most
-// three values of depth <= 2: error <= ~10 u, inside CF)
-__device__ __forceinline__ void twiddle8(float2 (&v)[8], float2 w1) {
-    const float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
-    v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3); v[4] = cmul(v[4], w4);
+// v[a] *= w^a, a = 1..15, the powers built from w^1 and w^4 (both table-exact): every power is a
+// product of at most three table values (error <= ~17 u, inside CF).  Interleaved so that only
+// w1, w2, w3 and one of w4 / w8 / w12 are live at a time.
+__device__ __forceinline__ void twiddle_powers(float2 (&v)[16], float2 w1, float2 w4) {
+    const float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+    v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3);
+    v[4] = cmul(v[4], w4);
     v[5] = cmul(v[5], cmul(w4, w1)); v[6] = cmul(v[6], cmul(w4, w2)); v[7] = cmul(v[7], cmul(w4, w3));
+    const float2 w8 = cmul(w4, w4);
+    v[8] = cmul(v[8], w8);
+    v[9] = cmul(v[9], cmul(w8, w1)); v[10] = cmul(v[10], cmul(w8, w2)); v[11] = cmul(v[11], cmul(w8, w3));
+    const float2 w12 = cmul(w8, w4);
+    v[12] = cmul(v[12], w12);
+    v[13] = cmul(v[13], cmul(w12, w1)); v[14] = cmul(v[14], cmul(w12, w2)); v[15] = cmul(v[15], cmul(w12, w3));
 }
 
-// loop-invariant twiddle seeds of a thread: exp(2 pi i tid/4096), exp(2 pi i (tid&63)/512), exp(2 pi i (tid&7)/64)
-struct Seeds { float2 s1, s2, s3; };
+// loop-invariant twiddle seeds of a thread: pass A uses powers of exp(2 pi i tid/4096), pass B powers of
+// exp(2 pi i (tid&15)/256)
+struct Seeds { float2 a1, a4, b1, b4; };
 __device__ __forceinline__ Seeds load_seeds(const float2 *__restrict__ tw, int tid) {
     Seeds s;
-    s.s1 = __ldg(tw + tid);
-    s.s2 = __ldg(tw + 8 * (tid & 63));
-    s.s3 = __ldg(tw + 64 * (tid & 7));
+    const int t1 = tid & 15;
+    s.a1 = __ldg(tw + tid);
+    s.a4 = __ldg(tw + 4 * tid);
+    s.b1 = __ldg(tw + 16 * t1);
+    s.b4 = __ldg(tw + 64 * t1);
     return s;
 }
 
-// Inverse 4096-point transform by one CTA of 512 threads, 8 complex values per thread, four radix-8
-// passes (4096 = 8 x 8 x 8 x 8; 64 registers per thread: 32 resident warps per SM).
-//   In : v[i] = x[tid + 512 i].
-//   Out: v[d] = X[kb + 512 d],  kb = (tid >> 6) + 8 ((tid >> 3) & 7) + 64 (tid & 7)   (tid's octal digits reversed).
-// Exchange 1 is CTA-wide (the transform's only CTA barrier; `before_first_barrier()` / `after_first_barrier()`
-// run right in front of / behind it -- every thread has consumed the staged spectrum by then); exchange 2 stays
-// inside a group of 64 threads (named barrier 1 + group); exchange 3 is an 8 x 8 transpose inside 8 lanes.
-// ex1: 8 x 512 float2; ex2: 8 groups x 8 rows x 72 float2 (rows padded: conflict-free 64-bit accesses).
-constexpr int EX1_FLOAT2 = 8 * 512;
-constexpr int EX2_ROW = 72;
-constexpr int EX2_FLOAT2 = 64 * EX2_ROW;
-
-__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
+// inverse 4096-point transform by one CTA of 256 threads.  In: v[i] = x[tid + 256 i].
+// Out: v[c] = X[(tid >> 4) + 16 (tid & 15) + 256 c].  `after_first_barrier()` runs right behind the
+// transform's only CTA barrier: every thread has consumed the staged spectrum by then;
+// `before_first_barrier()` right in front of it (what it writes to shared memory is visible behind it).
 template <typename F0, typename F>
-__device__ __forceinline__ void ifft4096(float2 (&v)[8], float2 *ex1, float2 *ex2, int tid, const Seeds &seeds,
+__device__ __forceinline__ void ifft4096(float2 (&v)[16], float2 *ex, int tid, const Seeds &seeds,
                                          F0 before_first_barrier, F after_first_barrier) {
-    ifft8(v);                                   // over n3 -> c
-    twiddle8(v, seeds.s1);                      // w4096^(tid c)
+    ifft16(v);  // over i -> a
+    twiddle_powers(v, seeds.a1, seeds.a4);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) ex1[c * 512 + tid] = v[c];
+    for (int a = 0; a < 16; ++a) ex[a * EX_STRIDE + tid] = v[a];
     before_first_barrier();
     __syncthreads();
     after_first_barrier();
-    const int c = tid >> 6, bp = tid & 63, x = (tid >> 3) & 7, y = tid & 7;
+    const int a2 = tid >> 4, t1 = tid & 15;
 #pragma unroll
-    for (int a = 0; a < 8; ++a) v[a] = ex1[c * 512 + 64 * a + bp];
-    ifft8(v);                                   // over a' -> c'
-    twiddle8(v, seeds.s2);                      // w512^(bp c')
-    float2 *g2 = ex2 + c * (8 * EX2_ROW);       // the 64 threads sharing c exchange among themselves
-#pragma unroll
-    for (int cp = 0; cp < 8; ++cp) g2[cp * EX2_ROW + bp] = v[cp];
-    bar_sync_named(1 + c, 64);
-    float2 *g3 = g2 + x * EX2_ROW;              // row x is read, then reused, by the 8 lanes (c, x, .) only
-#pragma unroll
-    for (int a = 0; a < 8; ++a) v[a] = g3[8 * a + y];
-    ifft8(v);                                   // over a'' -> c''
-    twiddle8(v, seeds.s3);                      // w64^(y c'')
+    for (int i = 0; i < 16; ++i) v[i] = ex[a2 * EX_STRIDE + t1 + 16 * i];
+    ifft16(v);  // over tau2 -> b
+    twiddle_powers(v, seeds.b1, seeds.b4);
+    // row a2 of ex is read (above) and rewritten (below) by the 16 threads of this half-warp only
     __syncwarp();
 #pragma unroll
-    for (int cq = 0; cq < 8; ++cq) g3[cq * 9 + y] = v[cq];
+    for (int b = 0; b < 16; ++b) ex[a2 * EX_STRIDE + b * 17 + t1] = v[b];
     __syncwarp();
 #pragma unroll
-    for (int b = 0; b < 8; ++b) v[b] = g3[y * 9 + b];
-    ifft8(v);                                   // over b'' -> d
+    for (int t = 0; t < 16; ++t) v[t] = ex[a2 * EX_STRIDE + t1 * 17 + t];
+    ifft16(v);  // over tau1 -> c
 }
 
-// window of output register d of thread tid: kb(tid) + 512 d
-__device__ __forceinline__ int out_base(int tid) { return (tid >> 6) + 8 * ((tid >> 3) & 7) + 64 * (tid & 7); }
+// window of output register c of thread tid: kb(tid) + 256 c
+__device__ __forceinline__ int out_base(int tid) { return (tid >> 4) + 16 * (tid & 15); }
 
 }  // namespace fx2

@@ -38,36 +38,29 @@ inline bool fft_aux_layout(long long R, long long T, int W, int H, unsigned char
 }
 
 // debug / test entry: batched 4096-point transform of n independent signals
-//   dir -1 / +1: table-twiddle forward / inverse (the dataset spectra use the forward one), 256 threads
-//   dir +3     : the scan's packed radix-8 inverse (512 threads), output un-permuted
+//   dir -1 / +1: table-twiddle forward / inverse (the dataset spectra use the forward one)
+//   dir +3     : the scan's packed inverse, output un-permuted
 __global__ void __launch_bounds__(fftx::THREADS) fft_debug_kernel(const float2 *__restrict__ in, float2 *out,
                                                                   const float2 *__restrict__ tw, int dir) {
-    __shared__ float2 ex[fftx::EX_FLOAT2];
+    __shared__ float2 ex[fx2::EX_FLOAT2];
     const int tid = threadIdx.x;
     const float2 *x = in + (size_t)blockIdx.x * fftx::N;
     float2 *y = out + (size_t)blockIdx.x * fftx::N;
     float2 v[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = x[tid + 256 * i];
+    if (dir >= 3) {
+        fx2::ifft4096(v, ex, tid, fx2::load_seeds(tw, tid), []() {}, []() {});
+        const int kb = fx2::out_base(tid);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) y[kb + 256 * c] = v[c];
+        return;
+    }
     const fftx::TwSeeds seeds = fftx::load_seeds(tw, tid);
     if (dir > 0) fftx::fft4096<1, true>(v, ex, tw, tid, seeds);
     else fftx::fft4096<-1, true>(v, ex, tw, tid, seeds);
 #pragma unroll
     for (int c = 0; c < 16; ++c) y[tid + 256 * c] = v[c];
-}
-__global__ void __launch_bounds__(fx2::THREADS) fft_debug_scan_kernel(const float2 *__restrict__ in, float2 *out,
-                                                                      const float2 *__restrict__ tw) {
-    extern __shared__ __align__(16) float2 dbg_ex[];
-    const int tid = threadIdx.x;
-    const float2 *x = in + (size_t)blockIdx.x * fx2::N;
-    float2 *y = out + (size_t)blockIdx.x * fx2::N;
-    float2 v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = x[tid + 512 * i];
-    fx2::ifft4096(v, dbg_ex, dbg_ex + fx2::EX1_FLOAT2, tid, fx2::load_seeds(tw, tid), []() {}, []() {});
-    const int kb = fx2::out_base(tid);
-#pragma unroll
-    for (int d = 0; d < 8; ++d) y[kb + 512 * d] = v[d];
 }
 
 __device__ __forceinline__ float block_max_256(float v, float *red) {
@@ -157,8 +150,8 @@ __global__ void __launch_bounds__(fftx::THREADS) fft_prep_spectra_kernel(const f
     }
 }
 
-// window energies of a pair's two virtual rows, in the scan's output order (position p = tid + 512 d holds
-// window t = kb(tid) + 512 d, kb = tid's octal digits reversed), scaled by the pair's power of two es and rounded DOWN to fp16; +inf
+// window energies of a pair's two virtual rows, in the scan's output order (position p = tid + 256 c holds
+// window t = kb(tid) + 256 c, kb = tid's hex digits swapped), scaled by the pair's power of two es and rounded DOWN to fp16; +inf
 // where the virtual row owns no window.  Identity: Y2[t] = sum_{j<W} y_{t+j}^2 from an fp64 prefix sum.
 // EMBK (pshadow_embed_fft.cuh): E2[t] = sum_n e_n(t)^2 (1 - 16u) from an fp64 prefix sum of y and the
 // kernel's runs.  One CTA per pair.
@@ -212,7 +205,7 @@ __global__ void __launch_bounds__(fftx::THREADS) fft_prep_energy_kernel(const fl
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
             const int pos = tid + 256 * c;
-            const int t = fx2::out_base(pos & 511) + (pos & ~511);  // position pos holds window kb(pos & 511) + 512 (pos >> 9)
+            const int t = fx2::out_base(pos & 255) + (pos & ~255);  // position pos holds window kb(pos & 255) + 256 (pos >> 8)
             const bool mine = have && t < a.span && o0 + t < Tp;   // the windows this virtual row owns
             float out = INF;
             if (mine) {
@@ -459,7 +452,7 @@ __device__ __forceinline__ void fft_refresh_threshold(const FftScanParams &p, in
     }
 }
 
-// Seeding pass: the CTA's 512 entries (one bin per thread, `cnt` false: none) are first counted in a
+// Seeding pass: the CTA's 256 entries (one bin per thread, `cnt` false: none) are first counted in a
 // shared-memory histogram (`sh`: HB uints, the idle exchange buffer) and only the non-empty bins go to the
 // global histogram -- the per-thread minima of all CTAs fall into a few dozen fine bins and one or two
 // coarse ones, and ~10^5 atomics on the same few addresses serialise in L2 (measured: 50 us per launch).
@@ -471,32 +464,94 @@ __device__ __forceinline__ void seed_hist_flush(unsigned int *hq, unsigned int *
     __syncthreads();
     if (cnt) atomicAdd(sh + bin, 1u);
     __syncthreads();
-    // warp w owns the bins [512 w, 512 w + 512) = the coarse bins 4 w .. 4 w + 3
+    // warp w owns the bins [1024 w, 1024 w + 1024) = the coarse bins 8 w .. 8 w + 7
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
+    for (int m = 0; m < 8; ++m) {
         unsigned int csum = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int fb = 512 * warp + 128 * m + 32 * j + lane;
+            const int fb = 1024 * warp + 128 * m + 32 * j + lane;
             const unsigned int h = sh[fb];
             if (h != 0u) atomicAdd(hq + fb, h);
             csum += h;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(FULL, csum, o);
-        if (lane == 0 && csum != 0u) atomicAdd(hq + HB + 4 * warp + m, csum);
+        if (lane == 0 && csum != 0u) atomicAdd(hq + HB + 8 * warp + m, csum);
     }
     __syncthreads();                                   // the exchange buffers may be overwritten
 }
 
-// One CTA (512 threads) per row pair and iteration: Z^ * conj(Q)/N -> inverse FFT -> (D_a[t], D_b[t]);
+// The rare part of the epilogue (some window of the warp passed): per-window test, candidate append, upper
+// bounds into the threshold histogram.  (Out of line it cost 17 %: the transform's registers went through the stack.)
+__device__ __forceinline__ void fft_append_candidates(const FftScanParams &p, int b, const float2 (&v)[16], const __half2 *Ys,
+                                                   bool any, float m2, float cu, float rhs, float inv_es, float base0,
+                                                   float slack, int pair, int kb, bool count_ub) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const float INF = __int_as_float(0x7f800000);
+    unsigned int *hq = p.hist + (size_t)b * HSTRIDE;
+    const int hb = hist_base(p.st[b].q2);
+    unsigned int mask = 0;
+    if (any) {
+#pragma unroll
+        for (int d = 0; d < 16; ++d) {
+            const float2 yf = __half22float2(Ys[tid + 256 * d]);
+            const float2 val = fx2::fma2(v[d], make_float2(m2, m2), yf);
+            if (val.x <= rhs && yf.x < INF) mask |= 1u << d;
+            if (val.y <= rhs && yf.y < INF) mask |= 1u << (16 + d);
+        }
+    }
+    const int cnt = __popc(mask);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += u;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    if (total == 0) return;
+    unsigned int basepos = 0;
+    if (lane == 31) basepos = atomicAdd(&p.st[b].ccount, (unsigned int)total);
+    basepos = __shfl_sync(FULL, basepos, 31);
+    unsigned int pos = basepos + (unsigned int)(incl - cnt);
+    unsigned int *dst = p.cand + (size_t)b * p.cap;
+    // flat window index of local window 0 of each virtual row: row * T' + piece * hop
+    const long long ra = 2 * (long long)pair, rb = ra + 1;   // virtual rows
+    const unsigned int fa = (unsigned int)((unsigned long long)(ra / p.nsegv) * (unsigned long long)p.Tp
+                                           + (unsigned long long)(ra % p.nsegv) * (unsigned long long)p.hop);
+    const unsigned int fb = (unsigned int)((unsigned long long)(rb / p.nsegv) * (unsigned long long)p.Tp
+                                           + (unsigned long long)(rb % p.nsegv) * (unsigned long long)p.hop);
+#pragma unroll
+    for (int d = 0; d < 16; ++d) {
+        if (mask & (0x10001u << d)) {
+            const unsigned int t = (unsigned int)(kb + 256 * d);
+            const float2 yf = __half22float2(Ys[tid + 256 * d]);
+            const float2 ub2 = fx2::fma2(yf, make_float2(cu, cu), fx2::fma2(v[d], make_float2(m2, m2), yf));
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (mask & (1u << (16 * h + d))) {
+                    if (pos < p.cap) dst[pos] = (h ? fb : fa) + t;
+                    ++pos;
+                    if (count_ub) {   // upper bound of the window's exact squared distance
+                        const float u0 = h ? ub2.y : ub2.x;
+                        const float ub = fmaxf((((u0 + 5.9604644775390625e-8f) * inv_es + base0) + 2.0f * slack) * 1.000001f, 0.0f);
+                        const int bin = (int)(__float_as_uint(ub) >> 13) - hb;
+                        if (ub < INF && bin < HB) hist_add_ub(hq, bin < 0 ? 0 : bin, 1u);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// One CTA (256 threads) per row pair and iteration: Z^ * conj(Q)/N -> inverse FFT -> (D_a[t], D_b[t]);
 // lower bound
 //   LB = Q2 + Y2^ - 2 D^ - slack,
 //   slack = 2 cf_u Qmax ynorm + 2 zqerr ||g|| + 12u (Q2 + ynorm^2)
 // (FFT error; quantisation of the spectrum; Y2, Q2 roundings and the combination), tested in the pair's
 // scaled units as fma(m2, v, yf) <= rhs.  Staging: the pair's spectrum (16 KiB) and its interleaved energy
 // rows (16 KiB) + its statistics (16 bytes) arrive by TMA bulk copies issued one pair ahead.  With a single
-// query its spectrum stays in registers (8 values per thread, a function of tid only).
+// query its spectrum stays in registers (16 values per thread, a function of tid only).
 //
 // Pairs are handed out dynamically (an atomic slot counter; CTAs progress at different speeds), in a
 // permuted order so that every prefix is a spread-out sample of the ensemble.
@@ -504,8 +559,8 @@ __device__ __forceinline__ void seed_hist_flush(unsigned int *hq, unsigned int *
 // Thresholds.  Every kept window adds its UPPER bound UB = LB + 2 slack + (fp16 floor of Y2) to the
 // query's histogram; CTAs take turns re-deriving the threshold from it (one warp, no barrier) and publish
 // it, every CTA picks the published value up once per pair.  p.seed: thresholds start at +inf; every CTA
-// first evaluates its first pair WITHOUT appending anything -- each thread adds the minimum UB of its 16
-// windows (512 distinct windows per CTA) -- waits until `seed_need` CTAs have done so (a fraction of the
+// first evaluates its first pair WITHOUT appending anything -- each thread adds the minimum UB of its 32
+// windows (256 distinct windows per CTA) -- waits until `seed_need` CTAs have done so (a fraction of the
 // grid: no co-residency assumption), derives its first threshold and only then tests the pair's windows
 // (one query: the transform's output is still in registers; a group of queries: the pair is transformed
 // again).  This replaces round 1's separate seed launch.
@@ -518,9 +573,8 @@ __global__ void __launch_bounds__(fx2::THREADS, 2) fft_scan_kernel(const FftScan
     extern __shared__ __align__(128) unsigned char fsm[];
     __half2 *Zs = reinterpret_cast<__half2 *>(fsm);
     __half2 *Ys = Zs + fx2::N;
-    float2 *ex1 = reinterpret_cast<float2 *>(Ys + fx2::N);
-    float2 *ex2 = ex1 + fx2::EX1_FLOAT2;
-    float4 *pis = reinterpret_cast<float4 *>(ex2 + fx2::EX2_FLOAT2);
+    float2 *ex = reinterpret_cast<float2 *>(Ys + fx2::N);
+    float4 *pis = reinterpret_cast<float4 *>(ex + fx2::EX_FLOAT2);
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(pis + 1);
     __shared__ float s_thr[QG_MAX], s_q2[QG_MAX], s_qmax[QG_MAX], s_gn[QG_MAX];
     __shared__ __align__(16) uint4 s_pub[QG_MAX];   // {published threshold bits, ...} of each query, one pair behind
@@ -563,13 +617,13 @@ __global__ void __launch_bounds__(fx2::THREADS, 2) fft_scan_kernel(const FftScan
     int pair = fft_pair_of_slot(p, slot);
     if (tid == 0) { issue_z(pair); issue_y(pair); }
 
-    float2 qreg[8];
+    float2 qreg[16];
     if (SINGLEQ) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) qreg[i] = __ldg(p.Qc + tid + 512 * i);
+        for (int i = 0; i < 16; ++i) qreg[i] = __ldg(p.Qc + tid + 256 * i);
     }
     const fx2::Seeds seeds = fx2::load_seeds(p.tw, tid);
-    const int kb = fx2::out_base(tid);   // v[d] belongs to window kb + 512 d of both rows of the pair
+    const int kb = fx2::out_base(tid);   // v[d] belongs to window kb + 256 d of both rows of the pair
     uint32_t phZ = 0, phY = 0;
     bool seeding = p.seed != 0;
     bool staged = false;        // this pair's spectrum and energies are already in shared memory (a group's pass after seeding)
@@ -578,7 +632,7 @@ __global__ void __launch_bounds__(fx2::THREADS, 2) fft_scan_kernel(const FftScan
     int par = 0;
     for (int iter = 0;;) {
         // warp 3 draws the slot behind this pair now and turns it into a pair right in front of the
-        // transform's barrier -- the atomic's round trip hides behind the first radix-8 pass
+        // transform's barrier -- the atomic's round trip hides behind the first radix-16 pass
         const bool draw = !(seeding && rerun);
         unsigned int drawn = 0;
         if (draw && tid == 96) drawn = atomicAdd(p.hist + H_SLOT, 1u);
@@ -594,21 +648,21 @@ __global__ void __launch_bounds__(fx2::THREADS, 2) fft_scan_kernel(const FftScan
         }
         if (!staged) { mbar_wait(barZ, phZ); phZ ^= 1; }
         for (int b = 0; b < p.nq; ++b) {
-            float2 v[8];
+            float2 v[16];
             if (SINGLEQ) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = fx2::cmul(__half22float2(Zs[tid + 512 * i]), qreg[i]);
+                for (int i = 0; i < 16; ++i) v[i] = fx2::cmul(__half22float2(Zs[tid + 256 * i]), qreg[i]);
             } else {
                 const float2 *Qb = p.Qc + (size_t)b * fx2::N;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = __ldg(Qb + tid + 512 * i);   // (L1/L2-resident; lands in v)
+                for (int i = 0; i < 16; ++i) v[i] = __ldg(Qb + tid + 256 * i);   // (L1/L2-resident; lands in v)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = fx2::cmul(__half22float2(Zs[tid + 512 * i]), v[i]);
+                for (int i = 0; i < 16; ++i) v[i] = fx2::cmul(__half22float2(Zs[tid + 256 * i]), v[i]);
             }
             // behind the transform's only CTA barrier every thread has consumed the staged spectrum:
             // the next pair's copy is issued there (last query of the group)
             const bool last_q = b == p.nq - 1;
-            fx2::ifft4096(v, ex1, ex2, tid, seeds, [&]() {
+            fx2::ifft4096(v, ex, tid, seeds, [&]() {
                 if (b == 0 && tid == 96) {
                     const long long ns = (long long)p.i0 + (long long)gridDim.x + (long long)drawn;
                     s_npair[par] = (draw && ns < (long long)p.i1) ? fft_pair_of_slot(p, (int)ns) : -1;
@@ -631,8 +685,8 @@ __global__ void __launch_bounds__(fx2::THREADS, 2) fft_scan_kernel(const FftScan
                 // minimum over the thread's windows of the UPPER bound (scaled units); windows beyond T' are +inf
                 float mn = INF;
 #pragma unroll
-                for (int d = 0; d < 8; ++d) {
-                    const float2 yf = __half22float2(Ys[tid + 512 * d]);
+                for (int d = 0; d < 16; ++d) {
+                    const float2 yf = __half22float2(Ys[tid + 256 * d]);
                     const float2 ub2 = fx2::fma2(yf, make_float2(cu, cu), fx2::fma2(v[d], make_float2(m2, m2), yf));
                     mn = fminf(mn, fminf(ub2.x, ub2.y));
                 }
@@ -641,7 +695,7 @@ __global__ void __launch_bounds__(fx2::THREADS, 2) fft_scan_kernel(const FftScan
                 int bin = (int)(__float_as_uint(ub) >> 13) - hb;
                 bin = bin < 0 ? 0 : bin;
                 const bool cnt = ub < INF && bin < HB;   // false for +inf (no valid window) and NaN
-                seed_hist_flush(hq, reinterpret_cast<unsigned int *>(ex1), cnt ? bin : 0, cnt);
+                seed_hist_flush(hq, reinterpret_cast<unsigned int *>(ex), cnt ? bin : 0, cnt);
                 if (rerun) continue;
                 PSH_STAMP(1);
                 // one query: every increment of this CTA is ordered before its arrival (barrier + fence); wait
@@ -665,73 +719,18 @@ __global__ void __launch_bounds__(fx2::THREADS, 2) fft_scan_kernel(const FftScan
             const float thr = s_thr[b];
             const float tdiff = thr - base0;
             const float rhs = fmaf(fabsf(tdiff), 9.5367431640625e-7f, tdiff) * es;   // (+2^-20: roundings of rhs and of the fma below)
-            // v[d] = (D_a, D_b) of window kb + 512 d; the energies are stored in that order, both rows of the
+            // v[d] = (D_a, D_b) of window kb + 256 d; the energies are stored in that order, both rows of the
             // pair in one word: one FFMA2 per pair of windows
             float mn = INF;
 #pragma unroll
-            for (int d = 0; d < 8; ++d) {
-                const float2 val = fx2::fma2(v[d], make_float2(m2, m2), __half22float2(Ys[tid + 512 * d]));
+            for (int d = 0; d < 16; ++d) {
+                const float2 val = fx2::fma2(v[d], make_float2(m2, m2), __half22float2(Ys[tid + 256 * d]));
                 mn = fminf(mn, fminf(val.x, val.y));
             }
             const bool any = mn <= rhs;   // (+inf <= +inf while thr = +inf: sorted out per window below)
-            if (__any_sync(FULL, any)) {
-                unsigned int mask = 0;
-                if (any) {
-#pragma unroll
-                    for (int d = 0; d < 8; ++d) {
-                        const float2 yf = __half22float2(Ys[tid + 512 * d]);
-                        const float2 val = fx2::fma2(v[d], make_float2(m2, m2), yf);
-                        if (val.x <= rhs && yf.x < INF) mask |= 1u << d;
-                        if (val.y <= rhs && yf.y < INF) mask |= 1u << (8 + d);
-                    }
-                }
-                const int cnt = __popc(mask);
-                int incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int u = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += u;
-                }
-                const int total = __shfl_sync(FULL, incl, 31);
-                if (total > 0) {
-                    unsigned int basepos = 0;
-                    if (lane == 31) basepos = atomicAdd(&p.st[b].ccount, (unsigned int)total);
-                    basepos = __shfl_sync(FULL, basepos, 31);
-                    unsigned int pos = basepos + (unsigned int)(incl - cnt);
-                    unsigned int *dst = p.cand + (size_t)b * p.cap;
-                    // flat window index of local window 0 of each virtual row: row * T' + piece * hop
-                    const long long ra = 2 * (long long)pair, rb = ra + 1;   // virtual rows
-                    const unsigned int fa = (unsigned int)((unsigned long long)(ra / p.nsegv) * (unsigned long long)p.Tp
-                                                           + (unsigned long long)(ra % p.nsegv) * (unsigned long long)p.hop);
-                    const unsigned int fb = (unsigned int)((unsigned long long)(rb / p.nsegv) * (unsigned long long)p.Tp
-                                                           + (unsigned long long)(rb % p.nsegv) * (unsigned long long)p.hop);
-                    // the windows of a CTA's first pair were counted by the seeding pass already (one entry per
-                    // thread: its minimum); counting them again could count a window twice
-                    const bool count_ub = !(p.seed != 0 && iter == 0);
-#pragma unroll
-                    for (int d = 0; d < 8; ++d) {
-                        if (mask & (0x101u << d)) {
-                            const unsigned int t = (unsigned int)(kb + 512 * d);
-                            const float2 yf = __half22float2(Ys[tid + 512 * d]);
-                            const float2 ub2 = fx2::fma2(yf, make_float2(cu, cu), fx2::fma2(v[d], make_float2(m2, m2), yf));
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                if (mask & (1u << (8 * h + d))) {
-                                    if (pos < p.cap) dst[pos] = (h ? fb : fa) + t;
-                                    ++pos;
-                                    if (count_ub) {   // upper bound of the window's exact squared distance
-                                        const float u0 = h ? ub2.y : ub2.x;
-                                        const float ub = fmaxf((((u0 + 5.9604644775390625e-8f) * inv_es + base0) + 2.0f * slack) * 1.000001f, 0.0f);
-                                        const int bin = (int)(__float_as_uint(ub) >> 13) - hb;
-                                        if (ub < INF && bin < HB) hist_add_ub(hq, bin < 0 ? 0 : bin, 1u);
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-            __syncthreads();  // the exchange buffers (and, after the last query, the energy rows) may be overwritten
+            if (__any_sync(FULL, any))   // rare
+                fft_append_candidates(p, b, v, Ys, any, m2, cu, rhs, inv_es, base0, slack, pair, kb, !(p.seed != 0 && iter == 0));
+            __syncthreads();  // the exchange buffer (and, after the last query, the energy rows) may be overwritten
         }
         if (seeding && rerun) {
             // a group of queries: arrive, wait, derive every query's threshold, then the same pair again
