@@ -3,26 +3,31 @@
 (R=32768 x T=4096 synthetic Gaussian log-returns, W=252, H=20, k=1024, one query date per step).
 
   python bench.py --gpus N --steps K --warmup W            (our arm; torchrun for N > 1)
-  python bench.py --impl reference --gpus N --steps K ...  (CPU reference arm: oracle port)
+  python bench.py --impl reference --gpus N --steps K ...  (CPU reference arm)
+  python bench.py --scaling strong ...                     (the FIXED 32768-row ensemble split over the N ranks)
+  python bench.py --config cfg3 | cfg4 ...                 (BASELINE configs[2] / configs[3]; extra lines for profiles/)
 
 A "step" is one shadow scan of one query over the resident ensemble.  Prints ONE JSON line.
   value   : windows/s with the queries already in HBM: the K scans of the timed region are enqueued
             back to back through the C ABI (psh_scan_topk_f32 | PSH_FLAG_NOSYNC), alternating between
-            two streams with their own workspaces (query i+1's prologue and main launch overlap query
-            i's re-rank and select), and verified by ONE psh_scan_overflowed per workspace at the end
-            -- no host round trip between queries (CUDA events on the caller's stream, which joins
+            two streams with their own workspaces (query i+1's preparation and scan overlap query i's
+            re-rank, select and exchange) at EVERY N, and verified by ONE overflow check per workspace at
+            the end -- no host round trip between queries (CUDA events on the caller's stream, which joins
             both streams before the closing event)
   e2e     : windows/s through PathShadowing.shadow() with HOST numpy in/out, one call per step (pinned
             H2D of the query, scan, gather, D2H of distances+paths+indices, one synchronisation)
-  roofline: the scan kernels (seed + main launch) against the measured HBM peak
-            (MEASURED_PEAKS.json) -- plus the FP32-issue roof
-  cpu_baseline: the C oracle (port of the reference algorithm) on this box's host cores,
-            bounded row sample.
+  roofline: the scan kernel (ONE launch per query: it seeds its own threshold) against the measured HBM
+            peak (MEASURED_PEAKS.json); algorithmic bytes = the shard streamed once
+  cpu_baseline: the reference's own `cuda=False` path (unmodified package from baseline/_ref, torch on all
+            host threads) on a stated subsample -- kind "reference" -- with the C oracle port beside it
+  parity_checked: step 0's (distances, indices) of the timed pipeline compared bit for bit with the CPU
+            oracle: at N = 1 against a full scan of the shard; at N > 1 every rank checks the merged
+            result restricted to ITS rows against a full scan of its shard (together: the whole result)
   host_enqueue_ms_per_step: host time to enqueue one step (the device loop is GPU-bound while this
             stays below ms_per_step)
-N > 1: each rank holds its own 32768-row shard (weak scaling, ensemble = N*32768 rows); the per-rank
-top-k are exchanged over NVLink peer memory and merged by one kernel per step (NCCL all-gather +
-merge kernel if the peer mapping is unavailable).
+N > 1 (default, weak scaling): each rank holds its own 32768-row shard (ensemble = N*32768 rows); the
+per-rank top-k are exchanged over NVLink peer memory and merged by one kernel per step (NCCL all-gather
++ merge kernel if the peer mapping is unavailable).
 """
 from __future__ import annotations
 
@@ -41,8 +46,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-R_PER_GPU, T, W, H, K_NEIGH = 32768, 4096, 252, 20, 1024
-TP = T - W - H + 1
+R_FULL, T, W, H, K_NEIGH = 32768, 4096, 252, 20, 1024
 ALG_FLOP_PER_WINDOW = 3 * W           # exact mode: sub, mul, add per element
 METRIC = "shadowing windows/sec (R=32768xT=4096, W=252, k=1024)"
 
@@ -128,11 +132,31 @@ class ClockSampler(threading.Thread):
                 "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def make_shard(rank: int):
+# ---------------------------------------------------------------------------------------------
+# workloads (synthetic, SURVEY.md section 8d: CPU-generated so that oracle and GPU see identical bits)
+# ---------------------------------------------------------------------------------------------
+def workload(args, world: int):
+    """(rows per rank, T, description).  cfg2 weak: 32768 rows per rank; cfg2 strong: 32768 rows in total;
+    cfg4: 262144 rows x 8192 in total (BASELINE configs[3])."""
+    if args.config == "cfg4":
+        if 262144 % world:
+            raise SystemExit("cfg4 needs a rank count that divides 262144")
+        return 262144 // world, 8192, "BASELINE configs[3]: R=262144xT=8192 sharded over the ranks"
+    if args.scaling == "strong":
+        if R_FULL % world:
+            raise SystemExit("strong scaling needs a rank count that divides 32768")
+        return R_FULL // world, T, "BASELINE configs[1], the FIXED ensemble R=32768xT=4096 split over the ranks"
+    return R_FULL, T, "BASELINE configs[1]: R=32768xT=4096 per GPU"
+
+
+def make_rows(args, rank: int, world: int, rows: int, t_len: int):
     import torch
-    g = torch.Generator().manual_seed(0 + rank)
-    ds = torch.randn(R_PER_GPU, T, generator=g, dtype=torch.float32) * 0.01
-    return ds
+    if args.config != "cfg4" and args.scaling == "strong":
+        g = torch.Generator().manual_seed(0)       # the N = 1 ensemble; this rank keeps its block of rows
+        full = torch.randn(R_FULL, t_len, generator=g, dtype=torch.float32) * 0.01
+        return full[rank * rows:(rank + 1) * rows].clone()
+    g = torch.Generator().manual_seed(0 + rank)    # per-rank generation with seed 0 + rank
+    return torch.randn(rows, t_len, generator=g, dtype=torch.float32) * 0.01
 
 
 def make_queries(n: int):
@@ -142,65 +166,151 @@ def make_queries(n: int):
 
 
 def host_cores() -> int:
-    """Host threads this process may use (torchrun exports OMP_NUM_THREADS=1: the oracle is told the
-    thread count explicitly, so the CPU arm always runs on all the cores it can use)."""
+    """Host threads this process may use (torchrun exports OMP_NUM_THREADS=1: the CPU arms are told the
+    thread count explicitly, so they always run on all the cores they can use)."""
     try:
         return max(1, len(os.sched_getaffinity(0)))
     except AttributeError:
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_baseline_run(ds_np: np.ndarray, q_np: np.ndarray, target_s: float = 12.0):
-    """C oracle (all host threads) on a bounded sample of rows of the same workload."""
+# ---------------------------------------------------------------------------------------------
+# CPU arms: the reference's own cuda=False path (when its package is present) and the C oracle port
+# ---------------------------------------------------------------------------------------------
+def reference_available() -> bool:
+    from oracle import ref_loader
+    return ref_loader.available()
+
+
+def time_real_reference(ds_np: np.ndarray, q_np: np.ndarray, rows: int, n_splits: int, repeats: int = 1):
+    """The UNMODIFIED reference (RudyMorel/shadowing, PathShadowing.shadow(cuda=False),
+    path_shadowing.py:181) on the first `rows` trajectories; returns (seconds per call, windows, cores)."""
+    import torch
+    from oracle import ref_loader
+    ref = ref_loader.load()
+    cores = host_cores()
+    torch.set_num_threads(cores)
+    t_len = ds_np.shape[-1]
+    sub = np.ascontiguousarray(ds_np[:rows]).reshape(rows, 1, t_len)
+    obj = ref.path_shadowing.PathShadowing(ref.path_embedding.Identity(W), ref.path_distance.RelativeMSE(), sub,
+                                           ref.path_embedding.PredictionContext(H))
+    k = min(K_NEIGH, (rows // n_splits) * (t_len - W - H + 1))
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        obj.shadow(q_np.reshape(1, 1, W), k=k, n_splits=n_splits, cuda=False)
+        best = min(best, time.perf_counter() - t0)
+    return best, rows * (t_len - W - H + 1), cores, k
+
+
+def time_port(ds_np: np.ndarray, q_np: np.ndarray, rows: int):
     from oracle import oracle
     cores = host_cores()
-    rows = min(256 * max(cores // 8, 1), ds_np.shape[0])
+    t_len = ds_np.shape[-1]
     t0 = time.perf_counter()
     oracle.shadow_topk(ds_np[:rows], q_np, K_NEIGH, H, nthreads=cores)
-    dt = time.perf_counter() - t0
-    rate = rows * TP / dt
-    rows2 = int(min(ds_np.shape[0], max(rows, rate * target_s / TP)))
-    t0 = time.perf_counter()
-    oracle.shadow_topk(ds_np[:rows2], q_np, K_NEIGH, H, nthreads=cores)
-    dt = time.perf_counter() - t0
-    return {"value": rows2 * TP / dt, "unit": "windows/s", "cores": cores, "kind": "port",
-            "sample": f"first {rows2} of {ds_np.shape[0]} rows x T={T}, one query, W={W}, k={K_NEIGH}: "
-                      f"{rows2 * TP} windows in {dt:.2f} s (oracle/shadow_oracle.c, OpenMP, {cores} threads)"}
+    return time.perf_counter() - t0, rows * (t_len - W - H + 1), cores
+
+
+def cpu_baseline_run(ds_np: np.ndarray, q_np: np.ndarray):
+    """Bounded CPU sample of the same workload (10-30 s): the real reference on a row subsample when its
+    package is present (kind "reference"), the C oracle port on all rows next to it."""
+    dt_p, win_p, cores = time_port(ds_np, q_np, ds_np.shape[0])
+    port = {"value": win_p / dt_p, "unit": "windows/s", "cores": cores,
+            "sample": f"all {ds_np.shape[0]} rows x T={ds_np.shape[-1]}, one query: {win_p} windows in {dt_p:.2f} s "
+                      f"(oracle/shadow_oracle.c, OpenMP, {cores} threads)"}
+    if reference_available():
+        try:
+            time_real_reference(ds_np, q_np, 64, 1)                        # warm-up: imports, thread pool
+            dt, win, cores, k = time_real_reference(ds_np, q_np, 2048, 16)
+            return {"value": win / dt, "unit": "windows/s", "cores": cores, "kind": "reference",
+                    "sample": f"UNMODIFIED reference PathShadowing.shadow(cuda=False, n_splits=16), torch {cores} threads, "
+                              f"first 2048 of {ds_np.shape[0]} rows x T={ds_np.shape[-1]}, one query, W={W}, k={k}: "
+                              f"{win} windows in {dt:.2f} s", "port": port}
+        except Exception as e:   # the reference package is there but cannot run (missing dependency ...)
+            port["reference_error"] = repr(e)[:200]
+    port["kind"] = "port"
+    return port
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle
+    import torch
     cores = host_cores()
-    ds = make_shard(0).numpy()
+    g = torch.Generator().manual_seed(0)
+    ds = (torch.randn(R_FULL, T, generator=g, dtype=torch.float32) * 0.01).numpy()
     qs = make_queries(args.steps + args.warmup).numpy()
-    # bounded sample per step: ~2 s of CPU work, fixed across steps
-    rows = min(256 * max(cores // 8, 1), R_PER_GPU)
-    t0 = time.perf_counter()
-    oracle.shadow_topk(ds[:rows], qs[0], K_NEIGH, H, nthreads=cores)
-    rate = rows * TP / (time.perf_counter() - t0)
-    rows = int(min(R_PER_GPU, max(rows, rate * 2.0 / TP)))
-    for i in range(args.warmup):
-        oracle.shadow_topk(ds[:rows], qs[i], K_NEIGH, H, nthreads=cores)
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        oracle.shadow_topk(ds[:rows], qs[args.warmup + i], K_NEIGH, H, nthreads=cores)
-    dt = time.perf_counter() - t0
-    val = rows * TP * args.steps / dt
-    sample = (f"each step = first {rows} of {R_PER_GPU} rows x T={T}, one query (oracle/shadow_oracle.c port of "
-              f"path_shadowing.py:97-179, OpenMP {cores} threads)")
+    tp = T - W - H + 1
+    if reference_available():
+        # the reference's own code, bounded sample per step (~2-4 s on 16 threads)
+        rows, n_splits = 1024, 8
+        time_real_reference(ds, qs[0], 64, 1)
+        for i in range(args.warmup):
+            time_real_reference(ds, qs[i], rows, n_splits)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            _, win, cores, k = time_real_reference(ds, qs[args.warmup + i], rows, n_splits)
+        dt = time.perf_counter() - t0
+        kind = "reference"
+        sample = (f"each step = UNMODIFIED reference PathShadowing.shadow(cuda=False, n_splits={n_splits}) on the first "
+                  f"{rows} of {R_FULL} rows x T={T}, one query, k={k}, torch {cores} threads (path_shadowing.py:181)")
+    else:
+        from oracle import oracle
+        rows = min(256 * max(cores // 8, 1), R_FULL)
+        t0 = time.perf_counter()
+        oracle.shadow_topk(ds[:rows], qs[0], K_NEIGH, H, nthreads=cores)
+        rate = rows * tp / (time.perf_counter() - t0)
+        rows = int(min(R_FULL, max(rows, rate * 2.0 / tp)))
+        for i in range(args.warmup):
+            oracle.shadow_topk(ds[:rows], qs[i], K_NEIGH, H, nthreads=cores)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            oracle.shadow_topk(ds[:rows], qs[args.warmup + i], K_NEIGH, H, nthreads=cores)
+        dt = time.perf_counter() - t0
+        kind = "port"
+        sample = (f"each step = first {rows} of {R_FULL} rows x T={T}, one query (oracle/shadow_oracle.c port of "
+                  f"path_shadowing.py:97-179, OpenMP {cores} threads; the reference package is not installed)")
+    val = rows * tp * args.steps / dt
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "windows/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "BASELINE configs[1]: R=32768xT=4096 Gaussian dlnx, W=252, H=20, k=1024, "
-                               "Identity+RelativeMSE, one query per step", "sample_rows": rows},
-        "cpu_baseline": {"value": val, "unit": "windows/s", "cores": cores, "kind": "port", "sample": sample},
+                               "Identity+RelativeMSE, one query per step", "sample_rows": rows,
+                   "arm": "the reference's own cuda=False path" if kind == "reference" else "C/OpenMP port of the reference"},
+        "cpu_baseline": {"value": val, "unit": "windows/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def check_parity(dist_dev, idx_dev, ds_np, q_np, rank: int, world: int, rows: int, tp: int):
+    """Bit-exact comparison of a merged (dist, idx) with the oracle, restricted to this rank's rows:
+    every returned record whose trajectory lives here must be in the oracle's scan of the local shard with
+    the same distance bits, and every local record ordered before the k-th merged record must have been
+    returned.  Over all ranks this covers the whole result."""
+    from oracle import oracle
+    d = dist_dev.detach().cpu().numpy()[0]
+    idx = idx_dev.detach().cpu().numpy()[0]
+    lo = rank * rows
+    k_loc = min(K_NEIGH, rows * tp)
+    do, io = oracle.shadow_topk(ds_np, q_np, k_loc, H, row_offset=lo, nthreads=host_cores())
+    do, io = do[0], io[0]
+    if world == 1:
+        return bool(np.array_equal(d.view(np.uint32), do.view(np.uint32)) and np.array_equal(idx, io))
+    flat = lambda ii: ii[:, 0].astype(np.int64) * tp + ii[:, 1].astype(np.int64)
+    dk, fk = int(d[-1:].view(np.uint32)[0]), int(flat(idx[-1:])[0])          # the k-th merged record
+    mine = (idx[:, 0] >= lo) & (idx[:, 0] < lo + rows)
+    got = set(zip(d[mine].view(np.uint32).tolist(), map(tuple, idx[mine].tolist())))
+    dbo, fo = do.view(np.uint32).astype(np.int64), flat(io)
+    before = (dbo < dk) | ((dbo == dk) & (fo <= fk))                          # local records ordered up to it
+    want = set(zip(do[before].view(np.uint32).tolist(), map(tuple, io[before].tolist())))
+    return bool(got == want and (np.diff(d.view(np.uint32).astype(np.int64)) >= 0).all())
 
 
 def run_ours(args):
@@ -219,14 +329,16 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
 
-    ds_host = make_shard(rank)
+    rows_n, t_len, wl_name = workload(args, world)
+    tp = t_len - W - H + 1
+    ds_host = make_rows(args, rank, world, rows_n, t_len)
     nq = args.steps + args.warmup
-    qs_host = make_queries(nq)
+    qs_host = make_queries(max(nq, 256))
     qs_pinned = qs_host.clone().pin_memory()
     obj = sb.PathShadowing(sb.Identity(W), sb.RelativeMSE(), ds_host, sb.PredictionContext(H), device=dev,
-                           row_offset=rank * R_PER_GPU, process_group=pg, scan_mode=args.mode)
+                           row_offset=rank * rows_n, process_group=pg, scan_mode=args.mode)
     rows, _ = obj._resident_rows()
-    obj._pipe_streams = max(1, args.streams) if world == 1 else 1
+    obj._pipe_streams = max(1, args.streams)       # the same pipeline at every N
     qs_dev = qs_host.to(dev)
     torch.cuda.synchronize()
 
@@ -236,11 +348,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.config == "cfg3":
+        return run_cfg3(args, obj, qs_host, ds_host, rank, world, rows_n, tp, barrier, dev)
+
     def step_device(i):
-        # enqueue only: the K scans of the timed region form one pipeline on the stream (no host
+        # enqueue only: the K scans of the timed region form one pipeline on the stream(s) (no host
         # round trip between queries); `_check_pipeline` synchronises once and verifies that no
         # scan overflowed its candidate buffers (it would have to be repeated)
-        return obj._scan_device(qs_dev[i:i + 1], rows, T, K_NEIGH, nosync=True)
+        return obj._scan_device(qs_dev[i:i + 1], rows, t_len, K_NEIGH, nosync=True)
 
     def step_e2e(i):
         return obj.shadow(qs_pinned[i:i + 1], k=K_NEIGH)
@@ -256,14 +371,20 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     th0 = time.perf_counter()
+    first = None
     for i in range(args.steps):
-        step_device(args.warmup + i)
+        out = step_device(args.warmup + i)
+        if i == 0:
+            first = out
     host_enqueue_ms = (time.perf_counter() - th0) * 1e3 / args.steps   # host time to enqueue one step
     obj._check_pipeline()
     e1.record()
     barrier()
     ms_dev = e0.elapsed_time(e1)
     launches = _lib.launch_count() - n0
+
+    # ---------------- parity of the timed pipeline's first step (every rank, its own rows) ----------------
+    ok = check_parity(first[0], first[1], ds_host.numpy(), qs_host[args.warmup].numpy(), rank, world, rows_n, tp)
 
     # ---------------- end-to-end timing (host buffers in and out) ----------------
     for i in range(min(args.warmup, 3)):
@@ -284,6 +405,9 @@ def run_ours(args):
     pipe_streams = obj._pipe_streams
     obj._pipe_streams = 1
     L = _lib.lib()
+    for i in range(2):
+        step_device(i)
+    obj._check_pipeline()
     L.psh_profile_begin()
     for i in range(args.steps):
         step_device(args.warmup + i)
@@ -293,46 +417,43 @@ def run_ours(args):
     obj._check_pipeline()
     torch.cuda.synchronize()
 
-    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_dev, ms_e2e, 0.0 if ok else 1.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    ms_dev, ms_e2e, bad = float(t[0]), float(t[1]), float(t[2])
 
     eff_mode = "fft" if args.mode == "auto" else args.mode
     if rank == 0:
-        windows_per_step = world * R_PER_GPU * TP
+        windows_per_step = world * rows_n * tp
         value = windows_per_step * args.steps / (ms_dev * 1e-3)
         e2e = windows_per_step * args.steps / (ms_e2e * 1e-3)
         hbm_peak, peak_kind, sm_max = peaks()
         scan_ms_per_step = ms_kind[0] / args.steps
-        alg_bytes = R_PER_GPU * T * 4  # the shard streamed once per query pass (4.283 B/window)
+        alg_bytes = rows_n * t_len * 4  # the shard streamed once per query pass (4.283 B/window at cfg2)
         ach = alg_bytes / (scan_ms_per_step * 1e-3) / 1e9
         traffic = None
-        tp = ROOT / "profiles" / "traffic.json"
-        if tp.exists():
+        tpath = ROOT / "profiles" / "traffic.json"
+        if tpath.exists() and args.config == "cfg2" and rows_n == R_FULL:
             try:
-                traffic = json.loads(tp.read_text()).get("scan_dram_bytes_per_step")
+                traffic = json.loads(tpath.read_text()).get("scan_dram_bytes_per_step")
             except Exception:
                 traffic = None
-        eff_mode = "fft" if args.mode == "auto" else args.mode
-        # fp32 lane-ops per window actually issued by the scan flavour (exact: sub+mul+add per
-        # element; filter: one FMA per element; fft: ~1.6 k FP instructions per thread per pair of
-        # trajectories / 7650 windows, counted from SASS)
-        flop_per_win = {"exact": ALG_FLOP_PER_WINDOW, "filter": W, "fft": 27}[eff_mode]
         sm_clk = (clocks.get("sm_mhz") or sm_max) * 1e6
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-        fp32_rate = R_PER_GPU * TP * flop_per_win / (scan_ms_per_step * 1e-3)
+        metric = METRIC if args.config == "cfg2" else f"shadowing windows/sec ({wl_name})"
         out = {
-            "metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps,
+            "metric": metric, "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: R=32768xT=4096 Gaussian dlnx per GPU, W=252, H=20, "
-                                   "k=1024, Identity+RelativeMSE, one query date per step",
-                       "rows_per_gpu": R_PER_GPU, "scan_mode": eff_mode,
-                       "l2": "512 MiB shard per GPU > 126 MB L2 (inputs larger than L2)",
+            "scaling": "strong" if (args.scaling == "strong" or args.config == "cfg4") else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "parity_checked": bad == 0.0,
+            "config": {"workload": f"{wl_name}, Gaussian dlnx, W=252, H=20, k=1024, Identity+RelativeMSE, one query date per step",
+                       "rows_per_gpu": rows_n, "T": t_len, "scan_mode": eff_mode,
+                       "l2": f"{rows_n * t_len * 4 >> 20} MiB shard per GPU vs 126 MB L2 (every query streams the whole shard)",
                        "dataset": "resident in HBM (uploaded once at construction)",
                        "timing": f"K enqueue-only scans pipelined on {pipe_streams} stream(s) + one overflow check (value); "
                                  "one synchronous shadow() per step (e2e)",
+                       "parity": "step 0 of the timed pipeline vs the C oracle, bit-exact, every rank on its own rows",
                        "parallelism": f"rows sharded x{world}, peer-memory all-gather fused with the merge of per-GPU top-k"},
             "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": W * 4,
                     "d2h_bytes_per_step": int(d_np.nbytes + p_np.nbytes + i_np.nbytes),
@@ -342,20 +463,62 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                          "traffic": traffic, "peak_kind": peak_kind,
-                         "kernel": "scan kernels of one step (all chunk launches)",
+                         "kernel": "fft_scan_kernel (one launch per query; seeds its own threshold)",
                          "kernel_ms_per_step": scan_ms_per_step, "kernel_launches_per_step": n_kind[0] / args.steps,
                          "select_ms_per_step": ms_kind[1] / args.steps,
                          "merge_ms_per_step": ms_kind[2] / args.steps,
                          "alg_bytes_per_step": alg_bytes,
-                         "fp32": {"note": "binding roof (SURVEY 8d): lane-ops/s vs SMs*128*clock",
-                                  "flop_per_window": flop_per_win, "achieved_tlaneops": fp32_rate / 1e12,
-                                  "peak_tlaneops_at_sampled_clock": n_sm * 128 * sm_clk / 1e12,
-                                  "frac": fp32_rate / (n_sm * 128 * sm_clk)}},
+                         "note": "traffic: dram__bytes_read+write of the same kernel from the round's ncu --set full "
+                                 "capture (profiles/traffic.json); achieved: algorithmic bytes / CUDA-event duration"},
         }
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and args.config == "cfg2":
             out["cpu_baseline"] = cpu_baseline_run(ds_host.numpy(), qs_host[0].numpy())
         print(json.dumps(out))
     if world > 1:
+        dist.destroy_process_group()
+
+
+def run_cfg3(args, obj, qs_host, ds_host, rank, world, rows_n, tp, barrier, dev):
+    """BASELINE configs[2]: 256 query dates per step, predict_from_paths realised variance Ts=[5,10,20],
+    softmax eta=0.1, everything on the device (only the (256, 3) predictions leave it)."""
+    import torch
+    import shadowing_b200 as sb
+    from oracle import oracle
+    B = 256
+    q = qs_host[:B]
+    rv = sb.RealizedVariance([5, 10, 20], vol=False)
+    for _ in range(max(1, min(args.warmup, 3))):
+        pred, pstd = obj.predict(q, k=K_NEIGH, to_predict=rv, eta=0.1, proba_name="softmax")
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    steps = max(1, min(args.steps, 5))
+    for _ in range(steps):
+        pred, pstd = obj.predict(q, k=K_NEIGH, to_predict=rv, eta=0.1, proba_name="softmax")
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    # sampled parity: 4 queries against full oracle scans, their predictions against the numpy restatement
+    ok = True
+    if world == 1:
+        dsn = ds_host.numpy()
+        for b in (0, 31, 32, 255):
+            d, paths, idx = obj.shadow(q[b:b + 1], k=K_NEIGH)
+            do, po, io = oracle.shadow(dsn.reshape(rows_n, 1, -1), q[b:b + 1].numpy(), K_NEIGH, H)
+            mo, so = oracle.predict_from_paths(do, po, H, [5, 10, 20], False, "softmax", 0.1)
+            ok = ok and np.array_equal(d.view(np.uint32), do.view(np.uint32)) and np.array_equal(idx, io)
+            ok = ok and np.allclose(pred[b], mo[0], rtol=1e-6, atol=0) and np.allclose(pstd[b], so[0], rtol=1e-5, atol=0)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "shadowing query-windows/sec (BASELINE configs[2]: 256 query dates, R=32768xT=4096, W=252, k=1024, "
+                      "predict_from_paths RV Ts=[5,10,20], softmax eta=0.1)",
+            "value": B * world * rows_n * tp / (ms * 1e-3), "unit": "windows/s", "n_gpus": world, "steps": steps,
+            "ms_per_step": ms, "ms_per_query": ms / B, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+            "parity_checked": bool(ok),
+            "config": {"workload": "one PathShadowing.predict() call with 256 contexts per step; sampled queries vs the C oracle "
+                                   "(indices bit-exact, predictions 1e-6)", "rows_per_gpu": rows_n}}))
+    if world > 1:
+        import torch.distributed as dist
         dist.destroy_process_group()
 
 
@@ -366,9 +529,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="auto", choices=["auto", "fft", "filter", "exact"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's metric): 32768 rows per GPU; strong: 32768 rows in total")
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--streams", type=int, default=int(os.environ.get("PSH_STREAMS", "2")),
-                    help="streams the pipelined device loop alternates between (N = 1 only; 1: the caller's stream)")
+                    help="streams the pipelined device loop alternates between (1: the caller's stream)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -2,9 +2,10 @@
 
 Imports the unmodified reference modules from /root/reference with (i) a name-only stub of
 the un-vendored `scatspectra` dependency (`path_shadowing.py:9`) and (ii) a synthetic parent
-package so `shadowing/__init__.py:1-4` (matplotlib, PDV) is skipped.  Only usable in the
-build container (the GPU box has no /root/reference); used by `tests/gen_golden.py` to
-produce the committed fixtures under `tests/golden/` and by the container-only pin tests.
+package so `shadowing/__init__.py:1-4` (matplotlib, PDV) is skipped.  Sources: /root/reference (build container) or
+`baseline/_ref` (the same package pip-installed by the builder; it travels to the GPU box).  Used by
+`tests/gen_golden.py` to produce the committed fixtures under `tests/golden/`, by the pin tests, and by
+bench.py's CPU legs to time the reference's own `cuda=False` path beside the GPU.
 Nothing in the product package imports this file.
 """
 import importlib
@@ -12,7 +13,11 @@ import sys
 import types
 from pathlib import Path
 
-REF_ROOT = Path("/root/reference")
+# the build container mounts the reference at /root/reference; `baseline/_ref` holds the same unmodified
+# package installed with pip (git-ignored, but it travels to the GPU box with the snapshot)
+_CANDIDATES = [Path("/root/reference"), Path(__file__).resolve().parents[1] / "baseline" / "_ref"]
+REF_ROOT = next((c for c in _CANDIDATES if (c / "shadowing" / "path_shadowing" / "path_shadowing.py").is_file()),
+                _CANDIDATES[0])
 
 
 def available() -> bool:

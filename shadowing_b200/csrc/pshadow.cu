@@ -1061,17 +1061,20 @@ __global__ void __launch_bounds__(SEL_THREADS) merge_kernel(const float *d_parts
 // ------------------------------------------------------------------------------------------
 // all-gather over NVLink peer memory fused with the merge (multi-GPU, one process per GPU).
 // Every rank owns an exchange buffer that all other ranks have mapped (CUDA IPC):
-//     [epoch % 3][ records (G, B, k, 3) int32 | flags (G, B) uint32 ]
+//     [epoch % 4][ records (G, B, k, 3) int32 | flags (G, B) uint32 ]
 // CTA b of rank r stores query b's k packed records into slot r of EVERY rank's buffer (plain
 // stores over NVLink), fences (system scope), then raises flag (r, b) on every rank with the
 // step's epoch; it then waits until the G flags of query b in its OWN buffer carry the epoch
 // and merges the G*k records exactly like merge_kernel.  One launch replaces ncclAllGather +
-// merge_kernel.  Three buffers rotate with the epoch: in the split form (send of step i+1 enqueued
-// BEFORE the wait + merge of step i) a rank may be writing step i+2 while a peer still merges step i.
+// merge_kernel.  Four buffers rotate with the epoch (see XCHG_PARITIES).
 // A peer that never arrives (crashed rank) raises bit 1 of `flag` after `timeout_ns` instead of
 // hanging the GPU.
 // ------------------------------------------------------------------------------------------
 constexpr int XCHG_MAX_PEERS = 16;
+// Buffers rotate over 4 epochs.  One stream of fused send+merge launches needs 2 (a rank's step e+2 follows
+// its step e+1, which needed every peer's send e+1, which follows that peer's merge e).  Two streams that
+// alternate steps need 2 per stream, and so does the split form (send e+1 enqueued before merge e).
+constexpr int XCHG_PARITIES = 4;
 struct XchgParams {
     int *rec[XCHG_MAX_PEERS];            // this parity's record area on every rank
     unsigned int *flags[XCHG_MAX_PEERS]; // this parity's flag area on every rank
@@ -1135,20 +1138,26 @@ __global__ void __launch_bounds__(SEL_THREADS) xchg_merge_kernel(const XchgParam
 // memory, the output (r, t) is recovered from the flat index.  Needs G*k*12 bytes of shared memory
 // (else xchg_merge_kernel runs).  The record area of the exchange buffer is sized for this form.
 // ------------------------------------------------------------------------------------------
+// grid = (G, B): CTA (g, b) stores query b's records into rank g's buffer, then -- like its G - 1 siblings,
+// each on its own SM -- polls ALL G record lists of query b out of this rank's buffer (the loads of a batch
+// of records are issued together and validated afterwards: one L2 round trip per batch, not per word) and
+// places the records of list g only (merge by rank: position = own index + the number of records of the
+// other lists ordered before it).  Round 1 ran ONE CTA per query: G sequential remote-store loops, word-by-
+// word polling and the whole merge on one SM (0.076 ms at G = 8).
+constexpr int LL_BATCH = 4;   // records polled per thread and round trip (12 words in flight)
+
 __global__ void __launch_bounds__(SEL_THREADS) xchg_ll_kernel(const XchgParams x, int B, unsigned int k,
                                                                unsigned long long Tp, float *out_d, int *out_idx,
                                                                int *flag, int phases) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const unsigned int n3 = k * 3u;
     const unsigned long long tag = (unsigned long long)x.epoch << 32;
     if (phases & 1) {
         const int *src = x.local_rec + (size_t)b * n3;
-        for (int g = 0; g < x.G; ++g) {
-            volatile unsigned long long *dst =
-                reinterpret_cast<volatile unsigned long long *>(x.rec[g]) + ((size_t)x.rank * B + b) * n3;
-            for (unsigned int i = tid; i < n3; i += SEL_THREADS) dst[i] = tag | (unsigned int)src[i];
-        }
+        volatile unsigned long long *dst =
+            reinterpret_cast<volatile unsigned long long *>(x.rec[g]) + ((size_t)x.rank * B + b) * n3;
+        for (unsigned int i = tid; i < n3; i += SEL_THREADS) dst[i] = tag | (unsigned int)src[i];
     }
     if (!(phases & 2)) return;
     const unsigned int n = (unsigned int)x.G * k;
@@ -1157,33 +1166,46 @@ __global__ void __launch_bounds__(SEL_THREADS) xchg_ll_kernel(const XchgParams x
     const volatile unsigned long long *mine = reinterpret_cast<const volatile unsigned long long *>(x.rec[x.rank]);
     const unsigned long long t0 = globaltimer_ns();
     bool timed_out = false;
-    for (unsigned int i = tid; i < n; i += SEL_THREADS) {
-        const unsigned int g = i / k, j = i - g * k;
-        const volatile unsigned long long *w = mine + (((size_t)g * B + b) * k + j) * 3;
-        unsigned int v[3];
+    for (unsigned int i0 = tid; i0 < n; i0 += SEL_THREADS * LL_BATCH) {
+        unsigned long long word[LL_BATCH][3];
+        const volatile unsigned long long *wp[LL_BATCH];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            unsigned long long word = w[c];
-            while ((word >> 32) != x.epoch && !timed_out) {
-                if (globaltimer_ns() - t0 > x.timeout_ns) { timed_out = true; break; }
-                __nanosleep(64);
-                word = w[c];
-            }
-            v[c] = (unsigned int)word;
+        for (int u = 0; u < LL_BATCH; ++u) {
+            const unsigned int i = i0 + u * SEL_THREADS;
+            const unsigned int gg = i < n ? i / k : 0u, j = i < n ? i - gg * k : 0u;
+            wp[u] = mine + (((size_t)gg * B + b) * k + j) * 3;
         }
-        if (flag != nullptr && v[0] == 0xffffffffu) atomicOr(flag, 1);   // a shard overflowed
-        db[i] = v[0];
-        fl[i] = (unsigned long long)v[1] * Tp + (unsigned long long)v[2];
+#pragma unroll
+        for (int u = 0; u < LL_BATCH; ++u)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) word[u][c] = wp[u][c];
+#pragma unroll
+        for (int u = 0; u < LL_BATCH; ++u) {
+            const unsigned int i = i0 + u * SEL_THREADS;
+            if (i >= n) continue;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                while ((word[u][c] >> 32) != x.epoch && !timed_out) {
+                    if (globaltimer_ns() - t0 > x.timeout_ns) { timed_out = true; break; }
+                    __nanosleep(64);
+                    word[u][c] = wp[u][c];
+                }
+            }
+            const unsigned int v0 = (unsigned int)word[u][0];
+            if (flag != nullptr && v0 == 0xffffffffu && g == 0) atomicOr(flag, 1);   // a shard overflowed
+            db[i] = v0;
+            fl[i] = (unsigned long long)(unsigned int)word[u][1] * Tp + (unsigned long long)(unsigned int)word[u][2];
+        }
     }
     if (timed_out && flag != nullptr) atomicOr(flag, 2);
     __syncthreads();
-    for (unsigned int i = tid; i < n; i += SEL_THREADS) {
-        const unsigned int g = i / k, j = i - g * k;
+    for (unsigned int j = tid; j < k; j += SEL_THREADS) {   // the records of list g
+        const unsigned int i = (unsigned int)g * k + j;
         const unsigned int dk = db[i];
         const unsigned long long fk = fl[i];
         unsigned int rank = j;
         for (unsigned int g2 = 0; g2 < (unsigned int)x.G && rank < k; ++g2) {
-            if (g2 == g) continue;
+            if (g2 == (unsigned int)g) continue;
             const unsigned int base = g2 * k;
             unsigned int lo = 0, hi = k;
             while (lo < hi) {
@@ -1192,7 +1214,7 @@ __global__ void __launch_bounds__(SEL_THREADS) xchg_ll_kernel(const XchgParams x
                 bool before = d2 < dk;
                 if (d2 == dk) {
                     const unsigned long long f2 = fl[base + mid];
-                    before = f2 < fk || (f2 == fk && g2 < g);
+                    before = f2 < fk || (f2 == fk && g2 < (unsigned int)g);
                 }
                 if (before) lo = mid + 1; else hi = mid;
             }
@@ -1658,7 +1680,7 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
     if (use_fft) {
         // query state + spectrum of the vector the trajectories are correlated with (the context itself,
         // or g = K^T ex for an embedded scan) + a clean threshold histogram: ONE launch
-        qfft_kernel<<<dim3(fftx::N / QFFT_K, nq), 4 * QFFT_K, (size_t)W * sizeof(double), stream>>>(
+        qfft_kernel<<<dim3(fftx::N / QFFT_K, nq), QFFT_THREADS, (size_t)W * sizeof(double), stream>>>(
             d_q, qlen, emb ? emb->g : d_q, W, aux->tw64, qspec, st, fhist, qmaxp);
     } else {
         qprep_kernel<<<(nq + 3) / 4, 128, 0, stream>>>(d_q, qlen, nq, st);
@@ -2067,7 +2089,7 @@ static size_t xchg_flag_bytes(int G, int B) { return align_up((size_t)G * B * si
 
 size_t psh_xchg_bytes(int G, int B, int64_t k) {
     if (G <= 0 || G > XCHG_MAX_PEERS || B <= 0 || k <= 0) return 0;
-    return 3 * (xchg_rec_bytes(G, B, k) + xchg_flag_bytes(G, B));
+    return XCHG_PARITIES * (xchg_rec_bytes(G, B, k) + xchg_flag_bytes(G, B));
 }
 
 int psh_xchg_create(size_t bytes, void **d_buf, unsigned char *handle64) {
@@ -2115,7 +2137,7 @@ static int xchg_launch(const int32_t *d_rec_local, void *const *bufs, int G, int
     if (n > 0x7fffffffull) return PSH_E_TOO_LARGE;
     XchgParams x;
     const size_t rb = xchg_rec_bytes(G, B, k), fb = xchg_flag_bytes(G, B);
-    const size_t par = (size_t)(epoch % 3u) * (rb + fb);
+    const size_t par = (size_t)(epoch % (unsigned int)XCHG_PARITIES) * (rb + fb);
     for (int g = 0; g < G; ++g) {
         if (!bufs[g]) return PSH_E_ARG;
         unsigned char *base = static_cast<unsigned char *>(bufs[g]) + par;
@@ -2135,8 +2157,8 @@ static int xchg_launch(const int32_t *d_rec_local, void *const *bufs, int G, int
         const size_t smem_ll = (phases & 2) ? (size_t)n * 12 : 0;
         {
             ProfScope ps_merge(stream, 2);
-            xchg_ll_kernel<<<B, SEL_THREADS, smem_ll, stream>>>(x, B, (unsigned int)k, (unsigned long long)Tp, d_out_dist,
-                                                                d_out_idx, d_flag, phases);
+            xchg_ll_kernel<<<dim3(G, B), SEL_THREADS, smem_ll, stream>>>(x, B, (unsigned int)k, (unsigned long long)Tp,
+                                                                         d_out_dist, d_out_idx, d_flag, phases);
         }
         PSH_LAUNCHED();
         return PSH_OK;

@@ -260,7 +260,6 @@ constexpr int H_THR = HB + HC;              // published threshold (float bits, 
 constexpr int H_ARR = HB + HC + 1;          // seed arrivals of the launch (query 0's slot)
 constexpr int H_SLOT = HB + HC + 2;         // dynamic pair-slot counter of the launch (query 0's slot)
 constexpr int HSTRIDE = HB + HC + 32;       // uints per query
-constexpr int QMAXP = 64;                   // per-query partial maxima of |FFT(q)| written by qfft_kernel's blocks
 
 __device__ __forceinline__ int hist_base(float q2) { return (int)(__float_as_uint(8.0f * q2) >> 13) - HB; }
 // one entry (`n` of them in the same bin) for the upper bound ub >= 0
@@ -272,8 +271,12 @@ __device__ __forceinline__ void hist_add_ub(unsigned int *hq, int bin, unsigned 
 // conj(FFT_4096(g padded))/4096 per query (direct fp64 DFT on the exact twiddle table), max_k |G_k|, and
 // the query state: ||q|| in torch's contiguous-reduction order, Q2, ||g||; zeroes the query's histogram.
 // g is the correlated vector: the context itself (Identity) or K^T ex (embedded scan, q = ex).
-// grid = (4096/64, nq): 64 frequencies per CTA, 4 threads share one frequency.
-constexpr int QFFT_K = 64;
+// grid = (4096/16, nq): 16 frequencies per CTA, 16 threads share one frequency (256 CTAs: the whole
+// GPU works on one query's 10^6 fp64 multiply-adds; with 64 CTAs it took 13 us).
+constexpr int QFFT_K = 16;
+constexpr int QFFT_PARTS = 16;
+constexpr int QFFT_THREADS = QFFT_K * QFFT_PARTS;   // 256
+constexpr int QMAXP = fftx::N / QFFT_K;             // per-query partial maxima of |FFT(q)|, one per CTA
 
 __device__ __forceinline__ void qstate_init(const float *__restrict__ x, int n, QState *st, float gnorm) {
     // one warp; lanes 0..7 own torch's 8 interleaved partial sums (path_distance.py:65 `x.norm(dim=-1)`)
@@ -310,17 +313,17 @@ __device__ __forceinline__ void qstate_init(const float *__restrict__ x, int n, 
     }
 }
 
-__global__ void __launch_bounds__(4 * QFFT_K) qfft_kernel(const float *__restrict__ q, int qlen,
-                                                          const float *__restrict__ g, int W,
-                                                          const double2 *__restrict__ tw64, float2 *Qc, QState *st,
-                                                          unsigned int *hist, float *qmaxp) {
+__global__ void __launch_bounds__(QFFT_THREADS) qfft_kernel(const float *__restrict__ q, int qlen,
+                                                            const float *__restrict__ g, int W,
+                                                            const double2 *__restrict__ tw64, float2 *Qc, QState *st,
+                                                            unsigned int *hist, float *qmaxp) {
     extern __shared__ double qd[];
-    __shared__ double red[4 * QFFT_K / 32];
+    __shared__ double red[QFFT_THREADS / 32];
     const int b = blockIdx.y, tid = threadIdx.x;
-    for (int j = tid; j < W; j += 4 * QFFT_K) qd[j] = (double)g[(size_t)b * W + j];
+    for (int j = tid; j < W; j += QFFT_THREADS) qd[j] = (double)g[(size_t)b * W + j];
     // this query's threshold histogram starts at zero, its published threshold at +inf
     unsigned int *hq = hist + (size_t)b * HSTRIDE;
-    if (tid < HB / (fftx::N / QFFT_K)) hq[blockIdx.x * (HB / (fftx::N / QFFT_K)) + tid] = 0u;
+    if (tid < HB / QMAXP) hq[blockIdx.x * (HB / QMAXP) + tid] = 0u;
     if (blockIdx.x == 0 && tid < HSTRIDE - HB) hq[HB + tid] = (HB + tid == H_THR) ? 0x7f800000u : 0u;
     __syncthreads();
     if (blockIdx.x == 0 && tid < 32) {   // ||g||_2 of the correlated vector, rounded up; the query state
@@ -330,18 +333,21 @@ __global__ void __launch_bounds__(4 * QFFT_K) qfft_kernel(const float *__restric
         for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(FULL, s2, o);
         qstate_init(q + (size_t)b * qlen, qlen, st + b, __double2float_ru(sqrt(s2) * (1.0 + 1e-7)));
     }
-    const int k = blockIdx.x * QFFT_K + (tid >> 2), part = tid & 3;
-    const int per = (W + 3) / 4;
+    const int k = blockIdx.x * QFFT_K + tid / QFFT_PARTS, part = tid % QFFT_PARTS;
+    const int per = (W + QFFT_PARTS - 1) / QFFT_PARTS;
     const int j0 = part * per, j1 = min(W, j0 + per);
     double re = 0.0, im = 0.0;
-#pragma unroll 8
+#pragma unroll 4
     for (int j = j0; j < j1; ++j) {
         const double2 w = __ldg(tw64 + ((j * k) & (fftx::N - 1)));  // exp(+i theta): G_k = sum g_j exp(-i theta)
         re += qd[j] * w.x;
         im -= qd[j] * w.y;
     }
-    re += __shfl_xor_sync(FULL, re, 1); im += __shfl_xor_sync(FULL, im, 1);
-    re += __shfl_xor_sync(FULL, re, 2); im += __shfl_xor_sync(FULL, im, 2);
+#pragma unroll
+    for (int o = 1; o < QFFT_PARTS; o <<= 1) {
+        re += __shfl_xor_sync(FULL, re, o);
+        im += __shfl_xor_sync(FULL, im, o);
+    }
     if (part == 0) Qc[(size_t)b * fftx::N + k] = make_float2((float)(re / fftx::N), (float)(-im / fftx::N));
     double mx = re * re + im * im;
 #pragma unroll
@@ -349,7 +355,7 @@ __global__ void __launch_bounds__(4 * QFFT_K) qfft_kernel(const float *__restric
     if ((tid & 31) == 0) red[tid >> 5] = mx;
     __syncthreads();
     if (tid == 0) {
-        for (int i = 1; i < 4 * QFFT_K / 32; ++i) mx = fmax(mx, red[i]);
+        for (int i = 1; i < QFFT_THREADS / 32; ++i) mx = fmax(mx, red[i]);
         qmaxp[(size_t)b * QMAXP + blockIdx.x] = __double2float_ru(sqrt(mx) * (1.0 + 1e-7));
     }
 }
@@ -565,6 +571,9 @@ __device__ __forceinline__ void fft_append_candidates(const FftScanParams &p, in
 // (one query: the transform's output is still in registers; a group of queries: the pair is transformed
 // again).  This replaces round 1's separate seed launch.
 //
+// (Measured and rejected: ONE barrier per transform -- two alternating exchange buffers, the energy copy
+// issued behind the barrier of its own pair -- 0.251 ms against 0.232 ms.)
+//
 // The small per-pair chores are spread over the warps (a warp that does all of them is late at every
 // barrier): warp 0 issues the spectrum copy, warp 1 picks up published thresholds, warp 2 issues the
 // energy copy, warp 3 draws the next pair, warp 4 re-derives thresholds.
@@ -597,10 +606,16 @@ __global__ void __launch_bounds__(fx2::THREADS, 2) fft_scan_kernel(const FftScan
         s_thr[tid] = EMB ? t0 * p.thr_widen : t0;
         s_q2[tid] = p.st[tid].q2;
         s_gn[tid] = p.st[tid].gnorm;
-        float m = 0.0f;
-        for (int i = 0; i < QMAXP; ++i) m = fmaxf(m, __ldg(p.qmaxp + (size_t)tid * QMAXP + i));
-        s_qmax[tid] = m;
+        s_qmax[tid] = 0.0f;
         s_pub[tid] = make_uint4(0x7f800000u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    for (int b = 0; b < p.nq; ++b) {   // max_k |FFT(q)_k| from the QMAXP partial maxima (positive floats order as uints)
+        static_assert(QMAXP == fx2::THREADS, "one partial maximum per thread");
+        float m = __ldg(p.qmaxp + (size_t)b * QMAXP + tid);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+        if (lane == 0) atomicMax(reinterpret_cast<unsigned int *>(&s_qmax[b]), __float_as_uint(m));
     }
     __syncthreads();
 

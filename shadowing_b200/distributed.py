@@ -20,6 +20,30 @@ _INF = float("inf")
 _PAD_ROW = 2 ** 31 - 1
 
 
+class Lane:
+    """One stream of a pipeline of enqueue-only sharded scans: its own workspace, record buffers, overflow
+    flag and deferred merge; everything else (the plugin objects, the resident rows, the exchange buffers
+    and their epoch counter) is the PathShadowing object's.  `sharded_scan(lane, ...)` then runs unchanged."""
+    _OWN = frozenset({"stream", "_workspace", "_shard_bufs", "_pending_flag", "_pending_merge"})
+
+    def __init__(self, ps, stream):
+        object.__setattr__(self, "_ps", ps)
+        self.stream = stream
+        self._workspace = None
+        self._shard_bufs = None
+        self._pending_flag = None
+        self._pending_merge = None
+
+    def __getattr__(self, name):           # (only reached for names the lane does not hold itself)
+        return getattr(object.__getattribute__(self, "_ps"), name)
+
+    def __setattr__(self, name, value):
+        if name in Lane._OWN:
+            object.__setattr__(self, name, value)
+        else:
+            setattr(object.__getattribute__(self, "_ps"), name, value)
+
+
 def shard_bounds(R: int, world: int, rank: int) -> tuple[int, int]:
     """Contiguous block partition of R rows: the first R % world ranks hold one extra row."""
     base, extra = divmod(R, world)

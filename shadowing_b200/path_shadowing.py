@@ -128,6 +128,7 @@ class PathShadowing:
         self._pipeline_B = 0   # queries of the last enqueue-only scan on the main workspace
         self._side = None      # side streams [stream, workspace, B] of pipelined enqueue-only scans
         self._pipe_streams = max(1, int(os.environ.get("PSH_STREAMS", "1")))
+        self._lanes = None     # lanes (stream + per-stream state) of pipelined enqueue-only SHARDED scans
 
     # ------------------------------------------------------------------ device residency
     def _dev(self) -> torch.device:
@@ -227,8 +228,31 @@ class PathShadowing:
             self._pipeline_B = q.shape[0]
             return dist, idx
         from .distributed import finish_sharded, sharded_scan
+        if nosync and out is None and self._pipe_streams > 1:
+            return self._sharded_scan_on_lane(rows, T, q, H, k)
         res = sharded_scan(self, rows, T, q, H, k, defer=nosync)
         return res if nosync else finish_sharded(self, rows, T, q, H, k, res)
+
+    def _sharded_scan_on_lane(self, rows, T, q, H, k):
+        """Sharded pipelines of enqueue-only scans on `pipeline_streams` > 1 lanes: the same overlap as
+        `_scan_on_side_stream` (query i+1's preparation and scan run while query i's re-rank, select and
+        exchange finish), every lane with its own workspace, record buffers and flag.  Every rank
+        alternates lanes identically, so the exchange epochs stay aligned."""
+        from .distributed import Lane, sharded_scan
+        dev = rows.device
+        if self._lanes is None or len(self._lanes) != self._pipe_streams:
+            self._lanes = [Lane(self, torch.cuda.Stream(device=dev)) for _ in range(self._pipe_streams)]
+            self._lane_i = 0
+        lane = self._lanes[self._lane_i % self._pipe_streams]
+        self._lane_i += 1
+        cur = torch.cuda.current_stream(dev)
+        lane.stream.wait_stream(cur)
+        q.record_stream(lane.stream)
+        with torch.cuda.stream(lane.stream):
+            dist, idx = sharded_scan(lane, rows, T, q, H, k, defer=True)
+        dist.record_stream(cur)
+        idx.record_stream(cur)
+        return dist, idx
 
     def _scan_on_side_stream(self, rows, T, q, H, k, mode, aux):
         """Pipelines of enqueue-only scans, `pipeline_streams` > 1: consecutive queries alternate
@@ -334,12 +358,20 @@ class PathShadowing:
                 bad = _lib.scan_overflowed(self._workspace, self._pipeline_B) or bad
         else:
             from .distributed import flush_deferred_merge
-            flush_deferred_merge(self)
-            flag = getattr(self, "_pending_flag", None)
-            bad = flag is not None and int(flag.item()) != 0
-            if bad:
-                flag.zero_()
-            self._pending_flag = None
+            bad = False
+            cur = torch.cuda.current_stream(self._dev()) if torch.cuda.is_available() else None
+            for holder in [self] + list(self._lanes or []):
+                if holder is not self:
+                    with torch.cuda.stream(holder.stream):
+                        flush_deferred_merge(holder)
+                    cur.wait_stream(holder.stream)
+                else:
+                    flush_deferred_merge(holder)
+                flag = getattr(holder, "_pending_flag", None)
+                if flag is not None and int(flag.item()) != 0:
+                    bad = True
+                    flag.zero_()
+                holder._pending_flag = None
         if bad:
             raise _lib.PshadowError(_lib.PSH_E_OVERFLOW, "nosync scan pipeline")
 

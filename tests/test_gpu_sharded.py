@@ -32,7 +32,12 @@ PAD_ROW = 2 ** 31 - 1
 class VirtualRanks:
     """G ranks of the sharded scan inside one process: shard g lives on the same device, has its own
     stream and its own exchange buffer; `bufs` is what every rank of the multi-process path holds
-    after the IPC handshake (shadowing_b200/distributed.py:_PeerExchange)."""
+    after the IPC handshake (shadowing_b200/distributed.py:_PeerExchange).
+
+    All virtual ranks share ONE CUDA context, which real ranks do not: an exchange kernel that waits for a
+    peer must never be resident while that peer still has anything to do that needs the whole context
+    (lazy loading of a kernel's module on its first launch, an allocation) -- so the tests compute every
+    rank's records first, synchronise, and only then launch the exchange kernels concurrently."""
 
     def __init__(self, ds, G, B, k, T, W, H, mode=_lib.PSH_MODE_FILTER):
         self.G, self.B, self.k, self.T, self.W, self.H, self.mode = G, B, k, T, W, H, mode
@@ -93,8 +98,11 @@ def test_virtual_rank_exchange_fused(G, form, monkeypatch):
             for g in range(G):
                 with torch.cuda.stream(vr.streams[g]):
                     vr.streams[g].wait_stream(torch.cuda.current_stream())
-                    rec = vr.local_records(g, qd)
-                    step.append(_lib.allgather_merge_packed(rec, vr.bufs, g, vr.Tp, s + 1, vr.flags[g]))
+                    vr.local_records(g, qd)
+            torch.cuda.synchronize()
+            for g in range(G):
+                with torch.cuda.stream(vr.streams[g]):
+                    step.append(_lib.allgather_merge_packed(vr.rec[g], vr.bufs, g, vr.Tp, s + 1, vr.flags[g]))
             outs.append(step)
         torch.cuda.synchronize()
         for s, (do, io) in enumerate(_oracle_steps(ds, qs, k, H)):
@@ -122,11 +130,16 @@ def test_virtual_rank_exchange_split_pipeline(G, form, monkeypatch):
                   torch.empty((B, k, 2), dtype=torch.int32, device=vr.dev)) for _ in range(G)] for _ in range(steps)]
         for s in range(steps + 1):
             qd = torch.tensor(qs[s][:, 0, :]).to(vr.dev) if s < steps else None
+            if s < steps:
+                for g in range(G):
+                    with torch.cuda.stream(vr.streams[g]):
+                        vr.streams[g].wait_stream(torch.cuda.current_stream())
+                        vr.local_records(g, qd)
+                torch.cuda.synchronize()
             for g in range(G):
                 with torch.cuda.stream(vr.streams[g]):
-                    vr.streams[g].wait_stream(torch.cuda.current_stream())
                     if s < steps:
-                        _lib.xchg_send(vr.local_records(g, qd), vr.bufs, g, s + 1)
+                        _lib.xchg_send(vr.rec[g], vr.bufs, g, s + 1)
                     if s > 0:
                         d, i = outs[s - 1][g]
                         _lib.xchg_merge(vr.bufs, g, B, k, vr.Tp, s, d, i, vr.flags[g])
@@ -154,7 +167,11 @@ def test_virtual_rank_exchange_short_shards_and_ties():
         for g in range(G):
             with torch.cuda.stream(vr.streams[g]):
                 vr.streams[g].wait_stream(torch.cuda.current_stream())
-                outs.append(_lib.allgather_merge_packed(vr.local_records(g, qd), vr.bufs, g, vr.Tp, 1, vr.flags[g]))
+                vr.local_records(g, qd)
+        torch.cuda.synchronize()
+        for g in range(G):
+            with torch.cuda.stream(vr.streams[g]):
+                outs.append(_lib.allgather_merge_packed(vr.rec[g], vr.bufs, g, vr.Tp, 1, vr.flags[g]))
         torch.cuda.synchronize()
         do, io = oracle.shadow_topk(ds, q, k, H)
         for d, i in outs:
@@ -181,7 +198,10 @@ def test_virtual_rank_exchange_overflow_and_timeout_flags(form, monkeypatch):
                 rec = vr.local_records(g, qd)
                 if g == 2:
                     rec[1, 0, 0] = -1   # 0xffffffff: the overflow poison of select_kernel / finalize_kernel
-                _lib.allgather_merge_packed(rec, vr.bufs, g, vr.Tp, 1, vr.flags[g])
+        torch.cuda.synchronize()
+        for g in range(G):
+            with torch.cuda.stream(vr.streams[g]):
+                _lib.allgather_merge_packed(vr.rec[g], vr.bufs, g, vr.Tp, 1, vr.flags[g])
         torch.cuda.synchronize()
         assert all(int(f.item()) == 1 for f in vr.flags)
         # epoch 2: rank 3 never sends -> the others time out (bit 1), nobody hangs
@@ -189,8 +209,7 @@ def test_virtual_rank_exchange_overflow_and_timeout_flags(form, monkeypatch):
             f.zero_()
         for g in range(G - 1):
             with torch.cuda.stream(vr.streams[g]):
-                vr.streams[g].wait_stream(torch.cuda.current_stream())
-                _lib.allgather_merge_packed(vr.local_records(g, qd), vr.bufs, g, vr.Tp, 2, vr.flags[g])
+                _lib.allgather_merge_packed(vr.rec[g], vr.bufs, g, vr.Tp, 2, vr.flags[g])
         torch.cuda.synchronize()
         assert all(int(f.item()) & 2 for f in vr.flags[:G - 1])
     finally:
