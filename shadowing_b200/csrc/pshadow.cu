@@ -1145,8 +1145,9 @@ __global__ void __launch_bounds__(SEL_THREADS) xchg_merge_kernel(const XchgParam
 // other lists ordered before it).  Round 1 ran ONE CTA per query: G sequential remote-store loops, word-by-
 // word polling and the whole merge on one SM (0.076 ms at G = 8).
 constexpr int LL_BATCH = 4;   // records polled per thread and round trip (12 words in flight)
+constexpr int LL_THREADS = 512; // (46 registers: two CTAs per SM)
 
-__global__ void __launch_bounds__(SEL_THREADS) xchg_ll_kernel(const XchgParams x, int B, unsigned int k,
+__global__ void __launch_bounds__(LL_THREADS) xchg_ll_kernel(const XchgParams x, int B, unsigned int k,
                                                                unsigned long long Tp, float *out_d, int *out_idx,
                                                                int *flag, int phases) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1157,7 +1158,7 @@ __global__ void __launch_bounds__(SEL_THREADS) xchg_ll_kernel(const XchgParams x
         const int *src = x.local_rec + (size_t)b * n3;
         volatile unsigned long long *dst =
             reinterpret_cast<volatile unsigned long long *>(x.rec[g]) + ((size_t)x.rank * B + b) * n3;
-        for (unsigned int i = tid; i < n3; i += SEL_THREADS) dst[i] = tag | (unsigned int)src[i];
+        for (unsigned int i = tid; i < n3; i += LL_THREADS) dst[i] = tag | (unsigned int)src[i];
     }
     if (!(phases & 2)) return;
     const unsigned int n = (unsigned int)x.G * k;
@@ -1166,12 +1167,12 @@ __global__ void __launch_bounds__(SEL_THREADS) xchg_ll_kernel(const XchgParams x
     const volatile unsigned long long *mine = reinterpret_cast<const volatile unsigned long long *>(x.rec[x.rank]);
     const unsigned long long t0 = globaltimer_ns();
     bool timed_out = false;
-    for (unsigned int i0 = tid; i0 < n; i0 += SEL_THREADS * LL_BATCH) {
+    for (unsigned int i0 = tid; i0 < n; i0 += LL_THREADS * LL_BATCH) {
         unsigned long long word[LL_BATCH][3];
         const volatile unsigned long long *wp[LL_BATCH];
 #pragma unroll
         for (int u = 0; u < LL_BATCH; ++u) {
-            const unsigned int i = i0 + u * SEL_THREADS;
+            const unsigned int i = i0 + u * LL_THREADS;
             const unsigned int gg = i < n ? i / k : 0u, j = i < n ? i - gg * k : 0u;
             wp[u] = mine + (((size_t)gg * B + b) * k + j) * 3;
         }
@@ -1181,7 +1182,7 @@ __global__ void __launch_bounds__(SEL_THREADS) xchg_ll_kernel(const XchgParams x
             for (int c = 0; c < 3; ++c) word[u][c] = wp[u][c];
 #pragma unroll
         for (int u = 0; u < LL_BATCH; ++u) {
-            const unsigned int i = i0 + u * SEL_THREADS;
+            const unsigned int i = i0 + u * LL_THREADS;
             if (i >= n) continue;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -1199,7 +1200,7 @@ __global__ void __launch_bounds__(SEL_THREADS) xchg_ll_kernel(const XchgParams x
     }
     if (timed_out && flag != nullptr) atomicOr(flag, 2);
     __syncthreads();
-    for (unsigned int j = tid; j < k; j += SEL_THREADS) {   // the records of list g
+    for (unsigned int j = tid; j < k; j += LL_THREADS) {   // the records of list g
         const unsigned int i = (unsigned int)g * k + j;
         const unsigned int dk = db[i];
         const unsigned long long fk = fl[i];
@@ -1610,6 +1611,22 @@ static int device_setup(DevSetup **out) {
     PSH_CUDA(big_smem(merge_kernel, SMEM_BIG));
     PSH_CUDA(big_smem(xchg_merge_kernel, SMEM_BIG));
     PSH_CUDA(big_smem(xchg_ll_kernel, SMEM_BIG));
+    // CUDA loads a kernel's module lazily at its first launch, which synchronises the whole context: a
+    // first launch issued while an exchange kernel of another stream waits for a peer would stall behind it
+    // (and two ranks doing so for each other's sake would only be released by the exchange's timeout).
+    // Touch every kernel now, before any exchange kernel can be resident.
+    {
+        cudaFuncAttributes fa;
+        PSH_CUDA(cudaFuncGetAttributes(&fa, qprep_kernel));
+        PSH_CUDA(cudaFuncGetAttributes(&fa, qfft_kernel));
+        PSH_CUDA(cudaFuncGetAttributes(&fa, select_kernel));
+        PSH_CUDA(cudaFuncGetAttributes(&fa, gather_kernel));
+        PSH_CUDA(cudaFuncGetAttributes(&fa, rv_aggregate_kernel));
+        PSH_CUDA(cudaFuncGetAttributes(&fa, clear_sticky_kernel));
+        PSH_CUDA(cudaFuncGetAttributes(&fa, fft_prep_spectra_kernel));
+        PSH_CUDA(cudaFuncGetAttributes(&fa, fft_prep_energy_kernel<false>));
+        PSH_CUDA(cudaFuncGetAttributes(&fa, fft_prep_energy_kernel<true>));
+    }
     for (int i = 0; i < FFT_VARIANTS; ++i) {
         FftScanFn fn = fft_variant_fn((i >> 1) & 1, i & 1);
         PSH_CUDA(big_smem(fn, SMEM_FFT));
@@ -2157,7 +2174,7 @@ static int xchg_launch(const int32_t *d_rec_local, void *const *bufs, int G, int
         const size_t smem_ll = (phases & 2) ? (size_t)n * 12 : 0;
         {
             ProfScope ps_merge(stream, 2);
-            xchg_ll_kernel<<<dim3(G, B), SEL_THREADS, smem_ll, stream>>>(x, B, (unsigned int)k, (unsigned long long)Tp,
+            xchg_ll_kernel<<<dim3(G, B), LL_THREADS, smem_ll, stream>>>(x, B, (unsigned int)k, (unsigned long long)Tp,
                                                                          d_out_dist, d_out_idx, d_flag, phases);
         }
         PSH_LAUNCHED();
