@@ -9,7 +9,8 @@ Uniform, DiscreteProba.
 from .averaging import DiscreteProba, Softmax, Uniform, softmax_weights
 from .dataset import TimeSeriesDataset
 from .path_distance import PathDistance, RelativeMSE
-from .path_embedding import ArrayType, ContextManagerBase, Foveal, Identity, PathEmbedding, PredictionContext
+from .path_embedding import (ArrayType, ContextManagerBase, CrossChannelContext, Foveal, Identity, ImputationContext,
+                             PathEmbedding, PredictionContext)
 from .path_shadowing import PathShadowing, select_cartesian_product
 from .statistics import RealizedVariance, realized_variance
 
@@ -17,7 +18,7 @@ __version__ = "0.1.0"
 
 __all__ = [
     "PathShadowing", "PathEmbedding", "Identity", "Foveal", "PathDistance", "RelativeMSE",
-    "ContextManagerBase", "PredictionContext", "ArrayType", "realized_variance",
+    "ContextManagerBase", "PredictionContext", "ImputationContext", "CrossChannelContext", "ArrayType", "realized_variance",
     "RealizedVariance", "TimeSeriesDataset", "Softmax", "Uniform", "DiscreteProba", "softmax_weights",
     "select_cartesian_product",
 ]

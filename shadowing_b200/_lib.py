@@ -17,6 +17,7 @@ PSH_MODE_FFT = 2
 PSH_FLAG_NOSYNC = 0x100
 PSH_E_OVERFLOW = -6
 FFT_MAX_W = 2048   # psh_fft_prepare: context length at most half a 4096-point transform
+AGG_MAX_T = 16     # psh_rv_aggregate: maturities per launch (more: the host aggregation)
 
 _lib = None
 

@@ -1432,8 +1432,8 @@ bool seedless_enabled() {
 
 // optional per-kernel timing (bench.py's roofline leg): CUDA events on the caller's stream
 struct ProfRec { cudaEvent_t a, b; int kind; };
-bool g_prof_on = false;
-std::vector<ProfRec> g_prof;
+thread_local bool g_prof_on = false;          // per calling thread, like host_stage(): the ABI keeps no
+thread_local std::vector<ProfRec> g_prof;     // state shared between threads except the launch counter
 struct ProfScope {
     cudaStream_t s; int kind; cudaEvent_t a = nullptr, b = nullptr;
     ProfScope(cudaStream_t s_, int kind_) : s(s_), kind(kind_) {

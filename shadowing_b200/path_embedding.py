@@ -56,6 +56,69 @@ class PredictionContext(ContextManagerBase):
         return 0 if self.horizon is None else self.horizon
 
 
+class ImputationContext(ContextManagerBase):
+    """in-context = the first `l` and the last `r` samples of a window, out-context = the `c` samples in
+    between (`portion = (l, c, r)`; path_embedding.py:59-87).  The scan compares the l + r context
+    samples only: the embedding kernel is padded with `c` zero taps in the middle (`pad_context`)."""
+
+    def __init__(self, portion: tuple | None = None):
+        self.portion = portion
+
+    def select_in_context(self, x: ArrayType) -> ArrayType:
+        if self.portion is None:
+            return x
+        l, _, r = self.portion
+        if isinstance(x, torch.Tensor):
+            return torch.cat([x[..., :l], x[..., -r:]], dim=-1)
+        return np.concatenate([x[..., :l], x[..., -r:]], axis=-1)
+
+    def select_out_context(self, x: ArrayType) -> ArrayType:
+        if self.portion is None:
+            return x
+        l, _, r = self.portion
+        return x[..., l:-r]
+
+    # the reference spells it `slect_out_context` (path_embedding.py:71); both names work here
+    slect_out_context = select_out_context
+
+    def pad_context(self, x_in_context: torch.Tensor) -> torch.Tensor:
+        if self.portion is None:
+            return x_in_context
+        l, c, r = self.portion
+        zeros_middle = x_in_context.new_zeros(x_in_context.shape[:-1] + (c,))
+        return torch.cat([x_in_context[..., :l], zeros_middle, x_in_context[..., -r:]], dim=-1)
+
+    def get_out_times(self):
+        return 0 if self.portion is None else self.portion[1]
+
+
+class CrossChannelContext(ContextManagerBase):
+    """in-context = the first channels of a (.., C, T) path, out-context = its last `out_context_channels`
+    channels (path_embedding.py:90-114): the scan compares the in-context channel, the shadowing paths
+    come back with all channels."""
+
+    def __init__(self, out_context_channels: int):
+        self.out_context_channels = out_context_channels
+
+    def select_in_context(self, x: ArrayType) -> ArrayType:
+        return x[..., :x.shape[-2] - self.out_context_channels, :]
+
+    def select_out_context(self, x: ArrayType) -> ArrayType:
+        if self.out_context_channels is None:
+            return x
+        return x[..., -self.out_context_channels:, :]
+
+    def pad_context(self, x_in_context: torch.Tensor) -> torch.Tensor:
+        if self.out_context_channels is None:
+            return x_in_context
+        shape = list(x_in_context.shape)
+        shape[-2] = self.out_context_channels
+        return torch.cat([x_in_context, x_in_context.new_zeros(shape)], dim=-2)
+
+    def get_out_times(self):
+        return 0
+
+
 class PathEmbedding(nn.Module):
     """Linear embedding given by a (d, 1, W) kernel buffer (path_embedding.py:117-132)."""
 

@@ -29,8 +29,8 @@ from . import _lib
 from .averaging import DiscreteProba, Softmax, Uniform
 from .dataset import TimeSeriesDataset
 from .path_distance import PathDistance, RelativeMSE
-from .path_embedding import (ArrayType, ContextManagerBase, Foveal, Identity, PathEmbedding, PredictionContext,
-                             kernel_runs)
+from .path_embedding import (ArrayType, ContextManagerBase, CrossChannelContext, Foveal, Identity, ImputationContext,
+                             PathEmbedding, PredictionContext, kernel_runs)
 from .statistics import RealizedVariance
 
 
@@ -129,6 +129,7 @@ class PathShadowing:
         self._side = None      # side streams [stream, workspace, B] of pipelined enqueue-only scans
         self._pipe_streams = max(1, int(os.environ.get("PSH_STREAMS", "1")))
         self._lanes = None     # lanes (stream + per-stream state) of pipelined enqueue-only SHARDED scans
+        self._padded_kernel = None   # (key, kernel padded by an ImputationContext)
 
     # ------------------------------------------------------------------ device residency
     def _dev(self) -> torch.device:
@@ -145,37 +146,81 @@ class PathShadowing:
         if type(self.distance) is not RelativeMSE:
             raise NotImplementedError(
                 f"the B200 scan implements the RelativeMSE distance; got {type(self.distance).__name__}")
-        if type(self.context) is not PredictionContext:
+        if type(self.context) not in (PredictionContext, ImputationContext, CrossChannelContext):
             raise NotImplementedError(
-                f"the B200 scan implements PredictionContext; got {type(self.context).__name__}")
+                f"the B200 scan implements PredictionContext, ImputationContext and CrossChannelContext; "
+                f"got {type(self.context).__name__}")
 
-    @staticmethod
-    def _rows_to_device(y: ArrayType, dev: torch.device) -> tuple[torch.Tensor, int]:
-        """(R, 1, T) host/device array -> resident (R, row_stride) fp32 rows, row_stride % 4 == 0
-        so every row starts 16-byte aligned for the TMA bulk copies."""
+    def _imputation(self) -> bool:
+        return type(self.context) is ImputationContext and self.context.portion is not None
+
+    def _scan_kernel(self) -> torch.Tensor:
+        """The kernel the DATASET is embedded with (`embedding.adjust_to_context(context)`,
+        path_shadowing.py:140): ImputationContext pads the kernel with zero taps in the middle -- the
+        embedded scan skips them (runs of equal non-zero taps) -- any other context leaves the taps that
+        matter where they are (PredictionContext pads zeros behind them: the horizon H of the scan)."""
+        kernel = self.embedding.kernel
+        if not self._imputation():
+            return kernel
+        key = (kernel.data_ptr(), kernel._version, tuple(self.context.portion))
+        if self._padded_kernel is None or self._padded_kernel[0] != key:
+            self._padded_kernel = (key, self.context.pad_context(kernel.detach()).contiguous())
+        return self._padded_kernel[1]
+
+    def _scan_horizon(self) -> int:
+        """Trailing out-of-context samples of a window (0 for the contexts whose out-context is elsewhere)."""
+        return self.context.get_out_times() if type(self.context) is PredictionContext else 0
+
+    def _identity_scan(self) -> bool:
+        """Raw windows compared sample by sample: Identity without zero taps in the middle."""
+        return type(self.embedding) is Identity and not self._imputation()
+
+    def _rows_to_device(self, y: ArrayType, dev: torch.device) -> tuple[torch.Tensor, int]:
+        """(R, C, T) host/device array -> resident fp32 rows, row stride % 4 == 0 so every row starts
+        16-byte aligned for the TMA bulk copies.  Returns the rows the scan reads -- channel 0, a
+        (R, C * row_stride)-strided view -- and T; all channels stay reachable through `._channels`."""
         y = _dim_array(y)
-        if y.shape[1] != 1:
+        C = y.shape[1]
+        want = 1 + self.context.out_context_channels if type(self.context) is CrossChannelContext else 1
+        if C != want:
             raise RuntimeError(
-                f"expected a single-channel dataset (R, 1, T), got {tuple(y.shape)}: the embedding is a "
-                "conv1d with one input channel (path_embedding.py:130)")
+                f"expected a dataset with {want} channel(s) (R, {want}, T), got {tuple(y.shape)}: the embedding is a "
+                "conv1d over the in-context channel (path_embedding.py:130, CrossChannelContext.pad_context)")
         y = _torch(y)
         if y.dtype != torch.float32:
             raise RuntimeError(f"expected a float32 dataset tensor, got {y.dtype}")
         R, _, T = y.shape
         stride = (T + 3) // 4 * 4
-        rows = torch.zeros((R, stride), dtype=torch.float32, device=dev)
-        rows[:, :T].copy_(y[:, 0, :], non_blocking=True)
+        allc = torch.zeros((R * C, stride), dtype=torch.float32, device=dev)
+        allc.view(R, C, stride)[:, :, :T].copy_(y, non_blocking=True)
+        rows = allc[0::C] if C > 1 else allc
+        rows._channels = (allc, C)
         return rows, T
 
     def _resident_rows(self) -> tuple[torch.Tensor, int]:
         ds = self.dataset
-        key = (id(ds), tuple(ds.shape))
+        key = (id(ds), tuple(ds.shape), type(self.context), getattr(self.context, "out_context_channels", None))
         if self._resident is None or self._resident[0] != key:
             rows, T = self._rows_to_device(ds, self._dev())
             self._resident = (key, rows, T)
             self._workspace = None
             self._fft_aux = None
         return self._resident[1], self._resident[2]
+
+    def invalidate(self) -> None:
+        """Forget the resident copy of the dataset and everything derived from it (spectra, energies): call
+        it after editing `self.dataset` IN PLACE.  The ensemble is uploaded once and kept resident (the
+        reference re-reads it on every call); replacing `self.dataset` by another object is noticed."""
+        self._resident = None
+        self._workspace = None
+        self._fft_aux = None
+
+    def _gather(self, rows: torch.Tensor, T: int, idx: torch.Tensor, L: int, out=None) -> torch.Tensor:
+        """paths (B, k, C, L) of the winners: dataset[r, :, t:t+L] (path_shadowing.py:210-216)."""
+        allc, C = getattr(rows, "_channels", (rows, 1))
+        if C == 1:
+            return _lib.gather_paths(rows, T, idx, L, self._row_offset, out)
+        return torch.cat([_lib.gather_paths(allc[c::C], T, idx, L, self._row_offset) for c in range(C)], dim=2)
 
     def _mode_and_aux(self, rows: torch.Tensor, T: int, W: int, H: int):
         mode = self._scan_mode
@@ -208,8 +253,8 @@ class PathShadowing:
             raise RuntimeError(f"expected a float32 context, got {x.dtype}")  # reference: conv1d dtype error
         if x.shape[1] != 1:
             raise RuntimeError(f"expected a single-channel context (B, 1, W), got {tuple(x.shape)}")
-        H = self.context.get_out_times()
-        if type(self.embedding) is not Identity:
+        H = self._scan_horizon()
+        if not self._identity_scan():
             return self._scan_embedded(x, rows, T, k, H, out, nosync)
         q = x[:, 0, :].to(dev, non_blocking=True).contiguous()
         W = q.shape[1]
@@ -222,10 +267,13 @@ class PathShadowing:
             mode, aux = self._mode_and_aux(rows, T, W, H)
             if nosync and out is None and self._pipe_streams > 1:   # (shadow() brings its own `out`: one stream)
                 return self._scan_on_side_stream(rows, T, q, H, k, mode, aux)
+            if (self._pipeline_B and self._workspace is not None and self._workspace.numel() <
+                    _lib.lib().psh_scan_workspace_bytes(rows.shape[0], T, q.shape[0], W, H, k)):
+                self._check_pipeline()   # the workspace is about to be replaced: settle the scans still pending on it
             dist, idx, self._workspace = _lib.scan_topk(
                 rows, T, q, H, k, self._row_offset, mode | (_lib.PSH_FLAG_NOSYNC if nosync else 0),
                 self._workspace, aux, out)
-            self._pipeline_B = q.shape[0]
+            self._pipeline_B = max(self._pipeline_B, q.shape[0]) if nosync else q.shape[0]
             return dist, idx
         from .distributed import finish_sharded, sharded_scan
         if nosync and out is None and self._pipe_streams > 1:
@@ -278,9 +326,9 @@ class PathShadowing:
 
     def _run_table(self, device: torch.device):
         """Device run table of a non-Identity embedding kernel (None for Identity)."""
-        if type(self.embedding) is Identity:
+        if self._identity_scan():
             return None
-        kernel = self.embedding.kernel
+        kernel = self._scan_kernel()
         key = (kernel.data_ptr(), tuple(kernel.shape), kernel._version, str(device))
         if self._runs is None or self._runs[0] != key:
             runs = kernel_runs(kernel)
@@ -299,7 +347,7 @@ class PathShadowing:
             mode = "fft" if (64 <= W <= 1024 and T >= 1024) else "exact"
         if mode != "fft" or W > _lib.FFT_MAX_W:
             return {}
-        kernel = self.embedding.kernel
+        kernel = self._scan_kernel()
         runs = self._run_table(rows.device)
         key = (T, W, H, kernel.data_ptr(), kernel._version)
         resident = self._resident is not None and rows is self._resident[1]
@@ -319,10 +367,10 @@ class PathShadowing:
         """Foveal / PathEmbedding(kernel): the few query windows are embedded on the host with the
         embedding's own forward -- the reference's `embedding(x)[:, 0, :]`, path_shadowing.py:138 --
         and the ensemble is scanned in embedded space from prefix sums (never materialised)."""
-        kernel = self.embedding.kernel
-        W = int(kernel.shape[-1])
-        if x.shape[-1] != W:
-            raise RuntimeError(f"context length {x.shape[-1]} does not match the embedding kernel ({W})")
+        W = int(self._scan_kernel().shape[-1])   # window length in the dataset (l + c + r under an ImputationContext)
+        if x.shape[-1] != int(self.embedding.kernel.shape[-1]):
+            raise RuntimeError(f"context length {x.shape[-1]} does not match the embedding kernel "
+                               f"({int(self.embedding.kernel.shape[-1])})")
         Tp = T - W - H + 1
         if Tp <= 0:
             raise RuntimeError(f"context ({W}) + horizon ({H}) longer than the trajectories ({T})")
@@ -356,6 +404,7 @@ class PathShadowing:
                         slot[2] = 0
             if self._pipeline_B:
                 bad = _lib.scan_overflowed(self._workspace, self._pipeline_B) or bad
+                self._pipeline_B = 0
         else:
             from .distributed import flush_deferred_merge
             bad = False
@@ -405,7 +454,7 @@ class PathShadowing:
             out_paths = _packed[nd + ni:nd + ni + B * k * L].view(torch.float32).view(B, k, 1, L)
         dist, idx = self._scan_device(x, rows, T, k, out, nosync=_nosync and self._pg is None)
         if self._pg is None:
-            paths = _lib.gather_paths(rows, T, idx, L, self._row_offset, out_paths)
+            paths = self._gather(rows, T, idx, L, out_paths)
         else:
             from .distributed import sharded_gather
             paths = sharded_gather(self, rows, T, idx, L)
@@ -422,7 +471,7 @@ class PathShadowing:
         :return: numpy (distances (B,k) f32 ascending, paths (B,k,C,W+H) f32, indices (B,k,2) i32)
         """
         del n_splits, cuda
-        if self._pg is not None or not torch.cuda.is_available():
+        if self._pg is not None or not torch.cuda.is_available() or type(self.context) is CrossChannelContext:
             dist, paths, idx = self.shadow_device(x_context, k)
             return _numpy(dist), _numpy(paths), _numpy(idx)
         # results land in ONE device buffer [dist | idx | paths] (4-byte words) that is copied with a
@@ -485,6 +534,8 @@ class PathShadowing:
                         eta: float | None):
         if proba_name not in ("uniform", "softmax"):
             raise ValueError("Unrecognized averaging proba")
+        if proba_name == "softmax" and not (eta is not None and eta > 0):
+            raise ValueError("softmax averaging needs a positive eta (the width of the Gaussian weights)")
         H = self.context.get_out_times() or paths.shape[-1]
         order = sorted(range(len(rv.Ts)), key=lambda i: rv.Ts[i])
         Ts = torch.tensor([rv.Ts[i] for i in order], dtype=torch.int32, device=paths.device)
@@ -501,7 +552,8 @@ class PathShadowing:
         A `RealizedVariance` callable is evaluated by the fused CUDA kernel; any other callable
         is the user's own host function and is applied to the out-context on the host, exactly
         as the reference does (called twice there; once here)."""
-        if isinstance(to_predict, RealizedVariance) and paths.shape[2] == 1:
+        if (isinstance(to_predict, RealizedVariance) and paths.shape[2] == 1 and type(self.context) is PredictionContext
+                and len(to_predict.Ts) <= _lib.AGG_MAX_T):
             dev = self._dev()
             d = torch.as_tensor(distances, dtype=torch.float32).to(dev)
             p = torch.as_tensor(paths, dtype=torch.float32).to(dev)
@@ -523,7 +575,8 @@ class PathShadowing:
         preds, stds = [], []
         for bs in torch.arange(B).split(max(B // n_context_splits, 1)):
             xb = x[bs, ...]
-            if isinstance(to_predict, RealizedVariance):
+            if (isinstance(to_predict, RealizedVariance) and type(self.context) is PredictionContext
+                    and len(to_predict.Ts) <= _lib.AGG_MAX_T):
                 dist, paths, _ = self.shadow_device(xb, k)
                 mean, std = self._predict_device(dist, paths, to_predict, proba_name, eta)
                 preds.append(_numpy(mean))

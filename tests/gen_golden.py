@@ -107,6 +107,33 @@ def main():
                         paths=paths, meta=np.array([16, 300, 16, 4, 64, 3, 2], np.int64))
     print("dense kernel", d.shape, idx.shape)
 
+    # ImputationContext (path_embedding.py:59-87) and CrossChannelContext (:90-114): `shadow` only -- the
+    # reference's `slect_out_context` typo makes `predict` unusable with ImputationContext upstream
+    g = torch.Generator().manual_seed(20)
+    ds = torch.randn(24, 1, 700, generator=g) * 0.01
+    l, c, r = 30, 12, 20
+    x = torch.randn(3, 1, l + r, generator=g) * 0.01
+    obj = PS(ref.path_embedding.Identity(l + r), ref.path_distance.RelativeMSE(), ds,
+             ref.path_embedding.ImputationContext((l, c, r)))
+    d, paths, idx = obj.shadow(x, k=40, n_splits=2, cuda=False)
+    emb = ref.path_embedding.Foveal(1.15, 0.9, l + r)
+    objf = PS(emb, ref.path_distance.RelativeMSE(), ds, ref.path_embedding.ImputationContext((l, c, r)))
+    df, pathsf, idxf = objf.shadow(x, k=40, n_splits=1, cuda=False)
+    np.savez_compressed(OUT / "imputation_R24_T700.npz", dataset=ds.numpy(), x_context=x.numpy(),
+                        portion=np.array([l, c, r], np.int64), distances=d, paths=paths, indices=idx,
+                        foveal=np.array([1.15, 0.9, l + r]), foveal_distances=df, foveal_indices=idxf)
+    print("imputation", d.shape, paths.shape, idx.shape, df.shape)
+
+    g = torch.Generator().manual_seed(21)
+    ds = torch.randn(16, 3, 500, generator=g) * 0.01
+    x = torch.randn(2, 1, 25, generator=g) * 0.01
+    obj = PS(ref.path_embedding.Identity(25), ref.path_distance.RelativeMSE(), ds,
+             ref.path_embedding.CrossChannelContext(2))
+    d, paths, idx = obj.shadow(x, k=30, n_splits=1, cuda=False)
+    np.savez_compressed(OUT / "crosschannel_R16_C3_T500.npz", dataset=ds.numpy(), x_context=x.numpy(),
+                        out_channels=np.array([2], np.int64), distances=d, paths=paths, indices=idx)
+    print("cross-channel", d.shape, paths.shape, idx.shape)
+
 
 if __name__ == "__main__":
     main()

@@ -79,6 +79,38 @@ def test_prediction_context_and_identity():
     assert tuple(emb.shape) == (1, 4, 4) and torch.equal(emb[0, 2], y[0, 0, 2:6])
 
 
+def test_imputation_and_cross_channel_contexts():
+    """ImputationContext / CrossChannelContext mirror path_embedding.py:59-114 (checked against what the live
+    reference returned for the committed fixtures)."""
+    import numpy as np
+    import torch
+    import shadowing_b200 as sb
+    from conftest import GOLDEN
+    g = np.load(GOLDEN / "imputation_R24_T700.npz")
+    l, c, r = (int(v) for v in g["portion"])
+    ctx = sb.ImputationContext((l, c, r))
+    assert ctx.get_out_times() == c and sb.ImputationContext(None).get_out_times() == 0
+    k = torch.arange(float(2 * (l + r))).reshape(2, 1, l + r)
+    kp = ctx.pad_context(k)
+    assert kp.shape == (2, 1, l + c + r) and torch.equal(kp[..., :l], k[..., :l]) and torch.equal(kp[..., -r:], k[..., -r:])
+    assert float(kp[..., l:l + c].abs().sum()) == 0.0
+    paths = g["paths"]
+    assert np.array_equal(ctx.select_in_context(paths), np.concatenate([paths[..., :l], paths[..., -r:]], -1))
+    assert np.array_equal(ctx.select_out_context(paths), paths[..., l:-r])
+    assert np.array_equal(ctx.slect_out_context(paths), paths[..., l:-r])   # the reference's spelling
+    # the fixture's distances are the relative error on the in-context samples of the returned paths
+    x = g["x_context"]
+    err = np.linalg.norm(ctx.select_in_context(paths)[:, :, 0, :] - x, axis=-1) / np.linalg.norm(x, axis=-1)
+    assert np.allclose(err, g["distances"], rtol=1e-5)
+    h = np.load(GOLDEN / "crosschannel_R16_C3_T500.npz")
+    cc = sb.CrossChannelContext(2)
+    assert cc.get_out_times() == 0
+    assert cc.pad_context(torch.ones(4, 1, 25)).shape == (4, 3, 25)
+    assert float(cc.pad_context(torch.ones(4, 1, 25))[:, 1:].abs().sum()) == 0.0
+    assert np.array_equal(cc.select_in_context(h["paths"]), h["paths"][:, :, :1, :])
+    assert np.array_equal(cc.select_out_context(h["paths"]), h["paths"][:, :, 1:, :])
+
+
 def test_relative_mse_and_forward_topk_match_reference_fixture():
     import shadowing_b200 as sb
     g = load_golden("forward_topk_B8_d34")

@@ -602,6 +602,51 @@ def test_predict_with_foveal_end_to_end():
     assert np.allclose(pred, mo, rtol=1e-6) and np.allclose(std, so, rtol=1e-5)
 
 
+@pytest.mark.parametrize("mode", ["exact", "fft"])
+def test_imputation_context_matches_reference_fixture(mode):
+    """ImputationContext((l, c, r)) (path_embedding.py:59-87): the windows are compared on their first l and
+    last r samples, the c samples in between come back as out-context.  Identity and Foveal embeddings
+    against live-reference fixtures (the kernel padded with zero taps runs through the embedded scan:
+    distances within 1e-6, same windows up to near-ties)."""
+    from conftest import GOLDEN, assert_topk_close
+    g = np.load(GOLDEN / "imputation_R24_T700.npz")
+    l, c, r = (int(v) for v in g["portion"])
+    ds, x = g["dataset"], g["x_context"]
+    obj = sb.PathShadowing(sb.Identity(l + r), sb.RelativeMSE(), ds, sb.ImputationContext((l, c, r)), scan_mode=mode)
+    d, paths, idx = obj.shadow(x, k=40)
+    assert paths.shape == g["paths"].shape == (3, 40, 1, l + c + r) and idx.dtype == np.int32
+    assert_topk_close(d, idx, g["distances"], g["indices"])
+    assert np.array_equal(paths, _gather_ref(ds, idx, l + c + r))
+    out = obj.context.select_out_context(paths)
+    assert out.shape[-1] == c and np.array_equal(out, paths[..., l:l + c])
+    a, b, _ = (float(v) for v in g["foveal"])
+    fobj = sb.PathShadowing(sb.Foveal(a, b, l + r), sb.RelativeMSE(), ds, sb.ImputationContext((l, c, r)), scan_mode=mode)
+    fd, _, fidx = fobj.shadow(x, k=40)
+    assert_topk_close(fd, fidx, g["foveal_distances"], g["foveal_indices"])
+    # portion=None: the whole window is in-context (== PredictionContext(None))
+    d0, _, i0 = sb.PathShadowing(sb.Identity(l + r), sb.RelativeMSE(), ds, sb.ImputationContext(None)).shadow(x, k=40)
+    d1, _, i1 = sb.PathShadowing(sb.Identity(l + r), sb.RelativeMSE(), ds, sb.PredictionContext(None)).shadow(x, k=40)
+    assert np.array_equal(d0, d1) and np.array_equal(i0, i1)
+
+
+@pytest.mark.parametrize("mode", ["exact", "filter", "fft"])
+def test_cross_channel_context_bit_exact(mode):
+    """CrossChannelContext(2) (path_embedding.py:90-114): a (R, 3, T) dataset is scanned on its in-context
+    channel, the shadowing paths come back with all three channels -- bit-exact against the live-reference
+    fixture (Identity windows are exact)."""
+    from conftest import GOLDEN
+    g = np.load(GOLDEN / "crosschannel_R16_C3_T500.npz")
+    obj = sb.PathShadowing(sb.Identity(25), sb.RelativeMSE(), g["dataset"], sb.CrossChannelContext(2), scan_mode=mode)
+    d, paths, idx = obj.shadow(g["x_context"], k=30)
+    assert_topk_equal(d, idx, g["distances"], g["indices"])
+    assert np.array_equal(idx, g["indices"])
+    assert paths.shape == (2, 30, 3, 25) and np.array_equal(paths, g["paths"])
+    assert np.array_equal(obj.context.select_out_context(paths), paths[:, :, 1:, :])
+    with pytest.raises(RuntimeError):   # a single-channel dataset does not fit a 1 + 2 channel context
+        sb.PathShadowing(sb.Identity(25), sb.RelativeMSE(), g["dataset"][:, :1], sb.CrossChannelContext(2)).shadow(
+            g["x_context"], k=3)
+
+
 def test_unsupported_plugins_raise():
     class Cosine(sb.PathDistance):
         def forward(self, x, y):
