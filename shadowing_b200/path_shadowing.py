@@ -99,11 +99,16 @@ class PathShadowing:
         row_offset: int = 0,
         process_group=None,
         scan_mode: str = "auto",
+        stream_dataset: bool = False,
     ):
         if isinstance(dataset, (str, Path)):
-            dataset = TimeSeriesDataset(dpath=dataset, R=None).load()   # path_shadowing.py:84-85
-        elif hasattr(dataset, "load") and not isinstance(dataset, (np.ndarray, torch.Tensor)):
-            dataset = dataset.load()  # a TimeSeriesDataset(-like) object (path_shadowing.py:86-87)
+            dataset = TimeSeriesDataset(dpath=dataset, R=None)              # path_shadowing.py:84-85
+        if hasattr(dataset, "load") and not isinstance(dataset, (np.ndarray, torch.Tensor)):
+            # a TimeSeriesDataset(-like) object (path_shadowing.py:86-87): loaded into a host array as the
+            # reference does, or -- stream_dataset=True -- kept as it is and streamed file by file through
+            # pinned buffers into the resident device rows (no host copy of the ensemble)
+            if not (stream_dataset and hasattr(dataset, "to_device")):
+                dataset = dataset.load()
         self.dataset = dataset
         self.embedding = embedding
         self.distance = distance
@@ -179,9 +184,16 @@ class PathShadowing:
         """(R, C, T) host/device array -> resident fp32 rows, row stride % 4 == 0 so every row starts
         16-byte aligned for the TMA bulk copies.  Returns the rows the scan reads -- channel 0, a
         (R, C * row_stride)-strided view -- and T; all channels stay reachable through `._channels`."""
+        want = 1 + self.context.out_context_channels if type(self.context) is CrossChannelContext else 1
+        if hasattr(y, "to_device") and not isinstance(y, (np.ndarray, torch.Tensor)):   # streamed from its files
+            allc, T, C = y.to_device(dev)
+            if C != want:
+                raise RuntimeError(f"expected a dataset with {want} channel(s), the files hold {C}")
+            rows = allc[0::C] if C > 1 else allc
+            rows._channels = (allc, C)
+            return rows, T
         y = _dim_array(y)
         C = y.shape[1]
-        want = 1 + self.context.out_context_channels if type(self.context) is CrossChannelContext else 1
         if C != want:
             raise RuntimeError(
                 f"expected a dataset with {want} channel(s) (R, {want}, T), got {tuple(y.shape)}: the embedding is a "

@@ -248,3 +248,13 @@ def test_time_series_dataset_reads_npy_batches(tmp_path):
     assert np.array_equal(obj.dataset, full)
     obj = sb.PathShadowing(sb.Identity(8), sb.RelativeMSE(), sb.TimeSeriesDataset(tmp_path, R=4))
     assert obj.dataset.shape == (4, 1, 64) and obj.context.get_out_times() == 0
+    # the streaming loader (chunks smaller than a file, R limit, row stride padded to 16 bytes)
+    for R in (None, 7):
+        tsd = sb.TimeSeriesDataset(tmp_path, R=R)
+        rows, T, C = tsd.to_device("cpu", chunk_bytes=2 * 64 * 4)
+        want = full if R is None else full[:R]
+        assert (T, C) == (64, 1) and rows.shape == (want.shape[0], 64)
+        assert np.array_equal(rows.numpy(), want[:, 0, :]) and tsd.shape == want.shape
+        assert np.array_equal(np.asarray(tsd), want)
+    keep = sb.PathShadowing(sb.Identity(8), sb.RelativeMSE(), sb.TimeSeriesDataset(tmp_path), stream_dataset=True)
+    assert isinstance(keep.dataset, sb.TimeSeriesDataset) and keep.dataset.shape == (9, 1, 64)

@@ -647,6 +647,22 @@ def test_cross_channel_context_bit_exact(mode):
             g["x_context"], k=3)
 
 
+def test_streamed_dataset_equals_host_dataset(tmp_path):
+    """`stream_dataset=True`: `.npy` batch files (scripts/batch_generations.py:28-40) go through two pinned
+    staging buffers straight into the resident rows; results equal those of the host-array path."""
+    ds, q = make_inputs(48, 1030, 64, 2, seed=61)
+    for i in range(3):
+        np.save(tmp_path / f"batch{i + 1:04}.npy", ds[16 * i:16 * (i + 1)])
+    tsd = sb.TimeSeriesDataset(tmp_path)
+    rows, T, C = tsd.to_device("cuda", chunk_bytes=5 * 1030 * 4)    # chunks that do not divide a file
+    assert (T, C) == (1030, 1) and rows.shape == (48, 1032)
+    assert np.array_equal(rows[:, :1030].cpu().numpy(), ds[:, 0, :])
+    a = sb.PathShadowing(sb.Identity(64), sb.RelativeMSE(), tsd, sb.PredictionContext(5), stream_dataset=True)
+    b = _obj(ds, 64, 5)
+    for x, y in zip(a.shadow(q, k=70), b.shadow(q, k=70)):
+        assert np.array_equal(x, y)
+
+
 def test_unsupported_plugins_raise():
     class Cosine(sb.PathDistance):
         def forward(self, x, y):
