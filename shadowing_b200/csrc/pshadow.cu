@@ -1757,6 +1757,7 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
         fp.cf_u = 512.0f * 5.9604644775390625e-8f;
         fp.hist = fhist; fp.k = (unsigned int)k;
         fp.seed = 0; fp.seed_need = 1;
+        fp.stagger_ns = (unsigned int)env_int("PSH_FFT_STAGGER_NS", 0);
         fp.dbg = nullptr;
         { const char *e_ = getenv("PSH_FFT_DBG"); if (e_ != nullptr && e_[0] != 0) fp.dbg = reinterpret_cast<unsigned long long *>(strtoull(e_, nullptr, 0)); }
         fp.refresh_mask = (unsigned int)env_int("PSH_FFT_REFRESH", 7);

@@ -259,6 +259,7 @@ constexpr int HFINE_PER_COARSE = HB / HC;   // 128
 constexpr int H_THR = HB + HC;              // published threshold (float bits, atomicMin)
 constexpr int H_ARR = HB + HC + 1;          // seed arrivals of the launch (query 0's slot)
 constexpr int H_SLOT = HB + HC + 2;         // dynamic pair-slot counter of the launch (query 0's slot)
+constexpr int H_DONE = HB + HC + 3;         // the launch's seed thresholds have been published (query 0's slot)
 constexpr int HSTRIDE = HB + HC + 32;       // uints per query
 
 __device__ __forceinline__ int hist_base(float q2) { return (int)(__float_as_uint(8.0f * q2) >> 13) - HB; }
@@ -336,12 +337,18 @@ __global__ void __launch_bounds__(QFFT_THREADS) qfft_kernel(const float *__restr
     const int k = blockIdx.x * QFFT_K + tid / QFFT_PARTS, part = tid % QFFT_PARTS;
     const int per = (W + QFFT_PARTS - 1) / QFFT_PARTS;
     const int j0 = part * per, j1 = min(W, j0 + per);
+    // G_k = sum_j g_j exp(-2 pi i j k / N): the twiddle of the thread's first term and the step exp(2 pi i k / N)
+    // come from the exact table, the others by recurrence (<= 16 complex fp64 products: ~1e-15, far below the
+    // fp32 rounding of the result) -- a gather of the table per term made this kernel latency-bound (12 us)
     double re = 0.0, im = 0.0;
-#pragma unroll 4
+    double2 w = __ldg(tw64 + ((j0 * k) & (fftx::N - 1)));
+    const double2 w1 = __ldg(tw64 + (k & (fftx::N - 1)));
     for (int j = j0; j < j1; ++j) {
-        const double2 w = __ldg(tw64 + ((j * k) & (fftx::N - 1)));  // exp(+i theta): G_k = sum g_j exp(-i theta)
         re += qd[j] * w.x;
         im -= qd[j] * w.y;
+        const double wx = w.x * w1.x - w.y * w1.y;
+        w.y = w.x * w1.y + w.y * w1.x;
+        w.x = wx;
     }
 #pragma unroll
     for (int o = 1; o < QFFT_PARTS; o <<= 1) {
@@ -388,6 +395,7 @@ struct FftScanParams {
     float slack_coef, g_coef;
     float ub_y_coef;       // UB - LB grows by ub_y_coef * (staged energy): fp16 floor (+ the embedded scan's 2 x 16u)
     float thr_widen;       // thresholds read from the query state are widened by this factor (embedded scan)
+    unsigned int stagger_ns;   // CTAs of the second half of the grid start this much later (see the kernel)
     unsigned long long *dbg;   // optional per-CTA timeline (8 globaltimer stamps per CTA), NULL in production
 };
 
@@ -550,6 +558,39 @@ __device__ __forceinline__ void fft_append_candidates(const FftScanParams &p, in
     }
 }
 
+// End of a CTA's seeding pass: arrive (every histogram increment of this CTA is ordered before the arrival:
+// barrier + fence); the CTA whose arrival is the `seed_need`-th derives the thresholds of all queries from
+// the histograms and publishes them, every other CTA waits for that (bounded: arrivals never wait for
+// anybody) and picks them up -- 300 CTAs re-deriving the same thresholds from the same cache lines took 3 us.
+__device__ __forceinline__ void fft_seed_rendezvous(const FftScanParams &p, const float *s_q2, float *s_thr, int *s_flag) {
+    const int tid = threadIdx.x;
+    volatile unsigned int *done = p.hist + H_DONE;
+    if (tid == 0) {
+        __threadfence();
+        const unsigned int ticket = atomicAdd(p.hist + H_ARR, 1u);
+        *s_flag = (ticket + 1u == p.seed_need) ? 1 : 0;
+        if (ticket + 1u != p.seed_need) {
+            const unsigned long long t0 = globaltimer_ns();
+            while (*done == 0u) {
+                if (globaltimer_ns() - t0 > 2000000ull) break;   // 2 ms: thresholds stay loose, the call re-runs safely
+                __nanosleep(100);
+            }
+        }
+    }
+    __syncthreads();
+    if (*s_flag) {
+        if (tid < 32) {
+            for (int b = 0; b < p.nq; ++b) fft_refresh_threshold(p, b, s_q2[b], s_thr);
+            __threadfence();
+            if (tid == 0) *done = 1u;
+        }
+    } else if (tid < p.nq) {
+        const unsigned int tb = *reinterpret_cast<volatile unsigned int *>(p.hist + (size_t)tid * HSTRIDE + H_THR);
+        atomicMin(reinterpret_cast<unsigned int *>(&s_thr[tid]), tb);
+    }
+    __syncthreads();
+}
+
 // One CTA (256 threads) per row pair and iteration: Z^ * conj(Q)/N -> inverse FFT -> (D_a[t], D_b[t]);
 // lower bound
 //   LB = Q2 + Y2^ - 2 D^ - slack,
@@ -566,8 +607,9 @@ __device__ __forceinline__ void fft_append_candidates(const FftScanParams &p, in
 // query's histogram; CTAs take turns re-deriving the threshold from it (one warp, no barrier) and publish
 // it, every CTA picks the published value up once per pair.  p.seed: thresholds start at +inf; every CTA
 // first evaluates its first pair WITHOUT appending anything -- each thread adds the minimum UB of its 32
-// windows (256 distinct windows per CTA) -- waits until `seed_need` CTAs have done so (a fraction of the
-// grid: no co-residency assumption), derives its first threshold and only then tests the pair's windows
+// windows (256 distinct windows per CTA) -- and waits until `seed_need` CTAs have done so (a fraction of the
+// grid: no co-residency assumption); the `seed_need`-th derives the first threshold and publishes it, and
+// only then does a CTA test the pair's windows
 // (one query: the transform's output is still in registers; a group of queries: the pair is transformed
 // again).  This replaces round 1's separate seed launch.
 //
@@ -588,6 +630,7 @@ __global__ void __launch_bounds__(fx2::THREADS, 2) fft_scan_kernel(const FftScan
     __shared__ float s_thr[QG_MAX], s_q2[QG_MAX], s_qmax[QG_MAX], s_gn[QG_MAX];
     __shared__ __align__(16) uint4 s_pub[QG_MAX];   // {published threshold bits, ...} of each query, one pair behind
     __shared__ int s_npair[2];                       // the pair behind the current one (-1: none), by pass parity
+    __shared__ int s_flag;
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t barZ = smem_u32(&bars[0]), barY = smem_u32(&bars[1]);
     const float INF = __int_as_float(0x7f800000);
@@ -596,6 +639,13 @@ __global__ void __launch_bounds__(fx2::THREADS, 2) fft_scan_kernel(const FftScan
     if (slot >= p.i1) return;   // (a seeding launch is sized so that every CTA owns a pair)
 #define PSH_STAMP(i) do { if (p.dbg != nullptr && tid == 0) p.dbg[(size_t)blockIdx.x * 8 + (i)] = globaltimer_ns(); } while (0)
     PSH_STAMP(0);
+    // The two CTAs of an SM run the same code: started together they would sit in the same phase together --
+    // both in a radix-16 pass (the packed fp32 pipe is saturated there), then both at a barrier or in an
+    // exchange (it idles).  The second wave of CTAs starts half an iteration late so that the phases interleave.
+    if (blockIdx.x >= (gridDim.x + 1) / 2 && p.stagger_ns != 0) {
+        const unsigned long long t0 = globaltimer_ns();
+        while (globaltimer_ns() - t0 < p.stagger_ns) __nanosleep(200);
+    }
     if (tid == 0) {
         mbar_init(barZ, 1);
         mbar_init(barY, 1);
@@ -716,19 +766,7 @@ __global__ void __launch_bounds__(fx2::THREADS, 2) fft_scan_kernel(const FftScan
                 // one query: every increment of this CTA is ordered before its arrival (barrier + fence); wait
                 // for `seed_need` arrivals (bounded: a CTA that runs arrives without waiting for anybody), derive
                 // the threshold and test the windows whose transform is still in registers
-                if (tid == 0) {
-                    __threadfence();
-                    unsigned int *arr = p.hist + H_ARR;
-                    atomicAdd(arr, 1u);
-                    const unsigned long long t0 = globaltimer_ns();
-                    while (*reinterpret_cast<volatile unsigned int *>(arr) < p.seed_need) {
-                        if (globaltimer_ns() - t0 > 2000000ull) break;   // 2 ms: thresholds stay loose, the call re-runs safely
-                        __nanosleep(100);
-                    }
-                }
-                PSH_STAMP(2);
-                if (tid < 32) fft_refresh_threshold(p, 0, q2, s_thr);
-                __syncthreads();
+                fft_seed_rendezvous(p, s_q2, s_thr, &s_flag);
                 PSH_STAMP(3);
             }
             const float thr = s_thr[b];
@@ -748,20 +786,8 @@ __global__ void __launch_bounds__(fx2::THREADS, 2) fft_scan_kernel(const FftScan
             __syncthreads();  // the exchange buffer (and, after the last query, the energy rows) may be overwritten
         }
         if (seeding && rerun) {
-            // a group of queries: arrive, wait, derive every query's threshold, then the same pair again
-            if (tid == 0) {
-                __threadfence();
-                unsigned int *arr = p.hist + H_ARR;
-                atomicAdd(arr, 1u);
-                const unsigned long long t0 = globaltimer_ns();
-                while (*reinterpret_cast<volatile unsigned int *>(arr) < p.seed_need) {
-                    if (globaltimer_ns() - t0 > 2000000ull) break;
-                    __nanosleep(100);
-                }
-            }
-            if (tid < 32)
-                for (int b = 0; b < p.nq; ++b) fft_refresh_threshold(p, b, s_q2[b], s_thr);
-            __syncthreads();
+            // a group of queries: arrive, wait for the thresholds, then the same pair again
+            fft_seed_rendezvous(p, s_q2, s_thr, &s_flag);
             seeding = false;
             staged = true;
             par ^= 1;
