@@ -28,7 +28,8 @@ enum {
     PSH_E_K = -2,          /* k exceeds the number of windows (reference: torch.topk raises)  */
     PSH_E_WORKSPACE = -3,  /* workspace smaller than psh_scan_workspace_bytes()               */
     PSH_E_TOO_LARGE = -4,  /* R*T' >= 2^32 windows in one call: shard the rows and merge      */
-    PSH_E_UNSUPPORTED = -5, /* context length beyond the shared-memory budget of the scan     */
+    PSH_E_UNSUPPORTED = -5, /* context too long for the kernel asked for (direct scans: not   */
+                            /* even one query's staging fits shared memory; fft: W > 2048)    */
     PSH_E_OVERFLOW = -6     /* psh_scan_overflowed: repeat the scan without PSH_FLAG_NOSYNC   */
 };
 
@@ -38,7 +39,8 @@ enum {
     PSH_MODE_FILTER = 1, /* 1-FMA/element lower-bound filter, exact re-rank of the survivors; */
                          /* results identical to PSH_MODE_EXACT by construction               */
     PSH_MODE_FFT = 2     /* lower-bound filter through one inverse FFT per trajectory pair    */
-                         /* (needs psh_fft_prepare aux, T <= 4096; else behaves as FILTER);   */
+                         /* (needs psh_fft_prepare aux, else behaves as FILTER; trajectories  */
+                         /* longer than 4096 samples are cut into overlapping pieces);        */
                          /* same exact re-rank, results identical to PSH_MODE_EXACT           */
 };
 
@@ -128,15 +130,19 @@ int psh_scan_overflowed(const void *d_ws, int B, void *stream);
 /*
  * Dataset-side precomputation for PSH_MODE_FFT (no reference counterpart; the reference
  * recomputes everything per call).  Fills d_aux (>= psh_fft_aux_bytes, 256-byte aligned) with
- * the 4096-point spectra of all trajectory pairs, the window energies sum_{j<W} y_{t+j}^2 and
- * the pair norms.  Valid for this (dataset, W, H) only; T <= 4096 (else PSH_E_UNSUPPORTED / 0).
+ * the 4096-point spectra of all trajectory pairs quantised to fp16 pairs (per-pair power-of-two
+ * scale, measured quantisation error), the window energies sum_{j<W} y_{t+j}^2 scaled and rounded
+ * DOWN to fp16, and per-pair statistics: 8 bytes per pair of samples, the size of the raw rows.
+ * Valid for this (dataset, W, H) only; W <= 2048 (else PSH_E_UNSUPPORTED / 0); a trajectory longer
+ * than one 4096-point transform is cut into overlapping 4096-sample pieces (overlap-save).
  */
 size_t psh_fft_aux_bytes(int64_t R, int64_t T, int W, int H);
 int psh_fft_prepare(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride, int W, int H,
                     void *d_aux, size_t aux_bytes, void *stream);
 
-/* Test hook: n independent 4096-point complex transforms (dir -1 forward, +1 inverse,
- * unnormalised) with the library's FFT; d_aux is a prepared aux buffer (twiddles). */
+/* Test hook: n independent 4096-point complex transforms (dir -1 forward, +1 inverse, unnormalised,
+ * table twiddles; dir 3: the scan's own packed-fp32 inverse) with the library's FFT; d_aux is a
+ * prepared aux buffer (twiddles). */
 int psh_debug_fft4096(const void *d_in, void *d_out, int n, int dir, const void *d_aux, void *stream);
 
 /*
@@ -167,11 +173,11 @@ int psh_merge_topk_packed(const int32_t *d_rec_parts, int G, int B, int64_t k, i
  *   bufs        HOST array of G device pointers, bufs[g] = rank g's exchange buffer as mapped in
  *               this process (bufs[rank] = the own buffer)
  *   d_flag      int32, zeroed by the caller: bit 0 = a shard's NOSYNC scan overflowed,
- *               bit 1 = a peer's records did not arrive within 30 s (results invalid)
- * Each CTA stores its query's records into every rank's buffer -- every datum in one 8-byte store
- * together with the epoch, so the words validate themselves: no fence, no flag (fallback for
- * G*k*12 bytes > 200 KB: plain stores, a system-scope fence and per-(rank, query) flags) --, polls
- * the G record sets of its query and merges (same order as psh_merge_topk).
+ *               bit 1 = a peer's records did not arrive within 30 s (PSH_XCHG_TIMEOUT_MS; results invalid)
+ * G CTAs per query: CTA (g, b) stores query b's records into rank g's buffer -- every datum in one
+ * 8-byte store together with the epoch, so the words validate themselves: no fence, no flag (fallback
+ * for G*k*12 bytes > 200 KB: plain stores, a system-scope fence and per-(rank, query) flags) --, polls
+ * the G record sets of its query and places the records of list g (same order as psh_merge_topk).
  */
 size_t psh_xchg_bytes(int G, int B, int64_t k);
 int psh_xchg_create(size_t bytes, void **d_buf, unsigned char *ipc_handle_64);
@@ -185,7 +191,8 @@ int psh_allgather_merge_packed(const int32_t *d_rec_local, void *const *bufs, in
  * (wait for the G flags of the epoch, merge) -- so a pipeline of scans can enqueue
  *     scan(i+1), send(i+1), merge(i)
  * and a rank computes its next scan instead of idling until the slowest peer has delivered step i.
- * The exchange buffers hold three epochs (epoch % 3), which this order needs. */
+ * The exchange buffers hold four epochs (epoch % 4): two for one stream of fused launches, two more
+ * for this order or for a second stream alternating steps with the first. */
 int psh_xchg_send(const int32_t *d_rec_local, void *const *bufs, int G, int rank, int B, int64_t k,
                   uint32_t epoch, void *stream);
 int psh_xchg_merge(void *const *bufs, int G, int rank, int B, int64_t k, int64_t Tp, uint32_t epoch,
@@ -220,8 +227,8 @@ uint64_t psh_launch_count(void);
  * Measurement hooks (no reference counterpart): between begin and end every kernel the library
  * launches is bracketed by CUDA events on the caller's stream.  psh_profile_end waits for them
  * and returns summed milliseconds and launch counts per kind: 0 = scan kernels, 1 = select /
- * re-rank / finalise kernels, 2 = merge / peer-memory all-gather + merge kernels.  Not
- * thread-safe; for bench.py's roofline leg only.
+ * re-rank / finalise kernels, 2 = merge / peer-memory all-gather + merge kernels.  State is per
+ * calling thread (begin, the launches and end must come from the same thread); bench.py's roofline leg.
  */
 void psh_profile_begin(void);
 int psh_profile_end(double *ms_by_kind, uint64_t *launches_by_kind, int nkinds);

@@ -483,6 +483,8 @@ class PathShadowing:
         :return: numpy (distances (B,k) f32 ascending, paths (B,k,C,W+H) f32, indices (B,k,2) i32)
         """
         del n_splits, cuda
+        if self._pg is not None and torch.cuda.is_available() and type(self.context) is not CrossChannelContext:
+            return self._shadow_sharded(x_context, k)
         if self._pg is not None or not torch.cuda.is_available() or type(self.context) is CrossChannelContext:
             dist, paths, idx = self.shadow_device(x_context, k)
             return _numpy(dist), _numpy(paths), _numpy(idx)
@@ -520,6 +522,56 @@ class PathShadowing:
         nd, ni = B * k, B * k * 2
         return (flat[:nd].view(np.float32).reshape(B, k),
                 flat[nd + ni:].view(np.float32).reshape(B, k, 1, L),
+                flat[nd:nd + ni].reshape(B, k, 2))
+
+    def _shadow_sharded(self, x_context: ArrayType, k: int):
+        """`shadow` on an ensemble sharded over the process group: local scan (enqueue only), fused
+        exchange + merge, owner gather + all-reduce of the paths, then ONE device buffer
+        [dist | idx | paths | overflow flag] copied with ONE asynchronous copy into pinned memory and ONE
+        synchronisation (round 1: three pageable copies, an `.item()` on the flag, 1.0 ms at 8 GPUs)."""
+        from .distributed import flush_deferred_merge, sharded_gather
+        if self.embedding.kernel.shape[-1] != 0 and self.embedding.kernel.shape[-1] != _dim_array(x_context).shape[-1]:
+            raise Exception("The embedding kernel should be of the same size as the context.")
+        x = _torch(_dim_array(x_context))
+        rows, T = self._resident_rows()
+        B, L = x.shape[0], x.shape[-1] + self.context.get_out_times()
+        nd, ni, npth = B * k, B * k * 2, B * k * L
+        words = nd + ni + npth + 1
+        if self._staging is None or self._staging[0].numel() != words:
+            self._staging = (torch.empty(words, dtype=torch.int32, device=self._dev()), [], [0])
+        dev_buf, pool, outstanding = self._staging
+        host_buf = pool.pop() if pool else torch.empty(words, dtype=torch.int32, pin_memory=True)
+        streams, self._pipe_streams = self._pipe_streams, 1               # this call's own stream, no lanes
+        try:
+            dist, idx = self._scan_device(x, rows, T, k, nosync=True)
+        finally:
+            self._pipe_streams = streams
+        flush_deferred_merge(self)                                       # (PSH_DEFER=1: the split exchange)
+        flag = getattr(self, "_pending_flag", None)
+        self._pending_flag = None
+        paths = sharded_gather(self, rows, T, idx, L)
+        dev_buf[:nd].view(torch.float32).copy_(dist.reshape(-1))
+        dev_buf[nd:nd + ni].copy_(idx.reshape(-1))
+        dev_buf[nd + ni:nd + ni + npth].view(torch.float32).copy_(paths.reshape(-1))
+        if flag is not None:
+            dev_buf[-1:].copy_(flag)
+        else:
+            dev_buf[-1:].zero_()
+        host_buf.copy_(dev_buf, non_blocking=True)
+        torch.cuda.current_stream(dev_buf.device).synchronize()
+        flat = host_buf.numpy()
+        if int(flat[-1]) != 0:      # an overflow somewhere (every rank sees the same flag) or a peer timed out
+            pool.append(host_buf)
+            if flag is not None:
+                flag.zero_()
+            if int(flat[-1]) & 2:
+                raise RuntimeError("peer-memory all-gather: a rank did not deliver its records within the timeout")
+            dist, paths, idx = self.shadow_device(x_context, k)           # synchronous scans: the safe schedule
+            return _numpy(dist), _numpy(paths), _numpy(idx)
+        outstanding[0] += 1
+        weakref.finalize(flat, _recycle, pool, outstanding, host_buf)
+        return (flat[:nd].view(np.float32).reshape(B, k),
+                flat[nd + ni:nd + ni + npth].view(np.float32).reshape(B, k, 1, L),
                 flat[nd:nd + ni].reshape(B, k, 2))
 
     _POOL_MAX = 8   # pinned result buffers handed out at once before falling back to copies
