@@ -144,6 +144,10 @@ int psh_fft_prepare(const float *d_dataset, int64_t R, int64_t T, int64_t row_st
  * table twiddles; dir 3: the scan's own packed-fp32 inverse) with the library's FFT; d_aux is a
  * prepared aux buffer (twiddles). */
 int psh_debug_fft4096(const void *d_in, void *d_out, int n, int dir, const void *d_aux, void *stream);
+/* Test hook: n independent 1024-point complex transforms (dir +1: the scan's warp-level inverse, unnormalised;
+ * dir -1: the forward transform psh_fft_prepare uses for 1024-sample pieces), natural order in and out;
+ * d_aux is any prepared aux buffer (twiddles). */
+int psh_debug_fft1024(const void *d_in, void *d_out, int n, int dir, const void *d_aux, void *stream);
 
 /*
  * k-way merge of G per-shard results into the global top-k: replaces the cat + topk +

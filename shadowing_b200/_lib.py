@@ -62,6 +62,8 @@ def lib() -> ctypes.CDLL:
         L.psh_fft_prepare.argtypes = [vp, i64, i64, i64, ci, ci, vp, sz, vp]
         L.psh_debug_fft4096.restype = ci
         L.psh_debug_fft4096.argtypes = [vp, vp, ci, ci, vp, vp]
+        L.psh_debug_fft1024.restype = ci
+        L.psh_debug_fft1024.argtypes = [vp, vp, ci, ci, vp, vp]
         L.psh_merge_topk.restype = ci
         L.psh_merge_topk.argtypes = [vp, vp, ci, ci, i64, i64, vp, vp, vp]
         L.psh_merge_topk_packed.restype = ci
@@ -175,6 +177,18 @@ def debug_fft4096(x: torch.Tensor, direction: int, aux: torch.Tensor) -> torch.T
     with torch.cuda.device(x.device):
         rc = L.psh_debug_fft4096(x.data_ptr(), out.data_ptr(), x.shape[0], direction, aux.data_ptr(), _stream(x))
     _check(rc, "psh_debug_fft4096")
+    return out
+
+
+def debug_fft1024(x: torch.Tensor, direction: int, aux: torch.Tensor) -> torch.Tensor:
+    """x (n, 1024) complex64 cuda -> unnormalised DFT (direction -1) / inverse (+1) with the warp-level
+    transform of the 1024-point fft flavour, test hook."""
+    L = lib()
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = L.psh_debug_fft1024(x.data_ptr(), out.data_ptr(), x.shape[0], direction, aux.data_ptr(), _stream(x))
+    _check(rc, "psh_debug_fft1024")
     return out
 
 

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 
 #include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "pshadow.h"
@@ -504,6 +505,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, EXACT ? 2 : 3) scan_kernel(const
 // FFT flavour: preparation kernels, query spectrum, scan
 // ------------------------------------------------------------------------------------------
 #include "pshadow_fftscan.cuh"
+#include "pshadow_fft3.cuh"
 
 #include "pshadow_embed_fft.cuh"
 
@@ -1520,24 +1522,48 @@ static int fft_prepare_impl(const float *d_dataset, int64_t R, int64_t T, int64_
     // twiddle tables: exp(+2 pi i m / 4096) in fp64, rounded once for the fp32 copy
     static std::vector<double2> h64;
     static std::vector<float2> h32;
-    if (h64.empty()) {
-        h64.resize(fftx::N); h32.resize(fftx::N);
-        for (int m = 0; m < fftx::N; ++m) {
-            const double ang = 6.283185307179586476925286766559 * (double)m / (double)fftx::N;
-            h64[m].x = cos(ang); h64[m].y = sin(ang);
-            h32[m].x = (float)h64[m].x; h32[m].y = (float)h64[m].y;
+    static std::vector<float4> h2;   // 1024-point flavour: {w^(lane 2j), w^(lane (2j+1))} at [j * 32 + lane]
+    static std::mutex tw_mutex;
+    {
+        std::lock_guard<std::mutex> lock(tw_mutex);
+        if (h64.empty()) {
+            h64.resize(fftx::N); h32.resize(fftx::N); h2.resize(512);
+            for (int m = 0; m < fftx::N; ++m) {
+                const double ang = 6.283185307179586476925286766559 * (double)m / (double)fftx::N;
+                h64[m].x = cos(ang); h64[m].y = sin(ang);
+                h32[m].x = (float)h64[m].x; h32[m].y = (float)h64[m].y;
+            }
+            for (int j = 0; j < 16; ++j)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int m0 = (lane * 2 * j) & 1023, m1 = (lane * (2 * j + 1)) & 1023;   // powers of exp(2 pi i / 1024)
+                    h2[j * 32 + lane] = make_float4(h32[4 * m0].x, h32[4 * m0].y, h32[4 * m1].x, h32[4 * m1].y);
+                }
         }
     }
     PSH_CUDA(cudaMemcpyAsync(a.tw64, h64.data(), sizeof(double2) * fftx::N, cudaMemcpyHostToDevice, stream));
     PSH_CUDA(cudaMemcpyAsync(a.tw32, h32.data(), sizeof(float2) * fftx::N, cudaMemcpyHostToDevice, stream));
+    PSH_CUDA(cudaMemcpyAsync(a.tw2, h2.data(), sizeof(float4) * 512, cudaMemcpyHostToDevice, stream));
+    const int Tp = (int)(T - W - H + 1);
+    if (a.nfft == fx3::N) {
+        fft3_prep_spectra_kernel<<<(unsigned int)((a.npairs + 3) / 4), 128, 0, stream>>>(d_dataset, (int)T, row_stride, a);
+        PSH_LAUNCHED();
+        if (d_runs != nullptr)
+            fft_prep_energy_kernel<true, 1024><<<(unsigned int)a.npairs, fftx::THREADS, smem, stream>>>(
+                d_dataset, (int)T, row_stride, W, Tp, a, d_runs, nruns);
+        else
+            fft_prep_energy_kernel<false, 1024><<<(unsigned int)a.npairs, fftx::THREADS, 0, stream>>>(
+                d_dataset, (int)T, row_stride, W, Tp, a, nullptr, 0);
+        PSH_LAUNCHED();
+        return PSH_OK;
+    }
     fft_prep_spectra_kernel<<<(unsigned int)a.npairs, fftx::THREADS, 0, stream>>>(d_dataset, (int)T, row_stride, a);
     PSH_LAUNCHED();
     if (d_runs != nullptr)
-        fft_prep_energy_kernel<true><<<(unsigned int)a.npairs, fftx::THREADS, smem, stream>>>(
-            d_dataset, (int)T, row_stride, W, (int)(T - W - H + 1), a, d_runs, nruns);
+        fft_prep_energy_kernel<true, 4096><<<(unsigned int)a.npairs, fftx::THREADS, smem, stream>>>(
+            d_dataset, (int)T, row_stride, W, Tp, a, d_runs, nruns);
     else
-        fft_prep_energy_kernel<false><<<(unsigned int)a.npairs, fftx::THREADS, 0, stream>>>(
-            d_dataset, (int)T, row_stride, W, (int)(T - W - H + 1), a, nullptr, 0);
+        fft_prep_energy_kernel<false, 4096><<<(unsigned int)a.npairs, fftx::THREADS, 0, stream>>>(
+            d_dataset, (int)T, row_stride, W, Tp, a, nullptr, 0);
     PSH_LAUNCHED();
     return PSH_OK;
 }
@@ -1552,6 +1578,17 @@ int psh_debug_fft4096(const void *d_in, void *d_out, int n, int dir, const void 
     if (!d_in || !d_out || !d_aux || n <= 0) return PSH_E_ARG;
     fft_debug_kernel<<<n, fftx::THREADS, 0, stream>>>(static_cast<const float2 *>(d_in), static_cast<float2 *>(d_out),
                                                       static_cast<const float2 *>(d_aux), dir);
+    PSH_LAUNCHED();
+    return PSH_OK;
+}
+
+int psh_debug_fft1024(const void *d_in, void *d_out, int n, int dir, const void *d_aux, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!d_in || !d_out || !d_aux || n <= 0 || (dir != 1 && dir != -1)) return PSH_E_ARG;
+    // the twiddle table of the 1024-point flavour sits behind the two 4096-entry tables of a prepared aux buffer
+    const float4 *tw2 = reinterpret_cast<const float4 *>(static_cast<const unsigned char *>(d_aux)
+                                                         + (sizeof(float2) + sizeof(double2)) * fftx::N);
+    fft3_debug_kernel<<<(n + 3) / 4, 128, 0, stream>>>(static_cast<const float2 *>(d_in), static_cast<float2 *>(d_out), n, tw2, dir);
     PSH_LAUNCHED();
     return PSH_OK;
 }
@@ -1582,6 +1619,8 @@ constexpr size_t SMEM_FFT = sizeof(__half2) * 2 * fx2::N + sizeof(float2) * fx2:
 typedef void (*FftScanFn)(const FftScanParams);
 struct FftVariant { FftScanFn fn; int ctas_per_sm; };
 constexpr int FFT_VARIANTS = 4;                  // [query spectrum in registers][emb]
+constexpr size_t SMEM_FFT3_SINGLE = fx3::TW_BYTES + fx3::Q_BYTES + (size_t)fx3::WARPS_SINGLE * fx3::WARP_BYTES_ALIAS;
+constexpr size_t SMEM_FFT3_GROUP = fx3::TW_BYTES + (size_t)fx3::WARPS_GROUP * fx3::WARP_BYTES_SEP;
 struct DevSetup { bool done = false; FftVariant fft[FFT_VARIANTS]; };
 static DevSetup g_dev[64];
 
@@ -1624,9 +1663,16 @@ static int device_setup(DevSetup **out) {
         PSH_CUDA(cudaFuncGetAttributes(&fa, rv_aggregate_kernel));
         PSH_CUDA(cudaFuncGetAttributes(&fa, clear_sticky_kernel));
         PSH_CUDA(cudaFuncGetAttributes(&fa, fft_prep_spectra_kernel));
-        PSH_CUDA(cudaFuncGetAttributes(&fa, fft_prep_energy_kernel<false>));
-        PSH_CUDA(cudaFuncGetAttributes(&fa, fft_prep_energy_kernel<true>));
+        PSH_CUDA(cudaFuncGetAttributes(&fa, fft_prep_energy_kernel<false, 4096>));
+        PSH_CUDA(cudaFuncGetAttributes(&fa, fft_prep_energy_kernel<true, 4096>));
+        PSH_CUDA(cudaFuncGetAttributes(&fa, fft_prep_energy_kernel<false, 1024>));
+        PSH_CUDA(cudaFuncGetAttributes(&fa, fft_prep_energy_kernel<true, 1024>));
+        PSH_CUDA(cudaFuncGetAttributes(&fa, fft3_prep_spectra_kernel));
     }
+    PSH_CUDA(big_smem((fft_scan_warp_kernel<false, true>), SMEM_FFT3_SINGLE));
+    PSH_CUDA(big_smem((fft_scan_warp_kernel<true, true>), SMEM_FFT3_SINGLE));
+    PSH_CUDA(big_smem((fft_scan_warp_kernel<false, false>), SMEM_FFT3_GROUP));
+    PSH_CUDA(big_smem((fft_scan_warp_kernel<true, false>), SMEM_FFT3_GROUP));
     for (int i = 0; i < FFT_VARIANTS; ++i) {
         FftScanFn fn = fft_variant_fn((i >> 1) & 1, i & 1);
         PSH_CUDA(big_smem(fn, SMEM_FFT));
@@ -1697,8 +1743,8 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
     if (use_fft) {
         // query state + spectrum of the vector the trajectories are correlated with (the context itself,
         // or g = K^T ex for an embedded scan) + a clean threshold histogram: ONE launch
-        qfft_kernel<<<dim3(fftx::N / QFFT_K, nq), QFFT_THREADS, (size_t)W * sizeof(double), stream>>>(
-            d_q, qlen, emb ? emb->g : d_q, W, aux->tw64, qspec, st, fhist, qmaxp);
+        qfft_kernel<<<dim3(aux->nfft / QFFT_K, nq), QFFT_THREADS, (size_t)W * sizeof(double), stream>>>(
+            d_q, qlen, emb ? emb->g : d_q, W, aux->tw64, qspec, st, fhist, qmaxp, aux->nfft);
     } else {
         qprep_kernel<<<(nq + 3) / 4, 128, 0, stream>>>(d_q, qlen, nq, st);
     }
@@ -1757,10 +1803,11 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
         fp.cf_u = 512.0f * 5.9604644775390625e-8f;
         fp.hist = fhist; fp.k = (unsigned int)k;
         fp.seed = 0; fp.seed_need = 1;
+        fp.tw2 = aux->tw2; fp.ncy = aux->ncy; fp.nqmax = aux->nfft / QFFT_K;
         fp.stagger_ns = (unsigned int)env_int("PSH_FFT_STAGGER_NS", 0);
         fp.dbg = nullptr;
         { const char *e_ = getenv("PSH_FFT_DBG"); if (e_ != nullptr && e_[0] != 0) fp.dbg = reinterpret_cast<unsigned long long *>(strtoull(e_, nullptr, 0)); }
-        fp.refresh_mask = (unsigned int)env_int("PSH_FFT_REFRESH", 7);
+        fp.refresh_mask = (unsigned int)env_int("PSH_FFT_REFRESH", aux->nfft == fx3::N ? 31 : 7);
         {
             const double w1 = 1.0 + 2.0 * (double)(qlen + 8) * 5.9604644775390625e-8;
             const double we = emb ? 1.0 + 1.0 / 512.0 : 1.0;   // the exact embedded evaluation vs the true S
@@ -1773,7 +1820,8 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
             fp.slack_coef = (emb ? 20.0f : 12.0f) * 5.9604644775390625e-8f;
             fp.g_coef = emb ? 2.0f * 5.9604644775390625e-8f : 0.0f;
             // UB - LB: the fp16 floor of the staged energies (2^-10) + the embedded scan's 2 x 16u
-            fp.ub_y_coef = 9.765625e-4f * 1.01f + (emb ? 2.0f * 16.0f * 5.9604644775390625e-8f * 1.001f : 0.0f);
+            // (1024-point flavour: bf16 energies, floor of 2^-7)
+            fp.ub_y_coef = (aux->nfft == fx3::N ? 7.8125e-3f : 9.765625e-4f) * 1.01f + (emb ? 2.0f * 16.0f * 5.9604644775390625e-8f * 1.001f : 0.0f);
         }
         // one query: its spectrum streamed from L1/L2 like a group's (measured 5 % faster: no spills at 128
         // registers) or held in registers (PSH_FFT_QREG=1)
@@ -1803,11 +1851,28 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return (int)cudaGetLastError();
     };
-    auto launch_fft = [&](unsigned int grid) {
+    // 1024-point flavour: `units` are warps (one transform each), a CTA of 16 (one query) or 12 (a group) per SM
+    const bool warp_fft = use_fft && aux->nfft == fx3::N;
+    const int fft3_warps = nq == 1 ? fx3::WARPS_SINGLE : fx3::WARPS_GROUP;
+    auto launch_fft = [&](unsigned int units) {
         ProfScope ps(stream, 0);
-        fv.fn<<<grid, fx2::THREADS, SMEM_FFT, stream>>>(fp);
+        if (warp_fft) {
+            const unsigned int grid = (units + fft3_warps - 1) / fft3_warps;
+            const size_t smem = nq == 1 ? SMEM_FFT3_SINGLE : SMEM_FFT3_GROUP;
+            if (nq == 1) {
+                if (emb) fft_scan_warp_kernel<true, true><<<grid, fft3_warps * 32, smem, stream>>>(fp);
+                else fft_scan_warp_kernel<false, true><<<grid, fft3_warps * 32, smem, stream>>>(fp);
+            } else {
+                if (emb) fft_scan_warp_kernel<true, false><<<grid, fft3_warps * 32, smem, stream>>>(fp);
+                else fft_scan_warp_kernel<false, false><<<grid, fft3_warps * 32, smem, stream>>>(fp);
+            }
+        } else {
+            fv.fn<<<units, fx2::THREADS, SMEM_FFT, stream>>>(fp);
+        }
     };
-    const long long fft_grid_max = (long long)sm_count() * fv.ctas_per_sm;
+    const long long fft_grid_max = warp_fft ? (long long)sm_count() * fft3_warps : (long long)sm_count() * fv.ctas_per_sm;
+    long long fft_unit_threads = fx2::THREADS;   // seed entries per unit
+    fp.seed_group = 1;
     const bool fuse_final = k <= SEL_LIST;                  // last select also sorts and decodes
 
     // ---- seedless schedule: ONE launch over all pairs that seeds its own threshold from every CTA's
@@ -1817,10 +1882,21 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
     // k best keys.  4 launches per query.
     if (use_fft && seedless_enabled()) {
         long long ctas = p.npairs < fft_grid_max ? p.npairs : fft_grid_max;
+        if (warp_fft) {
+            // entries per warp: as few as give 4 k entries over the launch (every entry costs two atomics on
+            // a handful of addresses; the threshold's quality depends on the windows seeded, not on the entries)
+            int e = env_int("PSH_FFT_SEED_ENTRIES", 0);
+            if (e != 1 && e != 2 && e != 4 && e != 8 && e != 16 && e != 32) {
+                e = 1;
+                while (e < 32 && ctas * e < 4 * k) e *= 2;
+            }
+            fft_unit_threads = e;
+            fp.seed_group = 32 / e;
+        }
         // (k-th smallest of ctas*256 per-thread minima: with k <= half of them the hidden second-smallest
         // values of a thread cost a few per cent of threshold quality, no more)
-        if (ctas >= 1 && ctas * (long long)fx2::THREADS >= 2 * k) {
-            long long need = ctas / 4, kq = (2 * k + fx2::THREADS - 1) / fx2::THREADS;
+        if (ctas >= 1 && ctas * fft_unit_threads >= 2 * k) {
+            long long need = ctas / 4, kq = (2 * k + fft_unit_threads - 1) / fft_unit_threads;
             if (need < kq) need = kq;
             if (need > ctas) need = ctas;
             if (need < 1) need = 1;
@@ -2066,7 +2142,6 @@ static int merge_impl(const float *d_parts, const int *i_parts, int dstride, int
     if (n * 12ull <= MERGE_RANK_SMEM_MAX && !merge_sort_forced()) { use_smem = 2; smem = (size_t)n * 12; }  // merge by rank
     unsigned long long *scratch = nullptr;
     if (!use_smem) PSH_CUDA(cudaMallocAsync(&scratch, (size_t)B * npow2 * sizeof(unsigned long long), stream));
-    { DevSetup *dv_ = nullptr; int rc_ = device_setup(&dv_); if (rc_ != PSH_OK) return rc_; }
     ProfScope ps_merge(stream, 2);
     merge_kernel<<<B, SEL_THREADS, smem, stream>>>(d_parts, i_parts, dstride, istride, G, B, (unsigned int)k,
                                                    (unsigned long long)Tp, npow2, scratch, use_smem, d_out_dist,
@@ -2162,7 +2237,6 @@ static int xchg_launch(const int32_t *d_rec_local, void *const *bufs, int G, int
         x.rec[g] = reinterpret_cast<int *>(base);
         x.flags[g] = reinterpret_cast<unsigned int *>(base + rb);
     }
-    { DevSetup *dv_ = nullptr; int rc_ = device_setup(&dv_); if (rc_ != PSH_OK) return rc_; }
     x.local_rec = d_rec_local; x.G = G; x.rank = rank; x.epoch = epoch;
     x.timeout_ns = xchg_timeout_ns();
     unsigned int npow2 = 1; while (npow2 < n) npow2 <<= 1;

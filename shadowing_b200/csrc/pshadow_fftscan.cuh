@@ -13,26 +13,44 @@ struct FftAux {            // device pointers into the caller's aux buffer
     int nsegv, hop, span;  // virtual rows, see ScanParams
     long long VR;
     size_t total;
+    int nfft;              // transform length: 1024 (one warp per transform, pshadow_fft3.cuh) or 4096 (one CTA)
+    int ncy;               // nfft = 1024: 128-window groups of a piece's energy row that hold windows
+    float4 *tw2;           // nfft = 1024: {w^(lane 2j), w^(lane (2j+1))} at [j * 32 + lane], w = exp(2 pi i / 1024)
 };
+
+// Transform length of the fft flavour for a context of W samples: 1024-point pieces while a piece still
+// yields enough windows (1025 - W of 1024), the 4096-point transform beyond.  PSH_FFT_N=4096 / 1024 forces
+// one (A/B measurements, tests); prepare and scan must see the same setting.
+constexpr int FFT3_MAX_W = 384;
+inline int fft_length_for(int W) {
+    const char *e = getenv("PSH_FFT_N");
+    const int forced = (e != nullptr && e[0] != 0) ? atoi(e) : 0;
+    if (forced == 4096) return 4096;
+    if (forced == 1024 && W <= 768) return 1024;
+    return W <= FFT3_MAX_W ? 1024 : 4096;
+}
 
 inline bool fft_aux_layout(long long R, long long T, int W, int H, unsigned char *base, FftAux &a) {
     if (R <= 0 || T <= 0 || W <= 0 || W > fftx::N / 2 || H < 0 || T - W - H + 1 <= 0) return false;
     const long long Tp = T - W - H + 1;
-    if (T <= fftx::N) { a.nsegv = 1; a.hop = fftx::N; a.span = (int)Tp; }
+    a.nfft = fft_length_for(W);
+    if (T <= a.nfft) { a.nsegv = 1; a.hop = a.nfft; a.span = (int)Tp; }
     else {
-        a.hop = (fftx::N - W + 1) & ~3;                   // windows per piece
+        a.hop = (a.nfft - W + 1) & ~3;                    // windows per piece
         a.span = a.hop;
         a.nsegv = (int)((Tp + a.hop - 1) / a.hop);
     }
+    a.ncy = (a.span + 127) / 128;
     a.VR = R * (long long)a.nsegv;
     if (a.VR > 0x7fffffffLL) return false;
     a.npairs = (a.VR + 1) / 2;
     size_t off = 0;
     a.tw32 = reinterpret_cast<float2 *>(base + off); off += sizeof(float2) * fftx::N;
     a.tw64 = reinterpret_cast<double2 *>(base + off); off += sizeof(double2) * fftx::N;
+    a.tw2 = reinterpret_cast<float4 *>(base + off); off += sizeof(float4) * 512;
     a.pinfo = reinterpret_cast<float4 *>(base + off); off += (sizeof(float4) * (size_t)a.npairs + 255) / 256 * 256;
-    a.Z = reinterpret_cast<__half2 *>(base + off); off += sizeof(__half2) * fftx::N * (size_t)a.npairs;
-    a.Y2 = reinterpret_cast<__half2 *>(base + off); off += sizeof(__half2) * fftx::N * (size_t)a.npairs;
+    a.Z = reinterpret_cast<__half2 *>(base + off); off += sizeof(__half2) * (size_t)a.nfft * (size_t)a.npairs;
+    a.Y2 = reinterpret_cast<__half2 *>(base + off); off += sizeof(__half2) * (size_t)a.nfft * (size_t)a.npairs;
     a.total = off;
     return true;
 }
@@ -155,11 +173,16 @@ __global__ void __launch_bounds__(fftx::THREADS) fft_prep_spectra_kernel(const f
 // where the virtual row owns no window.  Identity: Y2[t] = sum_{j<W} y_{t+j}^2 from an fp64 prefix sum.
 // EMBK (pshadow_embed_fft.cuh): E2[t] = sum_n e_n(t)^2 (1 - 16u) from an fp64 prefix sum of y and the
 // kernel's runs.  One CTA per pair.
-template <bool EMBK>
+template <int NFFT> __device__ __forceinline__ int fft_window_of_pos(int pos);
+template <> __device__ __forceinline__ int fft_window_of_pos<4096>(int pos) { return fx2::out_base(pos & 255) + (pos & ~255); }
+template <> __device__ __forceinline__ int fft_window_of_pos<1024>(int pos) { const int j = pos & 3, l = (pos >> 2) & 31, g = pos >> 7; return l + 32 * (4 * g + j); }
+
+template <bool EMBK, int NFFT>
 __global__ void __launch_bounds__(fftx::THREADS) fft_prep_energy_kernel(const float *__restrict__ ds, int T,
                                                                         long long row_stride, int W, int Tp, FftAux a,
                                                                         const EmbRun *__restrict__ runs, int nruns) {
-    __shared__ double pfx[fftx::N + 1];
+    constexpr int PER = NFFT / fftx::THREADS;   // samples (and output positions) per thread
+    __shared__ double pfx[NFFT + 1];
     __shared__ double wsum[8];
     __shared__ float redf[8];
     extern __shared__ EmbRun runs_s[];
@@ -167,7 +190,7 @@ __global__ void __launch_bounds__(fftx::THREADS) fft_prep_energy_kernel(const fl
     if (EMBK)
         for (int i = tid; i < nruns; i += fftx::THREADS) runs_s[i] = runs[i];
     const long long pair = blockIdx.x;
-    float en[2][16];
+    float en[2][PER];
     float mx = 0.0f;
     const float INF = __int_as_float(0x7f800000);
 #pragma unroll
@@ -178,11 +201,11 @@ __global__ void __launch_bounds__(fftx::THREADS) fft_prep_energy_kernel(const fl
         const int piece = (int)((have ? vr : 2 * pair) - row * a.nsegv);
         const int o0 = piece * a.hop;                     // first sample / window of this virtual row
         const float *y = ds + row * row_stride + o0;
-        double loc[16];
+        double loc[PER];
         double run = 0.0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int n = 16 * tid + i;
+        for (int i = 0; i < PER; ++i) {
+            const int n = PER * tid + i;
             const double x = o0 + n < T ? (double)y[n] : 0.0;
             run += EMBK ? x : x * x;
             loc[i] = run;
@@ -200,12 +223,12 @@ __global__ void __launch_bounds__(fftx::THREADS) fft_prep_energy_kernel(const fl
         for (int w = 0; w < warp; ++w) off += wsum[w];
         if (tid == 0) pfx[0] = 0.0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pfx[16 * tid + i + 1] = off + loc[i];
+        for (int i = 0; i < PER; ++i) pfx[PER * tid + i + 1] = off + loc[i];
         __syncthreads();
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
+        for (int c = 0; c < PER; ++c) {
             const int pos = tid + 256 * c;
-            const int t = fx2::out_base(pos & 255) + (pos & ~255);  // position pos holds window kb(pos & 255) + 256 (pos >> 8)
+            const int t = fft_window_of_pos<NFFT>(pos);   // the window the scan's epilogue finds at position pos
             const bool mine = have && t < a.span && o0 + t < Tp;   // the windows this virtual row owns
             float out = INF;
             if (mine) {
@@ -230,13 +253,20 @@ __global__ void __launch_bounds__(fftx::THREADS) fft_prep_energy_kernel(const fl
     float es = pow2_scale(block_max_256(mx, redf), 15);   // largest energy in [2^14, 2^15)
     float m2 = -2.0f * es / zs;
     if (!(fabsf(m2) < __int_as_float(0x7f800000)) || fabsf(m2) < 1e-30f) { es = zs; m2 = -2.0f; }
-    __half2 *o = a.Y2 + (size_t)pair * fftx::N;
+    __half2 *o = a.Y2 + (size_t)pair * NFFT;
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
+    for (int c = 0; c < PER; ++c) {
         // a finite energy stays finite (a clamped value is still a lower bound); +inf marks "no window"
         const float ea = en[0][c] < INF ? fminf(en[0][c] * es, 65504.0f) : INF;
         const float eb = en[1][c] < INF ? fminf(en[1][c] * es, 65504.0f) : INF;
-        o[tid + 256 * c] = __halves2half2(__float2half_rd(ea), __float2half_rd(eb));
+        if (NFFT == 1024) {
+            // 1024-point flavour: bf16 pairs (the scan unpacks them on the integer pipe); the values are >= 0,
+            // so dropping the low 16 bits rounds DOWN; +inf stays +inf
+            const unsigned int w = (__float_as_uint(ea) >> 16) | (__float_as_uint(eb) & 0xffff0000u);
+            reinterpret_cast<unsigned int *>(o)[tid + 256 * c] = w;
+        } else {
+            o[tid + 256 * c] = __halves2half2(__float2half_rd(ea), __float2half_rd(eb));
+        }
     }
     if (tid == 0) {
         a.pinfo[pair].z = es;
@@ -317,14 +347,15 @@ __device__ __forceinline__ void qstate_init(const float *__restrict__ x, int n, 
 __global__ void __launch_bounds__(QFFT_THREADS) qfft_kernel(const float *__restrict__ q, int qlen,
                                                             const float *__restrict__ g, int W,
                                                             const double2 *__restrict__ tw64, float2 *Qc, QState *st,
-                                                            unsigned int *hist, float *qmaxp) {
+                                                            unsigned int *hist, float *qmaxp, int nfft) {
     extern __shared__ double qd[];
     __shared__ double red[QFFT_THREADS / 32];
     const int b = blockIdx.y, tid = threadIdx.x;
     for (int j = tid; j < W; j += QFFT_THREADS) qd[j] = (double)g[(size_t)b * W + j];
     // this query's threshold histogram starts at zero, its published threshold at +inf
     unsigned int *hq = hist + (size_t)b * HSTRIDE;
-    if (tid < HB / QMAXP) hq[blockIdx.x * (HB / QMAXP) + tid] = 0u;
+    const int zb = HB / (int)gridDim.x;   // fine bins this CTA clears (gridDim.x = nfft / 16 divides HB)
+    for (int i = tid; i < zb; i += QFFT_THREADS) hq[blockIdx.x * zb + i] = 0u;
     if (blockIdx.x == 0 && tid < HSTRIDE - HB) hq[HB + tid] = (HB + tid == H_THR) ? 0x7f800000u : 0u;
     __syncthreads();
     if (blockIdx.x == 0 && tid < 32) {   // ||g||_2 of the correlated vector, rounded up; the query state
@@ -341,8 +372,9 @@ __global__ void __launch_bounds__(QFFT_THREADS) qfft_kernel(const float *__restr
     // come from the exact table, the others by recurrence (<= 16 complex fp64 products: ~1e-15, far below the
     // fp32 rounding of the result) -- a gather of the table per term made this kernel latency-bound (12 us)
     double re = 0.0, im = 0.0;
-    double2 w = __ldg(tw64 + ((j0 * k) & (fftx::N - 1)));
-    const double2 w1 = __ldg(tw64 + (k & (fftx::N - 1)));
+    const int tws = fftx::N / nfft;       // the table holds exp(2 pi i m / 4096)
+    double2 w = __ldg(tw64 + ((j0 * k * tws) & (fftx::N - 1)));
+    const double2 w1 = __ldg(tw64 + ((k * tws) & (fftx::N - 1)));
     for (int j = j0; j < j1; ++j) {
         re += qd[j] * w.x;
         im -= qd[j] * w.y;
@@ -355,7 +387,9 @@ __global__ void __launch_bounds__(QFFT_THREADS) qfft_kernel(const float *__restr
         re += __shfl_xor_sync(FULL, re, o);
         im += __shfl_xor_sync(FULL, im, o);
     }
-    if (part == 0) Qc[(size_t)b * fftx::N + k] = make_float2((float)(re / fftx::N), (float)(-im / fftx::N));
+    // (1024-point flavour: the order in which a lane of the scan fetches its 32 values, see pshadow_fft3.cuh)
+    if (part == 0) Qc[(size_t)b * fftx::N + (nfft == fftx::N ? k : ((((k >> 5) >> 1) * 32 + (k & 31)) * 2 + ((k >> 5) & 1)))] =
+        make_float2((float)(re / nfft), (float)(-im / nfft));
     double mx = re * re + im * im;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
@@ -395,6 +429,9 @@ struct FftScanParams {
     float slack_coef, g_coef;
     float ub_y_coef;       // UB - LB grows by ub_y_coef * (staged energy): fp16 floor (+ the embedded scan's 2 x 16u)
     float thr_widen;       // thresholds read from the query state are widened by this factor (embedded scan)
+    const float4 *tw2;     // 1024-point flavour: twiddle table, energy groups per piece, partial maxima per query
+    int ncy, nqmax;
+    int seed_group;        // 1024-point flavour: lanes per seed entry (32 / entries per warp)
     unsigned int stagger_ns;   // CTAs of the second half of the grid start this much later (see the kernel)
     unsigned long long *dbg;   // optional per-CTA timeline (8 globaltimer stamps per CTA), NULL in production
 };

@@ -249,7 +249,7 @@ class PathShadowing:
         # aux -- a data_ptr() key could be recycled by the caching allocator for the next same-shaped y
         if self._resident is None or rows is not self._resident[1]:
             return _lib.PSH_MODE_FFT, _lib.fft_prepare(rows, T, W, H)
-        key = (T, W, H)
+        key = (T, W, H, os.environ.get("PSH_FFT_N", ""))   # (the library picks the transform length from W and this knob)
         if self._fft_aux is None or self._fft_aux[0] != key or self._fft_aux[2] is not rows:
             self._fft_aux = (key, _lib.fft_prepare(rows, T, W, H), rows)
         return _lib.PSH_MODE_FFT, self._fft_aux[1]
@@ -361,7 +361,7 @@ class PathShadowing:
             return {}
         kernel = self._scan_kernel()
         runs = self._run_table(rows.device)
-        key = (T, W, H, kernel.data_ptr(), kernel._version)
+        key = (T, W, H, kernel.data_ptr(), kernel._version, os.environ.get("PSH_FFT_N", ""))
         resident = self._resident is not None and rows is self._resident[1]
         if not resident:   # a foreign `y`: throwaway aux (see _mode_and_aux)
             K = kernel.detach().cpu()[:, 0, :].double()

@@ -112,6 +112,54 @@ def test_fft4096_matches_numpy_and_error_budget():
     assert err < 16 * bound_unit, (err / bound_unit)   # CF = 512 leaves >= 32x head-room
 
 
+def test_fft1024_matches_numpy_and_error_budget():
+    """The warp-level 1024-point transform (pshadow_fft3.cuh) against numpy (fp64), both directions, and the
+    constant the lower bound relies on, through the full pipeline forward -> conj(Q)/N -> inverse."""
+    rng = np.random.default_rng(1)
+    ds = (rng.standard_normal((6, 1024)) * 0.01).astype(np.float32)
+    aux = _lib.fft_prepare(torch.tensor(ds).cuda(), 1024, 252, 20)
+    z = (rng.standard_normal((7, 1024)) + 1j * rng.standard_normal((7, 1024))).astype(np.complex64)
+    zd = torch.tensor(z).cuda()
+    for direction, ref in ((-1, np.fft.fft(z.astype(np.complex128), axis=1)),
+                           (1, np.fft.ifft(z.astype(np.complex128), axis=1) * 1024)):
+        out = _lib.debug_fft1024(zd, direction, aux).cpu().numpy()
+        err = np.linalg.norm(out - ref, axis=1) / np.linalg.norm(ref, axis=1)
+        assert err.max() < 40 * 2.0 ** -24, (direction, err)
+    q = (rng.standard_normal(252) * 0.01).astype(np.float32)
+    pair = (ds[0] + 1j * ds[1]).astype(np.complex64)[None]
+    Z = _lib.debug_fft1024(torch.tensor(pair).cuda(), -1, aux)
+    Q = np.fft.fft(np.pad(q.astype(np.float64), (0, 1024 - 252)))
+    Qc = torch.tensor((np.conj(Q) / 1024).astype(np.complex64)).cuda()
+    c = _lib.debug_fft1024(Z * Qc[None], 1, aux).cpu().numpy()[0]
+    Tp = 1024 - 252 + 1
+    ca = np.array([np.dot(q.astype(np.float64), ds[0, t:t + 252].astype(np.float64)) for t in range(Tp)])
+    cb = np.array([np.dot(q.astype(np.float64), ds[1, t:t + 252].astype(np.float64)) for t in range(Tp)])
+    err = max(np.abs(c.real[:Tp] - ca).max(), np.abs(c.imag[:Tp] - cb).max())
+    bound_unit = 2.0 ** -24 * np.abs(Q).max() * np.sqrt((ds[0].astype(np.float64) ** 2).sum() + (ds[1].astype(np.float64) ** 2).sum())
+    assert err < 16 * bound_unit, (err / bound_unit)   # CF = 512 leaves >= 32x head-room
+
+
+@pytest.mark.parametrize("nfft", ["1024", "4096"])
+@pytest.mark.parametrize("R,T,W,H,k,B", [
+    (2048, 4096, 252, 20, 1024, 1),   # north-star window/k: seedless schedule, one query (spectrum staged in the tile)
+    (2048, 4096, 252, 20, 1024, 3),   # a group of queries (separate spectrum buffer, the pair transformed twice while seeding)
+    (600, 3000, 500, 10, 200, 2),     # long context: 1024-point pieces yield 525 windows each
+    (37, 1024, 64, 0, 50, 1),         # T = one piece exactly
+    (9, 1030, 300, 3, 40, 2),         # a second piece holding a handful of windows
+    (3, 5000, 380, 0, 4000, 1),       # odd number of rows, k close to the number of windows
+])
+def test_fft_flavours_bit_exact(R, T, W, H, k, B, nfft, monkeypatch):
+    """Both transform lengths of the fft flavour (warp-level 1024-point pieces / CTA-level 4096-point rows),
+    forced through PSH_FFT_N, against the oracle."""
+    monkeypatch.setenv("PSH_FFT_N", nfft)
+    ds, q = make_inputs(R, T, W, B, seed=4000 + R)
+    obj = _obj(ds, W, H or None, scan_mode="fft")
+    d, paths, idx = obj.shadow(q, k=k)
+    do, po, io = oracle.shadow(ds, q, k, H)
+    assert_topk_equal(d, idx, do, io)
+    assert np.array_equal(paths, po)
+
+
 def _perm_stride(R):
     if R <= 2:
         return 1
