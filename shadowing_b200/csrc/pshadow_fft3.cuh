@@ -187,11 +187,14 @@ __device__ __forceinline__ void ifft1024(float2 (&v)[32], float2 *ex, const floa
 
 }  // namespace fx3
 
-// atomicAdd whose result is NOT needed right away: the compiler turns a plain atomicAdd under a lane predicate into
-// its warp-aggregated form (vote, one atomic, shuffle of the result) and the shuffle waits for the round trip
-__device__ __forceinline__ unsigned int atom_add_relaxed(unsigned int *p, unsigned int v) {
-    unsigned int r;
-    asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "r"(v));
+// atomicAdd by LANE 0 whose result is not needed right away.  ptxas turns an atomic add on a warp-uniform address
+// into its warp-aggregated form (vote, one atomic, SHFL of the result) -- also for inline PTX, also under a
+// lane predicate -- and the shuffle waits for the round trip (8 % of all warp samples sat there).  An address
+// that formally depends on %laneid (0 for the only caller) keeps the plain instruction.
+__device__ __forceinline__ unsigned int atom_add_lane0(unsigned int *p, unsigned int v) {
+    unsigned int r, l;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
+    asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], %2;" : "=r"(r) : "l"(p + l), "r"(v));
     return r;
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -363,7 +366,12 @@ __device__ __forceinline__ void fft3_append_candidates(const FftScanParams &p, i
 // End of a WARP's seeding pass: arrive (every histogram increment of this warp is ordered before the arrival:
 // __syncwarp + fence); the warp whose arrival is the `seed_need`-th derives the thresholds of all queries and
 // publishes them, every other warp waits for that (bounded: arrivals never wait for anybody) and picks them up.
-__device__ __forceinline__ void fft3_seed_rendezvous(const FftScanParams &p, const float *s_q2, float *s_thr, int lane) {
+// Only ONE warp per CTA polls the global flag (the first of the CTA to get here) and relays it through shared
+// memory: 2368 warps polling one L2 line every 200 ns kept the line so busy that the arrivals and the
+// publication themselves queued behind the polls (measured: 12 us from the median arrival to the release).
+// s_seed[0]: ticket of the CTA's poller, s_seed[1]: the launch's thresholds are published.
+__device__ __forceinline__ void fft3_seed_rendezvous(const FftScanParams &p, const float *s_q2, float *s_thr, int lane,
+                                                     volatile unsigned int *s_seed) {
     volatile unsigned int *done = p.hist + H_DONE;
     __syncwarp();
     int last = 0;
@@ -372,10 +380,12 @@ __device__ __forceinline__ void fft3_seed_rendezvous(const FftScanParams &p, con
         const unsigned int ticket = atomicAdd(p.hist + H_ARR, 1u);
         last = (ticket + 1u == p.seed_need) ? 1 : 0;
         if (!last) {
+            const bool poller = atomicAdd(const_cast<unsigned int *>(&s_seed[0]), 1u) == 0u;
             const unsigned long long t0 = globaltimer_ns();
-            while (*done == 0u) {
+            while (s_seed[1] == 0u) {
+                if (poller && *done != 0u) { s_seed[1] = 1u; break; }
                 if (globaltimer_ns() - t0 > 2000000ull) break;   // 2 ms: thresholds stay loose, the call re-runs safely
-                __nanosleep(200);
+                __nanosleep(poller ? 250 : 100);
             }
         }
     }
@@ -386,6 +396,7 @@ __device__ __forceinline__ void fft3_seed_rendezvous(const FftScanParams &p, con
         if (lane == 0) {
             __threadfence();
             *done = 1u;
+            s_seed[1] = 1u;
         }
     } else if (lane < p.nq) {
         const unsigned int tb = *reinterpret_cast<volatile unsigned int *>(p.hist + (size_t)lane * HSTRIDE + H_THR);
@@ -407,6 +418,7 @@ template <bool EMB, bool SINGLE>
 __global__ void __launch_bounds__(fx3::WARPS_SINGLE * 32, 1) fft_scan_warp_kernel(const FftScanParams p) {
     extern __shared__ __align__(128) unsigned char fsm[];
     __shared__ float s_thr[QG_MAX], s_q2[QG_MAX], s_qmax[QG_MAX], s_gn[QG_MAX];
+    __shared__ unsigned int s_seed[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     constexpr bool single = SINGLE;   // one query: its spectrum in shared memory, the pair's spectrum staged inside the tile
     const float INF = __int_as_float(0x7f800000);
@@ -438,6 +450,7 @@ __global__ void __launch_bounds__(fx3::WARPS_SINGLE * 32, 1) fft_scan_warp_kerne
         mbar_init(barY, 1);
         mbar_fence_init();
     }
+    if (tid < 2) s_seed[tid] = 0u;
     __syncthreads();
     for (int b = 0; b < p.nq; ++b) {   // max_k |FFT(q)_k| from the partial maxima (positive floats order as uints)
         float m = 0.0f;
@@ -451,6 +464,9 @@ __global__ void __launch_bounds__(fx3::WARPS_SINGLE * 32, 1) fft_scan_warp_kerne
     const int gw = (int)blockIdx.x * nw + warp, tw = (int)gridDim.x * nw;
     const int slot = p.i0 + gw;
     if (slot >= p.i1) return;   // (a seeding launch is sized so that every warp owns a pair)
+    // optional per-warp timeline (8 globaltimer stamps per warp; tests/timeline.py), NULL in production
+#define PSH_STAMP3(i) do { if (p.dbg != nullptr && lane == 0) p.dbg[(size_t)gw * 8 + (i)] = globaltimer_ns(); } while (0)
+    PSH_STAMP3(0);
 
     const uint32_t ybytes = (uint32_t)p.ncy * 512u;
     auto issue_z = [&](int pr) {  // lane 0
@@ -475,7 +491,7 @@ __global__ void __launch_bounds__(fx3::WARPS_SINGLE * 32, 1) fft_scan_warp_kerne
         // lane 0 draws the slot behind this pair now; the atomic's round trip hides behind the first pass
         const bool draw = !(seeding && rerun);
         unsigned int drawn = 0;
-        if (draw && lane == 0) drawn = atom_add_relaxed(p.hist + H_SLOT, 1u);
+        if (draw && lane == 0) drawn = atom_add_lane0(p.hist + H_SLOT, 1u);
         // thresholds other warps have published: fetched now, merged at the end of the iteration
         const bool pick = ((iter + gw) & 3) == 0;
         unsigned int pub = 0x7f800000u;
@@ -562,7 +578,9 @@ __global__ void __launch_bounds__(fx3::WARPS_SINGLE * 32, 1) fft_scan_warp_kerne
                 const unsigned int same = __match_any_sync(FULL, cnt ? bin : HB + lane);
                 if (cnt && lane == __ffs(same) - 1) hist_add_ub(p.hist + (size_t)b * HSTRIDE, bin, (unsigned int)__popc(same));
                 if (rerun) continue;
-                fft3_seed_rendezvous(p, s_q2, s_thr, lane);
+                PSH_STAMP3(1);
+                fft3_seed_rendezvous(p, s_q2, s_thr, lane, s_seed);
+                PSH_STAMP3(2);
             }
             const float thr = s_thr[b];
             const float tdiff = thr - base0;
@@ -586,7 +604,7 @@ __global__ void __launch_bounds__(fx3::WARPS_SINGLE * 32, 1) fft_scan_warp_kerne
         }
         if (seeding && rerun) {
             // a group of queries: arrive, wait for the thresholds, then the same pair again
-            fft3_seed_rendezvous(p, s_q2, s_thr, lane);
+            fft3_seed_rendezvous(p, s_q2, s_thr, lane, s_seed);
             seeding = false;
             staged = true;
             continue;
@@ -596,7 +614,11 @@ __global__ void __launch_bounds__(fx3::WARPS_SINGLE * 32, 1) fft_scan_warp_kerne
         __syncwarp();   // every lane is done with the staged energies
         if (lane == 0 && npair >= 0) issue_y(npair);
         if (pick && lane < p.nq && pub < __float_as_uint(s_thr[lane])) atomicMin(reinterpret_cast<unsigned int *>(&s_thr[lane]), pub);
-        if (npair < 0) break;
+        if (iter == 0) PSH_STAMP3(3);
+        if (iter == 1) PSH_STAMP3(4);
+        if (iter == 8) PSH_STAMP3(5);
+        if (iter == 24) PSH_STAMP3(6);
+        if (npair < 0) { PSH_STAMP3(7); break; }
         if (((iter + gw) & p.refresh_mask) == 0)
             for (int b = 0; b < p.nq; ++b) fft_refresh_threshold(p, b, s_q2[b], s_thr);
         pair = npair;

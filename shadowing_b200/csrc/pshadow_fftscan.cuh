@@ -287,10 +287,12 @@ constexpr int HB = 8192;
 constexpr int HC = 64;
 constexpr int HFINE_PER_COARSE = HB / HC;   // 128
 constexpr int H_THR = HB + HC;              // published threshold (float bits, atomicMin)
-constexpr int H_ARR = HB + HC + 1;          // seed arrivals of the launch (query 0's slot)
-constexpr int H_SLOT = HB + HC + 2;         // dynamic pair-slot counter of the launch (query 0's slot)
-constexpr int H_DONE = HB + HC + 3;         // the launch's seed thresholds have been published (query 0's slot)
-constexpr int HSTRIDE = HB + HC + 32;       // uints per query
+// (each in a 128-byte line of its own: the arrivals, the slot draws and the polls of `done` come from every
+// CTA / warp of the launch and must not queue up behind one another in one L2 line)
+constexpr int H_ARR = HB + HC + 32;         // seed arrivals of the launch (query 0's slot)
+constexpr int H_SLOT = HB + HC + 64;        // dynamic pair-slot counter of the launch (query 0's slot)
+constexpr int H_DONE = HB + HC + 96;        // the launch's seed thresholds have been published (query 0's slot)
+constexpr int HSTRIDE = HB + HC + 128;      // uints per query
 
 __device__ __forceinline__ int hist_base(float q2) { return (int)(__float_as_uint(8.0f * q2) >> 13) - HB; }
 // one entry (`n` of them in the same bin) for the upper bound ub >= 0
