@@ -463,7 +463,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                          "traffic": traffic, "peak_kind": peak_kind,
-                         "kernel": "fft_scan_kernel (one launch per query; seeds its own threshold)",
+                         "kernel": "fft_scan_warp_kernel (one warp per 1024-point transform; one launch per query, seeds its own threshold)",
                          "kernel_ms_per_step": scan_ms_per_step, "kernel_launches_per_step": n_kind[0] / args.steps,
                          "select_ms_per_step": ms_kind[1] / args.steps,
                          "merge_ms_per_step": ms_kind[2] / args.steps,

@@ -47,6 +47,10 @@ enum {
 /* OR-ed into `mode`: enqueue only, do not synchronise; the caller must call
  * psh_scan_overflowed() (which synchronises) before trusting the results. */
 #define PSH_FLAG_NOSYNC 0x100
+/* OR-ed into `mode`: this scan is one of a pipeline alternating between streams -- its persistent scan kernel
+ * leaves six SMs (PSH_SPARE_SMS) to the other streams' small kernels (re-rank, select, exchange), which would
+ * otherwise wait until the scan has drained.  Results are unaffected. */
+#define PSH_FLAG_SHARE_SMS 0x200
 
 int psh_version(void);
 const char *psh_error_string(int code);
@@ -94,7 +98,7 @@ int psh_scan_topk_f32(const float *d_dataset, int64_t R, int64_t T, int64_t row_
  *            windows itself, as path_shadowing.py:138 does)
  *   d_runs   (nruns) records {int32 row, int32 a, int32 b, float c}: kernel[row][a..b) == c,
  *            0 <= a < b <= W, rows ascending (rows without runs are all-zero taps)
- *   flags    0 or PSH_FLAG_NOSYNC;   everything else as psh_scan_topk_f32 (same workspace size)
+ *   flags    0, PSH_FLAG_NOSYNC and / or PSH_FLAG_SHARE_SMS;   everything else as psh_scan_topk_f32 (same workspace size)
  *
  * Distances follow the reference's sequence over the embedded dimensions (s accumulated n
  * ascending, non-fused; sqrt; divide by ||ex|| in torch's order); the embedded values themselves

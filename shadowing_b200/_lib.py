@@ -15,6 +15,7 @@ PSH_MODE_EXACT = 0
 PSH_MODE_FILTER = 1
 PSH_MODE_FFT = 2
 PSH_FLAG_NOSYNC = 0x100
+PSH_FLAG_SHARE_SMS = 0x200
 PSH_E_OVERFLOW = -6
 FFT_MAX_W = 2048   # psh_fft_prepare: context length at most half a 4096-point transform
 AGG_MAX_T = 16     # psh_rv_aggregate: maturities per launch (more: the host aggregation)

@@ -518,7 +518,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, EXACT ? 2 : 3) scan_kernel(const
 // ------------------------------------------------------------------------------------------
 constexpr int RR_WARPS = 4;
 constexpr int RR_THREADS = RR_WARPS * 32;
-constexpr int RR_JC = 256;          // reduction steps staged per pass
+constexpr int RR_JC = 128;          // reduction steps staged per pass (66 KB per CTA: three CTAs per SM, so the re-rank of a pipelined
+                                    // scan gets through on the two SMs the neighbouring stream's scan leaves free)
 constexpr int RR_WP = RR_JC + 1;    // tile row stride (floats)
 
 
@@ -1732,7 +1733,8 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
                           const float *d_q, int nq, int W, int H, long long k, int row_offset,
                           const Plan &pl, QState *st, unsigned long long *keys, unsigned int *cand, float2 *qspec,
                           unsigned int *fhist, float *qmaxp, const FftAux *aux, int mode, bool safe,
-                          float *d_out_dist, int *d_out_idx, cudaStream_t stream, const EmbParams *emb = nullptr) {
+                          float *d_out_dist, int *d_out_idx, cudaStream_t stream, const EmbParams *emb = nullptr,
+                          int spare_sms = 0) {
     (void)H;
     DevSetup *dv = nullptr;
     { int rc_ = device_setup(&dv); if (rc_ != PSH_OK) return rc_; }
@@ -1843,7 +1845,7 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
                 d_dataset, row_stride, (unsigned int)pl.Tp, W, emb->d, d_q, ep.runs, ep.nruns, st, cand, keys, pl.cap);
         } else {
             unsigned int rb = (pl.cap + RR_THREADS - 1) / RR_THREADS;
-            const unsigned int rb_max = (unsigned int)sm_count() * 2u;
+            const unsigned int rb_max = (unsigned int)sm_count() * 3u;
             if (rb > rb_max) rb = rb_max;
             rerank_kernel<<<dim3(rb, nq), RR_THREADS, smem_rr, stream>>>(
                 d_dataset, row_stride, (unsigned int)pl.Tp, W, d_q, st, cand, keys, pl.cap);
@@ -1870,7 +1872,9 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
             fv.fn<<<units, fx2::THREADS, SMEM_FFT, stream>>>(fp);
         }
     };
-    const long long fft_grid_max = warp_fft ? (long long)sm_count() * fft3_warps : (long long)sm_count() * fv.ctas_per_sm;
+    // (a pipelined scan leaves `spare_sms` SMs to the other streams' small kernels)
+    const int fft_sms = sm_count() - spare_sms > 0 ? sm_count() - spare_sms : 1;
+    const long long fft_grid_max = warp_fft ? (long long)fft_sms * fft3_warps : (long long)fft_sms * fv.ctas_per_sm;
     long long fft_unit_threads = fx2::THREADS;   // seed entries per unit
     fp.seed_group = 1;
     const bool fuse_final = k <= SEL_LIST;                  // last select also sorts and decodes
@@ -2000,7 +2004,8 @@ static int scan_entry(const float *d_dataset, int64_t R, int64_t T, int64_t row_
     cudaStream_t stream = (cudaStream_t)stream_;
     const int qstride = emb ? emb->d : W;   // floats per query in d_queries
     const bool nosync = (mode & PSH_FLAG_NOSYNC) != 0;
-    mode &= ~PSH_FLAG_NOSYNC;
+    const int spare_sms = (mode & PSH_FLAG_SHARE_SMS) ? env_int("PSH_SPARE_SMS", 6) : 0;
+    mode &= ~(PSH_FLAG_NOSYNC | PSH_FLAG_SHARE_SMS);
     if (mode != PSH_MODE_EXACT && mode != PSH_MODE_FILTER && mode != PSH_MODE_FFT) return PSH_E_ARG;
     if (!d_dataset || !d_queries || !d_out_dist || !d_ws) return PSH_E_ARG;  // d_out_idx NULL: packed records
     if (row_stride < T) return PSH_E_ARG;
@@ -2046,7 +2051,8 @@ static int scan_entry(const float *d_dataset, int64_t R, int64_t T, int64_t row_
                               pl, st + g0, keys + (size_t)g0 * 2 * pl.cap, cand + (size_t)g0 * pl.cap,
                               qspec + (size_t)g0 * fftx::N, fhist_all + (size_t)g0 * HSTRIDE, qmaxp_all + (size_t)g0 * QMAXP,
                               auxp, mode, safe, d_out_dist + (size_t)g0 * k * (d_out_idx ? 1 : 3),
-                              d_out_idx ? d_out_idx + (size_t)g0 * k * 2 : nullptr, stream, group_emb(g0, eg));
+                              d_out_idx ? d_out_idx + (size_t)g0 * k * 2 : nullptr, stream, group_emb(g0, eg),
+                              safe ? 0 : spare_sms);
     };
     for (int g0 = 0; g0 < B; g0 += QG) {
         int rc = run_group(g0, B - g0 < QG ? B - g0 : QG, false);
@@ -2091,7 +2097,7 @@ int psh_scan_topk_embed_f32(const float *d_dataset, int64_t R, int64_t T, int64_
                             int32_t row_offset, int flags, const void *d_runs, int nruns,
                             const float *d_g, const void *d_aux, size_t aux_bytes,
                             float *d_out_dist, int32_t *d_out_idx, void *d_ws, size_t ws_bytes, void *stream_) {
-    if (!d_runs || nruns <= 0 || d <= 0 || (flags & ~PSH_FLAG_NOSYNC) != 0) return PSH_E_ARG;
+    if (!d_runs || nruns <= 0 || d <= 0 || (flags & ~(PSH_FLAG_NOSYNC | PSH_FLAG_SHARE_SMS)) != 0) return PSH_E_ARG;
     if (d_aux != nullptr && d_g == nullptr) return PSH_E_ARG;
     EmbParams ep;
     ep.runs = static_cast<const EmbRun *>(d_runs);

@@ -329,8 +329,8 @@ class PathShadowing:
         side.wait_stream(cur)                      # the query comes from `cur`
         q.record_stream(side)
         with torch.cuda.stream(side):
-            dist, idx, slot[1] = _lib.scan_topk(rows, T, q, H, k, self._row_offset, mode | _lib.PSH_FLAG_NOSYNC,
-                                                slot[1], aux)
+            dist, idx, slot[1] = _lib.scan_topk(rows, T, q, H, k, self._row_offset,
+                                                mode | _lib.PSH_FLAG_NOSYNC | _lib.PSH_FLAG_SHARE_SMS, slot[1], aux)
         slot[2] = q.shape[0]
         dist.record_stream(cur)                    # the results are consumed on `cur` after the join
         idx.record_stream(cur)
@@ -495,7 +495,10 @@ class PathShadowing:
         B, L = shp[0], shp[-1] + self.context.get_out_times()
         words = B * k * (3 + L)
         if self._staging is None or self._staging[0].numel() != words:
-            self._staging = (torch.empty(words, dtype=torch.int32, device=self._dev()), [], [0])
+            # (two pinned buffers up front: a caller that keeps the previous result while asking for the next
+            # one would otherwise pay a 2 ms cudaHostAlloc inside its second call)
+            self._staging = (torch.empty(words, dtype=torch.int32, device=self._dev()),
+                             [torch.empty(words, dtype=torch.int32, pin_memory=True) for _ in range(2)], [0])
         dev_buf, pool, outstanding = self._staging
         if pool:
             host_buf = pool.pop()
@@ -538,7 +541,8 @@ class PathShadowing:
         nd, ni, npth = B * k, B * k * 2, B * k * L
         words = nd + ni + npth + 1
         if self._staging is None or self._staging[0].numel() != words:
-            self._staging = (torch.empty(words, dtype=torch.int32, device=self._dev()), [], [0])
+            self._staging = (torch.empty(words, dtype=torch.int32, device=self._dev()),
+                             [torch.empty(words, dtype=torch.int32, pin_memory=True) for _ in range(2)], [0])
         dev_buf, pool, outstanding = self._staging
         host_buf = pool.pop() if pool else torch.empty(words, dtype=torch.int32, pin_memory=True)
         streams, self._pipe_streams = self._pipe_streams, 1               # this call's own stream, no lanes

@@ -2,7 +2,8 @@ import sys, time, torch, numpy as np
 sys.path.insert(0, "/root/repo")
 import bench, shadowing_b200 as sb
 from shadowing_b200 import _lib
-ds = bench.make_shard(0); qs = bench.make_queries(60); qp = qs.clone().pin_memory()
+g = torch.Generator().manual_seed(1234); ds = torch.randn(bench.R_FULL, 1, bench.T, generator=g) * 0.01
+qs = bench.make_queries(60); qp = qs.clone().pin_memory()
 obj = sb.PathShadowing(sb.Identity(bench.W), sb.RelativeMSE(), ds, sb.PredictionContext(bench.H), device="cuda:0")
 for i in range(5): obj.shadow(qp[i:i+1], k=1024)
 torch.cuda.synchronize()
