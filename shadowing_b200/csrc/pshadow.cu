@@ -1632,6 +1632,16 @@ static FftScanFn fft_variant_fn(int sq, int em) {
     return fft_scan_kernel<false, false>;
 }
 
+// [embedded][one query][energy groups per piece: 7 / run-time]
+static FftScanFn fft3_variant_fn(int em, int single, int ncy) {
+    if (ncy == 7) {
+        if (single) return em ? fft_scan_warp_kernel<true, true, 7> : fft_scan_warp_kernel<false, true, 7>;
+        return em ? fft_scan_warp_kernel<true, false, 7> : fft_scan_warp_kernel<false, false, 7>;
+    }
+    if (single) return em ? fft_scan_warp_kernel<true, true, 0> : fft_scan_warp_kernel<false, true, 0>;
+    return em ? fft_scan_warp_kernel<true, false, 0> : fft_scan_warp_kernel<false, false, 0>;
+}
+
 #define big_smem(kernel, bytes) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
 
 static int device_setup(DevSetup **out) {
@@ -1670,10 +1680,8 @@ static int device_setup(DevSetup **out) {
         PSH_CUDA(cudaFuncGetAttributes(&fa, fft_prep_energy_kernel<true, 1024>));
         PSH_CUDA(cudaFuncGetAttributes(&fa, fft3_prep_spectra_kernel));
     }
-    PSH_CUDA(big_smem((fft_scan_warp_kernel<false, true>), SMEM_FFT3_SINGLE));
-    PSH_CUDA(big_smem((fft_scan_warp_kernel<true, true>), SMEM_FFT3_SINGLE));
-    PSH_CUDA(big_smem((fft_scan_warp_kernel<false, false>), SMEM_FFT3_GROUP));
-    PSH_CUDA(big_smem((fft_scan_warp_kernel<true, false>), SMEM_FFT3_GROUP));
+    for (int i = 0; i < 8; ++i)
+        PSH_CUDA(big_smem(fft3_variant_fn(i & 1, (i >> 1) & 1, (i >> 2) & 1 ? 7 : 0), ((i >> 1) & 1) ? SMEM_FFT3_SINGLE : SMEM_FFT3_GROUP));
     for (int i = 0; i < FFT_VARIANTS; ++i) {
         FftScanFn fn = fft_variant_fn((i >> 1) & 1, i & 1);
         PSH_CUDA(big_smem(fn, SMEM_FFT));
@@ -1861,13 +1869,7 @@ static int run_scan_group(const float *d_dataset, long long R, long long T, long
         if (warp_fft) {
             const unsigned int grid = (units + fft3_warps - 1) / fft3_warps;
             const size_t smem = nq == 1 ? SMEM_FFT3_SINGLE : SMEM_FFT3_GROUP;
-            if (nq == 1) {
-                if (emb) fft_scan_warp_kernel<true, true><<<grid, fft3_warps * 32, smem, stream>>>(fp);
-                else fft_scan_warp_kernel<false, true><<<grid, fft3_warps * 32, smem, stream>>>(fp);
-            } else {
-                if (emb) fft_scan_warp_kernel<true, false><<<grid, fft3_warps * 32, smem, stream>>>(fp);
-                else fft_scan_warp_kernel<false, false><<<grid, fft3_warps * 32, smem, stream>>>(fp);
-            }
+            fft3_variant_fn(emb != nullptr, nq == 1, fp.ncy)<<<grid, fft3_warps * 32, smem, stream>>>(fp);
         } else {
             fv.fn<<<units, fx2::THREADS, SMEM_FFT, stream>>>(fp);
         }

@@ -302,7 +302,7 @@ __device__ __forceinline__ float2 b2f(unsigned int w) { return make_float2(__uin
 // entries may be omitted (k entries at or below a bin still certify its edge), never invented.
 __device__ __forceinline__ void fft3_append_candidates(const FftScanParams &p, int b, const float2 (&v)[32], const uint4 *Ys4,
                                                        bool any, float m2, float cu, float rhs, float inv_es, float base0,
-                                                       float slack, int pair, int lane, bool count_ub) {
+                                                       float slack, int pair, int lane, bool count_ub, int ncy) {
     const float INF = __int_as_float(0x7f800000);
     const float2 m22 = make_float2(m2, m2);
     unsigned int ma = 0, mb = 0;
@@ -310,7 +310,7 @@ __device__ __forceinline__ void fft3_append_candidates(const FftScanParams &p, i
     if (any) {
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-            if (g < p.ncy) {
+            if (g < ncy) {
                 const uint4 y4 = Ys4[g * 32 + lane];
                 const unsigned int yw[4] = {y4.x, y4.y, y4.z, y4.w};
 #pragma unroll
@@ -414,13 +414,18 @@ __device__ __forceinline__ void fft3_seed_rendezvous(const FftScanParams &p, con
 // One query: the pair's spectrum is staged INSIDE the transpose tile (it is in registers before the tile
 // is written) and the next one is fetched when the tile has been read back.  A group of queries keeps the
 // spectrum in a buffer of its own for all its transforms.
-template <bool EMB, bool SINGLE>
+// NCY > 0: the number of 128-window groups of a piece's energy row is a compile-time constant (7 for
+// 129 <= W <= 253 on trajectories longer than one piece: the epilogue's eight guarded groups cost ~40
+// instructions of control per transform otherwise); NCY = 0: taken from p.ncy.
+template <bool EMB, bool SINGLE, int NCY>
 __global__ void __launch_bounds__(fx3::WARPS_SINGLE * 32, 1) fft_scan_warp_kernel(const FftScanParams p) {
     extern __shared__ __align__(128) unsigned char fsm[];
     __shared__ float s_thr[QG_MAX], s_q2[QG_MAX], s_qmax[QG_MAX], s_gn[QG_MAX];
     __shared__ unsigned int s_seed[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     constexpr bool single = SINGLE;   // one query: its spectrum in shared memory, the pair's spectrum staged inside the tile
+    const int ncy = NCY > 0 ? NCY : p.ncy;
+    const int nq = SINGLE ? 1 : p.nq;
     const float INF = __int_as_float(0x7f800000);
     float4 *tw2s = reinterpret_cast<float4 *>(fsm);
     const float4 *Qs4 = reinterpret_cast<const float4 *>(fsm + fx3::TW_BYTES);
@@ -438,7 +443,7 @@ __global__ void __launch_bounds__(fx3::WARPS_SINGLE * 32, 1) fft_scan_warp_kerne
     if (single)
         for (int i = tid; i < fx3::Q_BYTES / 16; i += blockDim.x)
             reinterpret_cast<float4 *>(fsm + fx3::TW_BYTES)[i] = __ldg(reinterpret_cast<const float4 *>(p.Qc) + i);
-    if (tid < p.nq) {
+    if (tid < nq) {
         const float t0 = ld_volatile_f32(&p.st[tid].thr_fast);
         s_thr[tid] = EMB ? t0 * p.thr_widen : t0;
         s_q2[tid] = p.st[tid].q2;
@@ -452,7 +457,7 @@ __global__ void __launch_bounds__(fx3::WARPS_SINGLE * 32, 1) fft_scan_warp_kerne
     }
     if (tid < 2) s_seed[tid] = 0u;
     __syncthreads();
-    for (int b = 0; b < p.nq; ++b) {   // max_k |FFT(q)_k| from the partial maxima (positive floats order as uints)
+    for (int b = 0; b < nq; ++b) {   // max_k |FFT(q)_k| from the partial maxima (positive floats order as uints)
         float m = 0.0f;
         for (int i = tid; i < p.nqmax; i += blockDim.x) m = fmaxf(m, __ldg(p.qmaxp + (size_t)b * QMAXP + i));
 #pragma unroll
@@ -468,7 +473,7 @@ __global__ void __launch_bounds__(fx3::WARPS_SINGLE * 32, 1) fft_scan_warp_kerne
 #define PSH_STAMP3(i) do { if (p.dbg != nullptr && lane == 0) p.dbg[(size_t)gw * 8 + (i)] = globaltimer_ns(); } while (0)
     PSH_STAMP3(0);
 
-    const uint32_t ybytes = (uint32_t)p.ncy * 512u;
+    const uint32_t ybytes = (uint32_t)ncy * 512u;
     auto issue_z = [&](int pr) {  // lane 0
         mbar_expect_tx(barZ, (uint32_t)fx3::Z_BYTES);
         bulk_g2s(smem_u32(zbuf), p.Z + (size_t)pr * fx3::N, (uint32_t)fx3::Z_BYTES, barZ);
@@ -485,7 +490,7 @@ __global__ void __launch_bounds__(fx3::WARPS_SINGLE * 32, 1) fft_scan_warp_kerne
     uint32_t phZ = 0, phY = 0;
     bool seeding = p.seed != 0;
     bool staged = false;          // this pair's spectrum and energies are already in shared memory (a group's pass after seeding)
-    const bool rerun = p.nq > 1;  // seeding a group of queries: the pair is transformed twice
+    const bool rerun = nq > 1;  // seeding a group of queries: the pair is transformed twice
     const float cu = p.ub_y_coef;
     for (int iter = 0;;) {
         // lane 0 draws the slot behind this pair now; the atomic's round trip hides behind the first pass
@@ -495,10 +500,10 @@ __global__ void __launch_bounds__(fx3::WARPS_SINGLE * 32, 1) fft_scan_warp_kerne
         // thresholds other warps have published: fetched now, merged at the end of the iteration
         const bool pick = ((iter + gw) & 3) == 0;
         unsigned int pub = 0x7f800000u;
-        if (pick && lane < p.nq) pub = __ldcg(p.hist + (size_t)lane * HSTRIDE + H_THR);
+        if (pick && lane < nq) pub = __ldcg(p.hist + (size_t)lane * HSTRIDE + H_THR);
         if (!staged) { mbar_wait(barZ, phZ); phZ ^= 1; }
         int npair = -1;
-        for (int b = 0; b < p.nq; ++b) {
+        for (int b = 0; b < nq; ++b) {
             float2 v[32];
             {
                 const float4 *Q4 = single ? Qs4 : reinterpret_cast<const float4 *>(p.Qc + (size_t)b * fftx::N);
@@ -514,7 +519,7 @@ __global__ void __launch_bounds__(fx3::WARPS_SINGLE * 32, 1) fft_scan_warp_kerne
                     v[4 * g + 3] = fx2::cmul(h2f(z4.w), make_float2(qb.z, qb.w));
                 }
             }
-            const bool last_q = b == p.nq - 1;
+            const bool last_q = b == nq - 1;
             // the pair behind this one: lane 0 turns the slot it drew at the top into a pair when the first pass
             // has hidden the atomic's round trip, and issues the copy of its spectrum
             auto next_pair = [&]() {
@@ -555,7 +560,7 @@ __global__ void __launch_bounds__(fx3::WARPS_SINGLE * 32, 1) fft_scan_warp_kerne
                 float mn = INF;
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
-                    if (g < p.ncy) {
+                    if (g < ncy) {
                         const uint4 y4 = Ys4[g * 32 + lane];
                         const unsigned int yw[4] = {y4.x, y4.y, y4.z, y4.w};
 #pragma unroll
@@ -588,7 +593,7 @@ __global__ void __launch_bounds__(fx3::WARPS_SINGLE * 32, 1) fft_scan_warp_kerne
             float mn = INF;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-                if (g < p.ncy) {
+                if (g < ncy) {
                     const uint4 y4 = Ys4[g * 32 + lane];
                     const unsigned int yw[4] = {y4.x, y4.y, y4.z, y4.w};
 #pragma unroll
@@ -600,7 +605,7 @@ __global__ void __launch_bounds__(fx3::WARPS_SINGLE * 32, 1) fft_scan_warp_kerne
             }
             const bool any = mn <= rhs;   // (+inf <= +inf while thr = +inf: sorted out per window in the append)
             if (__any_sync(FULL, any))    // rare
-                fft3_append_candidates(p, b, v, Ys4, any, m2, cu, rhs, inv_es, base0, slack, pair, lane, !(p.seed != 0 && iter == 0));
+                fft3_append_candidates(p, b, v, Ys4, any, m2, cu, rhs, inv_es, base0, slack, pair, lane, !(p.seed != 0 && iter == 0), ncy);
         }
         if (seeding && rerun) {
             // a group of queries: arrive, wait for the thresholds, then the same pair again
@@ -613,14 +618,14 @@ __global__ void __launch_bounds__(fx3::WARPS_SINGLE * 32, 1) fft_scan_warp_kerne
         staged = false;
         __syncwarp();   // every lane is done with the staged energies
         if (lane == 0 && npair >= 0) issue_y(npair);
-        if (pick && lane < p.nq && pub < __float_as_uint(s_thr[lane])) atomicMin(reinterpret_cast<unsigned int *>(&s_thr[lane]), pub);
+        if (pick && lane < nq && pub < __float_as_uint(s_thr[lane])) atomicMin(reinterpret_cast<unsigned int *>(&s_thr[lane]), pub);
         if (iter == 0) PSH_STAMP3(3);
         if (iter == 1) PSH_STAMP3(4);
         if (iter == 8) PSH_STAMP3(5);
         if (iter == 24) PSH_STAMP3(6);
         if (npair < 0) { PSH_STAMP3(7); break; }
         if (((iter + gw) & p.refresh_mask) == 0)
-            for (int b = 0; b < p.nq; ++b) fft_refresh_threshold(p, b, s_q2[b], s_thr);
+            for (int b = 0; b < nq; ++b) fft_refresh_threshold(p, b, s_q2[b], s_thr);
         pair = npair;
         ++iter;
     }
