@@ -57,6 +57,13 @@ __constant__ float2 c_w32[32] = {
     {9.238795325e-01f, -3.826834324e-01f},
     {9.807852804e-01f, -1.950903220e-01f}};
 
+#ifndef PSH_TWPF
+#define PSH_TWPF 3    // twiddle loads in flight
+#endif
+#ifndef PSH_TWPF0
+#define PSH_TWPF0 0   // of which issued before the first pass (measured: 0 / 3 best, 0.1687 -> 0.1663 ms)
+#endif
+
 namespace fx3 {
 
 constexpr int N = 1024;
@@ -139,6 +146,15 @@ __device__ __forceinline__ void ifft32(float2 (&v)[32]) {
     }
 }
 
+// 16-byte load whose position in the instruction stream is kept (volatile asm)
+template <bool SHARED>
+__device__ __forceinline__ float4 ld128_pinned(const float4 *p) {
+    float4 r;
+    if (SHARED) asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(smem_u32(p)));
+    else asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
 // Inverse 1024-point transform by ONE warp.  In: v[i] = x[lane + 32 i].  Out: v[c] = X[lane + 32 c].
 //   X[32 k1 + k2] = sum_{n1} w32^{n1 k1} w1024^{n1 k2} sum_{n2} x[n1 + 32 n2] w32^{n2 k2}
 // pass A on lane n1 (over n2), twiddle w1024^{lane k2} from the table tw2 (float4 {w^(lane 2j), w^(lane (2j+1))}
@@ -147,22 +163,25 @@ __device__ __forceinline__ void ifft32(float2 (&v)[32]) {
 // `tile_free()` runs when the warp has read the tile back (it may be overwritten from then on);
 // `inputs_read()` runs in front of the first write into the tile, behind a __syncwarp (every lane has
 // fetched what it needed from a buffer aliased with the tile).
-template <typename F0, typename F1>
+template <bool TW_SHARED, typename F0, typename F1>
 __device__ __forceinline__ void ifft1024(float2 (&v)[32], float2 *ex, const float4 *tw2, int lane, F0 inputs_read, F1 tile_free) {
-#ifdef PSH_FFT3_LOOP
-    // ONE copy of the radix-32 pass in the instruction stream (the 16 warps of an SM run out of phase: the
-    // loop body is what the instruction caches have to hold)
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-        ifft32(v);
-        if (pass == 1) break;
-#else
     {
+        // the twiddles are fetched PSH_TWPF ahead of their use: ptxas issues a shared-memory load right in front
+        // of its consumer otherwise, and the warp sits out its latency 16 times
+        // (measured and rejected: ONE copy of the radix-32 pass in an `unroll 1` loop over the two passes --
+        // smaller code, 0.225 against 0.218 ms; 12 warps of 168 registers: 0.230 ms)
+        float4 tq[16];
+#pragma unroll
+        for (int j = 0; j < PSH_TWPF0; ++j) tq[j] = ld128_pinned<TW_SHARED>(tw2 + j * 32 + lane);
         ifft32(v);
-#endif
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            const float4 t = tw2[j * 32 + lane];
+            if (j + PSH_TWPF < 16 && j + PSH_TWPF >= PSH_TWPF0) tq[j + PSH_TWPF] = ld128_pinned<TW_SHARED>(tw2 + (j + PSH_TWPF) * 32 + lane);
+            if (j == 0) {
+#pragma unroll
+                for (int jj = PSH_TWPF0; jj < PSH_TWPF; ++jj) tq[jj] = ld128_pinned<TW_SHARED>(tw2 + jj * 32 + lane);
+            }
+            const float4 t = tq[j];
             if (j > 0) v[2 * j] = cmul(v[2 * j], make_float2(t.x, t.y));
             v[2 * j + 1] = cmul(v[2 * j + 1], make_float2(t.z, t.w));
         }
@@ -180,9 +199,7 @@ __device__ __forceinline__ void ifft1024(float2 (&v)[32], float2 *ex, const floa
         __syncwarp();
         tile_free();
     }
-#ifndef PSH_FFT3_LOOP
     ifft32(v);
-#endif
 }
 
 }  // namespace fx3
@@ -215,7 +232,7 @@ __global__ void __launch_bounds__(128) fft3_debug_kernel(const float2 *__restric
         v[i] = x[lane + 32 * i];
         if (dir < 0) v[i].y = -v[i].y;
     }
-    fx3::ifft1024(v, ex[warp], tw2, lane, []() {}, []() {});
+    fx3::ifft1024<false>(v, ex[warp], tw2, lane, []() {}, []() {});
 #pragma unroll
     for (int c = 0; c < 32; ++c) y[lane + 32 * c] = dir < 0 ? make_float2(v[c].x, -v[c].y) : v[c];
 }
@@ -243,7 +260,7 @@ __global__ void __launch_bounds__(128) fft3_prep_spectra_kernel(const float *__r
         v[i] = make_float2(xa, -xb);                       // conj(x): forward = conj(inverse(conj(x)))
         e += (double)xa * (double)xa + (double)xb * (double)xb;
     }
-    fx3::ifft1024(v, ex[warp], a.tw2, lane, []() {}, []() {});
+    fx3::ifft1024<false>(v, ex[warp], a.tw2, lane, []() {}, []() {});
     float mx = 0.0f;
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
@@ -531,7 +548,7 @@ __global__ void __launch_bounds__(fx3::WARPS_SINGLE * 32, 1) fft_scan_warp_kerne
                 return np;
             };
             int np0 = -1;
-            fx3::ifft1024(v, ex, tw2s, lane,
+            fx3::ifft1024<true>(v, ex, tw2s, lane,
                 [&]() {   // every lane holds its part of the staged spectrum
                     if (!single && last_q) {
                         np0 = next_pair();

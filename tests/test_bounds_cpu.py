@@ -33,10 +33,15 @@ def _floor_f16(x):
     return h
 
 
-def _pair_correlation_f32(ya, yb, g, quantise=True):
+def _floor_bf16(x):
+    """fp32 >= 0 -> bf16 rounded toward -inf = the upper 16 bits (fft_prep_energy_kernel<., 1024>), +inf kept"""
+    return (x.astype(np.float32).view(np.uint32) & np.uint32(0xFFFF0000)).view(np.float32)
+
+
+def _pair_correlation_f32(ya, yb, g, quantise=True, N=4096):
     """v[t] (the kernel's transform output, in the pair's scaled units when `quantise`), and the per-pair
-    statistics psh_fft_prepare stores: zs, zqerr.  D^[t] = v[t] / zs."""
-    N = 4096
+    statistics psh_fft_prepare stores: zs, zqerr.  D^[t] = v[t] / zs.  N: the transform length of the
+    flavour (4096: one CTA per transform; 1024: one warp per transform, pieces of 1024 samples)."""
     z = np.zeros(N, np.complex64)
     z[:ya.size] = ya.astype(np.float32) + 1j * yb.astype(np.float32)
     Z = np.fft.fft(z).astype(np.complex64)
@@ -70,8 +75,9 @@ def _rows(rng, kind, T):
     raise ValueError(kind)
 
 
-def _staged_energies(y, W, Tp, embed=None):
-    """(yf (2, Tp) fp32 = what the kernel reads: energies * es floored to fp16), es"""
+def _staged_energies(y, W, Tp, embed=None, bf16=False):
+    """(yf (2, Tp) fp32 = what the kernel reads: energies * es floored to fp16 -- bf16 in the 1024-point
+    flavour), es"""
     e = []
     for row in range(2):
         y64 = y[row].astype(np.float64)
@@ -83,30 +89,34 @@ def _staged_energies(y, W, Tp, embed=None):
             e.append(np.nextafter(((E ** 2).sum(1) * (1 - 16 * U)).astype(np.float32), np.float32(-np.inf)).clip(min=0))
     e = np.stack(e)
     es = _pow2_scale(e.max(), 15)
+    if bf16:
+        return _floor_bf16(np.minimum(e * es, np.float32(65504.0))), es
     return _floor_f16(np.minimum(e * es, np.float32(65504.0))).astype(np.float32), es
 
 
+@pytest.mark.parametrize("N", [4096, 1024])
 @pytest.mark.parametrize("kind", ["gauss", "heavy", "near_copy", "mixed_scale"])
-def test_identity_fft_bounds_hold(kind):
+def test_identity_fft_bounds_hold(kind, N):
     """LB = Q2 + Y2^ - 2 D^ - slack <= S <= UB = LB + 2 slack + 2^-10 Y2^ (+ 2^-24 / es), with
     slack = 2 cf_u Qmax ynorm + 2 zqerr ||q|| + 12u (Q2 + ynorm^2), evaluated as the kernel does:
-    fma(m2, v, yf) in the pair's scaled units."""
+    fma(m2, v, yf) in the pair's scaled units.  N = 1024: the warp-level flavour's piece of 1024 samples,
+    energies floored to bf16 (UB - LB grows to 2^-7 Y2^)."""
     rng = np.random.default_rng(7)
-    T, W = 4096, 252
+    T, W = N, 252
     q = (rng.standard_normal(W) * 0.01).astype(np.float32)
     y = _rows(rng, kind, T)
     if y is None:
         y = np.tile(q.astype(np.float64), (2, T // W + 1))[:, :T] * (1 + 1e-4 * rng.standard_normal((2, T)))
     y = y.astype(np.float32)
     Tp = T - W + 1
-    va, vb, qmax, zs, zqerr = _pair_correlation_f32(y[0], y[1], q)
+    va, vb, qmax, zs, zqerr = _pair_correlation_f32(y[0], y[1], q, N=N)
     yn = np.float32(np.sqrt((y.astype(np.float64) ** 2).sum()) * (1 + 1e-7))
     gn = np.float32(np.linalg.norm(q.astype(np.float64)) * (1 + 1e-7))
     q2 = np.float32((q.astype(np.float64) ** 2).sum())
     slack = np.float32((2 * CF_U * qmax * yn + 2 * zqerr * gn + np.float32(12 * U) * (q2 + yn * yn)) * np.float32(1.0001))
-    yf, es = _staged_energies(y, W, Tp)
+    yf, es = _staged_energies(y, W, Tp, bf16=(N == 1024))
     m2 = np.float32(-2.0) * es / zs
-    cu = np.float32(2.0 ** -10 * 1.01)
+    cu = np.float32((2.0 ** -7 if N == 1024 else 2.0 ** -10) * 1.01)
     loosest = 0.0
     for row, v in ((0, va), (1, vb)):
         y64 = y[row].astype(np.float64)
