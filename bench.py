@@ -533,7 +533,7 @@ def main():
                     help="weak (default, the driver's metric): 32768 rows per GPU; strong: 32768 rows in total")
     ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("PSH_STREAMS", "2")),
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("PSH_STREAMS", "3")),
                     help="streams the pipelined device loop alternates between (1: the caller's stream)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

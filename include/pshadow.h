@@ -48,9 +48,11 @@ enum {
  * psh_scan_overflowed() (which synchronises) before trusting the results. */
 #define PSH_FLAG_NOSYNC 0x100
 /* OR-ed into `mode`: this scan is one of a pipeline alternating between streams -- its persistent scan kernel
- * leaves six SMs (PSH_SPARE_SMS) to the other streams' small kernels (re-rank, select, exchange), which would
- * otherwise wait until the scan has drained.  Results are unaffected. */
+ * leaves a few SMs to the other streams' small kernels (re-rank, select, exchange), which would otherwise
+ * wait until the scan has drained.  PSH_SHARE_SMS(n) leaves n SMs (n = 1..63); the bare flag leaves six
+ * (PSH_SPARE_SMS overrides both).  Results are unaffected. */
 #define PSH_FLAG_SHARE_SMS 0x200
+#define PSH_SHARE_SMS(n) (PSH_FLAG_SHARE_SMS | (((n) & 0x3f) << 12))
 
 int psh_version(void);
 const char *psh_error_string(int code);
@@ -199,8 +201,8 @@ int psh_allgather_merge_packed(const int32_t *d_rec_local, void *const *bufs, in
  * (wait for the G flags of the epoch, merge) -- so a pipeline of scans can enqueue
  *     scan(i+1), send(i+1), merge(i)
  * and a rank computes its next scan instead of idling until the slowest peer has delivered step i.
- * The exchange buffers hold four epochs (epoch % 4): two for one stream of fused launches, two more
- * for this order or for a second stream alternating steps with the first. */
+ * The exchange buffers hold eight epochs (epoch % 8): two per stream of a pipeline that alternates steps
+ * between up to four streams (this order needs two as well). */
 int psh_xchg_send(const int32_t *d_rec_local, void *const *bufs, int G, int rank, int B, int64_t k,
                   uint32_t epoch, void *stream);
 int psh_xchg_merge(void *const *bufs, int G, int rank, int B, int64_t k, int64_t Tp, uint32_t epoch,

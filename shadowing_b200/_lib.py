@@ -16,6 +16,12 @@ PSH_MODE_FILTER = 1
 PSH_MODE_FFT = 2
 PSH_FLAG_NOSYNC = 0x100
 PSH_FLAG_SHARE_SMS = 0x200
+
+
+def share_sms(n: int) -> int:
+    """PSH_SHARE_SMS(n): the pipelined scan leaves n SMs to the other streams' small kernels."""
+    return PSH_FLAG_SHARE_SMS | ((n & 0x3F) << 12)
+
 PSH_E_OVERFLOW = -6
 FFT_MAX_W = 2048   # psh_fft_prepare: context length at most half a 4096-point transform
 AGG_MAX_T = 16     # psh_rv_aggregate: maturities per launch (more: the host aggregation)

@@ -1064,20 +1064,21 @@ __global__ void __launch_bounds__(SEL_THREADS) merge_kernel(const float *d_parts
 // ------------------------------------------------------------------------------------------
 // all-gather over NVLink peer memory fused with the merge (multi-GPU, one process per GPU).
 // Every rank owns an exchange buffer that all other ranks have mapped (CUDA IPC):
-//     [epoch % 4][ records (G, B, k, 3) int32 | flags (G, B) uint32 ]
+//     [epoch % 8][ records (G, B, k, 3) int32 | flags (G, B) uint32 ]
 // CTA b of rank r stores query b's k packed records into slot r of EVERY rank's buffer (plain
 // stores over NVLink), fences (system scope), then raises flag (r, b) on every rank with the
 // step's epoch; it then waits until the G flags of query b in its OWN buffer carry the epoch
 // and merges the G*k records exactly like merge_kernel.  One launch replaces ncclAllGather +
-// merge_kernel.  Four buffers rotate with the epoch (see XCHG_PARITIES).
+// merge_kernel.  Eight buffers rotate with the epoch (see XCHG_PARITIES).
 // A peer that never arrives (crashed rank) raises bit 1 of `flag` after `timeout_ns` instead of
 // hanging the GPU.
 // ------------------------------------------------------------------------------------------
 constexpr int XCHG_MAX_PEERS = 16;
 // Buffers rotate over 4 epochs.  One stream of fused send+merge launches needs 2 (a rank's step e+2 follows
 // its step e+1, which needed every peer's send e+1, which follows that peer's merge e).  Two streams that
-// alternate steps need 2 per stream, and so does the split form (send e+1 enqueued before merge e).
-constexpr int XCHG_PARITIES = 4;
+// alternate steps need 2 per stream, and so does the split form (send e+1 enqueued before merge e): 8 buffers
+// cover pipelines of up to four streams.
+constexpr int XCHG_PARITIES = 8;
 struct XchgParams {
     int *rec[XCHG_MAX_PEERS];            // this parity's record area on every rank
     unsigned int *flags[XCHG_MAX_PEERS]; // this parity's flag area on every rank
@@ -2006,8 +2007,9 @@ static int scan_entry(const float *d_dataset, int64_t R, int64_t T, int64_t row_
     cudaStream_t stream = (cudaStream_t)stream_;
     const int qstride = emb ? emb->d : W;   // floats per query in d_queries
     const bool nosync = (mode & PSH_FLAG_NOSYNC) != 0;
-    const int spare_sms = (mode & PSH_FLAG_SHARE_SMS) ? env_int("PSH_SPARE_SMS", 6) : 0;
-    mode &= ~(PSH_FLAG_NOSYNC | PSH_FLAG_SHARE_SMS);
+    const int spare_arg = (mode >> 12) & 0x3f;
+    const int spare_sms = (mode & PSH_FLAG_SHARE_SMS) ? env_int("PSH_SPARE_SMS", spare_arg > 0 ? spare_arg : 6) : 0;
+    mode &= ~(PSH_FLAG_NOSYNC | PSH_FLAG_SHARE_SMS | (0x3f << 12));
     if (mode != PSH_MODE_EXACT && mode != PSH_MODE_FILTER && mode != PSH_MODE_FFT) return PSH_E_ARG;
     if (!d_dataset || !d_queries || !d_out_dist || !d_ws) return PSH_E_ARG;  // d_out_idx NULL: packed records
     if (row_stride < T) return PSH_E_ARG;
@@ -2099,7 +2101,7 @@ int psh_scan_topk_embed_f32(const float *d_dataset, int64_t R, int64_t T, int64_
                             int32_t row_offset, int flags, const void *d_runs, int nruns,
                             const float *d_g, const void *d_aux, size_t aux_bytes,
                             float *d_out_dist, int32_t *d_out_idx, void *d_ws, size_t ws_bytes, void *stream_) {
-    if (!d_runs || nruns <= 0 || d <= 0 || (flags & ~(PSH_FLAG_NOSYNC | PSH_FLAG_SHARE_SMS)) != 0) return PSH_E_ARG;
+    if (!d_runs || nruns <= 0 || d <= 0 || (flags & ~(PSH_FLAG_NOSYNC | PSH_FLAG_SHARE_SMS | (0x3f << 12))) != 0) return PSH_E_ARG;
     if (d_aux != nullptr && d_g == nullptr) return PSH_E_ARG;
     EmbParams ep;
     ep.runs = static_cast<const EmbRun *>(d_runs);

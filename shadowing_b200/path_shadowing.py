@@ -300,6 +300,8 @@ class PathShadowing:
         alternates lanes identically, so the exchange epochs stay aligned."""
         from .distributed import Lane, sharded_scan
         dev = rows.device
+        if self._pipe_streams > 4:
+            raise ValueError("sharded pipelines alternate between at most 4 streams (the exchange buffers hold 8 epochs)")
         if self._lanes is None or len(self._lanes) != self._pipe_streams:
             self._lanes = [Lane(self, torch.cuda.Stream(device=dev)) for _ in range(self._pipe_streams)]
             self._lane_i = 0
