@@ -10,8 +10,8 @@
 A "step" is one shadow scan of one query over the resident ensemble.  Prints ONE JSON line.
   value   : windows/s with the queries already in HBM: the K scans of the timed region are enqueued
             back to back through the C ABI (psh_scan_topk_f32 | PSH_FLAG_NOSYNC), alternating between
-            two streams with their own workspaces (query i+1's preparation and scan overlap query i's
-            re-rank, select and exchange) at EVERY N, and verified by ONE overflow check per workspace at
+            three streams with their own workspaces (query i+1's preparation and scan overlap query i's
+            re-rank, select and exchange; the scans leave a few SMs to those small kernels) at EVERY N, and verified by ONE overflow check per workspace at
             the end -- no host round trip between queries (CUDA events on the caller's stream, which joins
             both streams before the closing event)
   e2e     : windows/s through PathShadowing.shadow() with HOST numpy in/out, one call per step (pinned
