@@ -399,8 +399,10 @@ __device__ __forceinline__ void fft3_seed_rendezvous(const FftScanParams &p, con
         if (!last) {
             const bool poller = atomicAdd(const_cast<unsigned int *>(&s_seed[0]), 1u) == 0u;
             const unsigned long long t0 = globaltimer_ns();
-            while (s_seed[1] == 0u) {
-                if (poller && *done != 0u) { s_seed[1] = 1u; break; }
+            // (the relay flag is read and written with shared-memory atomics: a deliberate flag hand-off, and
+            // compute-sanitizer's racecheck stays clean)
+            while (atomicOr(const_cast<unsigned int *>(&s_seed[1]), 0u) == 0u) {
+                if (poller && *done != 0u) { atomicExch(const_cast<unsigned int *>(&s_seed[1]), 1u); break; }
                 if (globaltimer_ns() - t0 > 2000000ull) break;   // 2 ms: thresholds stay loose, the call re-runs safely
                 __nanosleep(poller ? 250 : 100);
             }
@@ -413,7 +415,7 @@ __device__ __forceinline__ void fft3_seed_rendezvous(const FftScanParams &p, con
         if (lane == 0) {
             __threadfence();
             *done = 1u;
-            s_seed[1] = 1u;
+            atomicExch(const_cast<unsigned int *>(&s_seed[1]), 1u);
         }
     } else if (lane < p.nq) {
         const unsigned int tb = *reinterpret_cast<volatile unsigned int *>(p.hist + (size_t)lane * HSTRIDE + H_THR);
