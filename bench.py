@@ -525,8 +525,8 @@ def run_cfg3(args, obj, qs_host, ds_host, rank, world, rows_n, tp, barrier, dev)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="auto", choices=["auto", "fft", "filter", "exact"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],

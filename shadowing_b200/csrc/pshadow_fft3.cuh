@@ -79,7 +79,7 @@ constexpr int Q_BYTES = N * 8;                 // one query's spectrum
 #define PSH_FFT3_WARPS 16
 #endif
 constexpr int WARPS_SINGLE = PSH_FFT3_WARPS;
-constexpr int WARPS_GROUP = 12;
+constexpr int WARPS_GROUP = 13;            // (13 x 16928 + 8192 bytes: what fits the 227 KB of a CTA)
 
 using fx2::add2;
 using fx2::sub2;

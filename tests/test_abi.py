@@ -258,3 +258,15 @@ def test_time_series_dataset_reads_npy_batches(tmp_path):
         assert np.array_equal(np.asarray(tsd), want)
     keep = sb.PathShadowing(sb.Identity(8), sb.RelativeMSE(), sb.TimeSeriesDataset(tmp_path), stream_dataset=True)
     assert isinstance(keep.dataset, sb.TimeSeriesDataset) and keep.dataset.shape == (9, 1, 64)
+
+
+def test_share_sms_flag_encoding():
+    """PSH_SHARE_SMS(n) of include/pshadow.h and its Python twin: flag bit 0x200 + n in bits 12..17."""
+    from shadowing_b200 import _lib
+    hdr = (ROOT / "include" / "pshadow.h").read_text()
+    assert "#define PSH_FLAG_SHARE_SMS 0x200" in hdr and "#define PSH_SHARE_SMS(n)" in hdr
+    assert _lib.PSH_FLAG_SHARE_SMS == 0x200 and _lib.PSH_FLAG_NOSYNC == 0x100
+    for n in (1, 6, 10, 63):
+        v = _lib.share_sms(n)
+        assert v & _lib.PSH_FLAG_SHARE_SMS and (v >> 12) & 0x3F == n
+        assert v & 0xFF == 0          # never collides with the scan mode

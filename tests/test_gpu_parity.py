@@ -720,16 +720,18 @@ def test_unsupported_plugins_raise():
         sb.PathShadowing(sb.Identity(8), Cosine(), ds, sb.PredictionContext(2)).shadow(q, k=3)
 
 
-def test_two_stream_pipeline_matches_single_stream():
-    """`_pipe_streams = 2`: consecutive enqueue-only scans alternate between two side streams with
-    their own workspaces; results are those of the one-stream pipeline, overflow is still caught."""
+@pytest.mark.parametrize("streams", [2, 3])
+def test_two_stream_pipeline_matches_single_stream(streams):
+    """`_pipe_streams = 2 | 3`: consecutive enqueue-only scans alternate between side streams with
+    their own workspaces (the scans carry PSH_SHARE_SMS: their persistent kernel leaves a few SMs to the
+    neighbours' small kernels); results are those of the one-stream pipeline, overflow is still caught."""
     R, T, W, H, k = 2048, 2048, 64, 4, 128
     ds, q = make_inputs(R, T, W, 6, seed=93)
     obj = _obj(ds, W, H, scan_mode="fft")
     rows, T_ = obj._resident_rows()
     qd = torch.tensor(q).cuda()
     do, io = oracle.shadow_topk(ds, q, k, H)
-    obj._pipe_streams = 2
+    obj._pipe_streams = streams
     outs = [obj._scan_device(qd[i:i + 1], rows, T_, k, nosync=True) for i in range(6)]
     obj._check_pipeline()
     for i, (d, idx) in enumerate(outs):
