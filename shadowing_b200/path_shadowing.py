@@ -330,12 +330,18 @@ class PathShadowing:
         side, cur = slot[0], torch.cuda.current_stream(dev)
         side.wait_stream(cur)                      # the query comes from `cur`
         q.record_stream(side)
-        with torch.cuda.stream(side):
-            dist, idx, slot[1] = _lib.scan_topk(rows, T, q, H, k, self._row_offset,
-                                                mode | _lib.PSH_FLAG_NOSYNC | _lib.PSH_FLAG_SHARE_SMS, slot[1], aux)
+        # the scan is enqueued on the side stream through its raw handle (no stream switch on the host:
+        # `with torch.cuda.stream(...)` costs more than the four launches); outputs and a first workspace are
+        # allocated on `cur` and handed to the side stream
+        ws_before = slot[1]
+        dist, idx, slot[1] = _lib.scan_topk(rows, T, q, H, k, self._row_offset,
+                                            mode | _lib.PSH_FLAG_NOSYNC | _lib.PSH_FLAG_SHARE_SMS, slot[1], aux,
+                                            stream=side.cuda_stream)
+        if slot[1] is not ws_before:               # a new (first or larger) workspace
+            slot[1].record_stream(side)
         slot[2] = q.shape[0]
-        dist.record_stream(cur)                    # the results are consumed on `cur` after the join
-        idx.record_stream(cur)
+        dist.record_stream(side)                   # written on `side`, consumed on `cur` after the join
+        idx.record_stream(side)
         return dist, idx
 
     def _run_table(self, device: torch.device):
