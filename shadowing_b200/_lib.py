@@ -151,8 +151,10 @@ def launch_count() -> int:
 
 
 def scan_topk_packed(ds: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int, row_offset: int, mode: int,
-                     workspace: torch.Tensor | None, aux: torch.Tensor | None, rec: torch.Tensor):
-    """Same scan, results as packed (B,k,3) int32 records [distance bits, r, t] written to `rec`."""
+                     workspace: torch.Tensor | None, aux: torch.Tensor | None, rec: torch.Tensor,
+                     stream: int | None = None):
+    """Same scan, results as packed (B,k,3) int32 records [distance bits, r, t] written to `rec`.
+    `stream`: raw CUDA stream to enqueue on (default: torch's current stream of ds.device)."""
     L = lib()
     R, row_stride = ds.shape[0], ds.stride(0)
     B, W = q.shape
@@ -163,7 +165,7 @@ def scan_topk_packed(ds: torch.Tensor, T: int, q: torch.Tensor, H: int, k: int, 
         rc = L.psh_scan_topk_f32(ds.data_ptr(), R, T, row_stride, q.data_ptr(), B, W, H, k, row_offset, mode,
                                  rec.data_ptr(), None, workspace.data_ptr(), workspace.numel(),
                                  aux.data_ptr() if aux is not None else None, aux.numel() if aux is not None else 0,
-                                 _stream(ds))
+                                 _stream(ds) if stream is None else stream)
     _check(rc, "psh_scan_topk_f32")
     return workspace
 
@@ -395,20 +397,21 @@ def xchg_destroy(ptr: int, device: torch.device) -> None:
 
 
 def allgather_merge_packed(rec: torch.Tensor, bufs: list[int], rank: int, Tp: int, epoch: int,
-                           flag: torch.Tensor | None = None):
+                           flag: torch.Tensor | None = None, stream: int | None = None, arr=None):
     """rec (B,k,3) i32 [distance bits, r, t] of this rank -> merged (B,k) f32, (B,k,2) i32 over all
     ranks: ONE kernel stores the records into every rank's exchange buffer over NVLink, waits for
     the peers' records and merges.  `flag` bit 0: a shard overflowed; bit 1: a peer timed out."""
     L = lib()
     B, k, _ = rec.shape
     G = len(bufs)
-    arr = (ctypes.c_void_p * G)(*bufs)
+    if arr is None:                      # (callers on the hot path keep the pointer array: _PeerExchange.arr)
+        arr = (ctypes.c_void_p * G)(*bufs)
     dist = torch.empty((B, k), dtype=torch.float32, device=rec.device)
     idx = torch.empty((B, k, 2), dtype=torch.int32, device=rec.device)
-    with torch.cuda.device(rec.device):
+    with _on_device(rec.device):
         rc = L.psh_allgather_merge_packed(rec.data_ptr(), arr, G, rank, B, k, Tp, epoch, dist.data_ptr(),
                                           idx.data_ptr(), flag.data_ptr() if flag is not None else None,
-                                          _stream(rec))
+                                          _stream(rec) if stream is None else stream)
     _check(rc, "psh_allgather_merge_packed")
     return dist, idx
 

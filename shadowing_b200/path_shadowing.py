@@ -298,7 +298,7 @@ class PathShadowing:
         `_scan_on_side_stream` (query i+1's preparation and scan run while query i's re-rank, select and
         exchange finish), every lane with its own workspace, record buffers and flag.  Every rank
         alternates lanes identically, so the exchange epochs stay aligned."""
-        from .distributed import Lane, sharded_scan
+        from .distributed import Lane, sharded_scan, sharded_scan_fast
         dev = rows.device
         if self._pipe_streams > 4:
             raise ValueError("sharded pipelines alternate between at most 4 streams (the exchange buffers hold 8 epochs)")
@@ -310,6 +310,12 @@ class PathShadowing:
         cur = torch.cuda.current_stream(dev)
         lane.stream.wait_stream(cur)
         q.record_stream(lane.stream)
+        out = sharded_scan_fast(lane, rows, T, q, H, k)      # steady state: raw stream handles, no stream switch
+        if out is not None:
+            dist, idx = out
+            dist.record_stream(lane.stream)                  # allocated on `cur`, written on the lane's stream
+            idx.record_stream(lane.stream)
+            return dist, idx
         with torch.cuda.stream(lane.stream):
             dist, idx = sharded_scan(lane, rows, T, q, H, k, defer=True)
         dist.record_stream(cur)
