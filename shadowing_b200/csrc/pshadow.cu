@@ -20,6 +20,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "pshadow.h"
@@ -1511,6 +1512,21 @@ size_t psh_fft_aux_bytes(int64_t R, int64_t T, int W, int H) {
     return a.total;
 }
 
+// Transform length every prepared aux buffer was laid out with (keyed by its device address): a scan uses the
+// length of ITS buffer even if the PSH_FFT_N knob changed between psh_fft_prepare and the scan.
+static std::mutex g_aux_mu;
+static std::unordered_map<const void *, int> g_aux_nfft;
+static void aux_nfft_record(const void *d_aux, int nfft) {
+    std::lock_guard<std::mutex> lock(g_aux_mu);
+    if (g_aux_nfft.size() > 65536) g_aux_nfft.clear();   // (stale addresses of freed buffers: bounded)
+    g_aux_nfft[d_aux] = nfft;
+}
+static int aux_nfft_lookup(const void *d_aux) {
+    std::lock_guard<std::mutex> lock(g_aux_mu);
+    auto it = g_aux_nfft.find(d_aux);
+    return it == g_aux_nfft.end() ? 0 : it->second;
+}
+
 // spectra + pair statistics, then the energy table: window energies (Identity) or, with a run table, the
 // embedded energies E2 = sum_n e_n(t)^2
 static int fft_prepare_impl(const float *d_dataset, int64_t R, int64_t T, int64_t row_stride, int W, int H,
@@ -1519,6 +1535,7 @@ static int fft_prepare_impl(const float *d_dataset, int64_t R, int64_t T, int64_
     FftAux a;
     if (!fft_aux_layout(R, T, W, H, static_cast<unsigned char *>(d_aux), a)) return W > fftx::N / 2 ? PSH_E_UNSUPPORTED : PSH_E_ARG;
     if (aux_bytes < a.total || (reinterpret_cast<uintptr_t>(d_aux) & 255u)) return PSH_E_WORKSPACE;
+    aux_nfft_record(d_aux, a.nfft);
     const size_t smem = (size_t)nruns * sizeof(EmbRun);
     if (smem > 12 * 1024) return PSH_E_UNSUPPORTED;   // next to the 32 KiB fp64 prefix array
     // twiddle tables: exp(+2 pi i m / 4096) in fp64, rounded once for the fp32 copy
@@ -2032,7 +2049,8 @@ static int scan_entry(const float *d_dataset, int64_t R, int64_t T, int64_t row_
     FftAux aux;
     const FftAux *auxp = nullptr;
     if (mode == PSH_MODE_FFT && d_aux != nullptr) {
-        if (!fft_aux_layout(R, T, W, H, const_cast<unsigned char *>(static_cast<const unsigned char *>(d_aux)), aux) ||
+        if (!fft_aux_layout(R, T, W, H, const_cast<unsigned char *>(static_cast<const unsigned char *>(d_aux)), aux,
+                            aux_nfft_lookup(d_aux)) ||
             aux_bytes < aux.total || (reinterpret_cast<uintptr_t>(d_aux) & 255u))
             return PSH_E_WORKSPACE;
         auxp = &aux;

@@ -30,10 +30,10 @@ inline int fft_length_for(int W) {
     return W <= FFT3_MAX_W ? 1024 : 4096;
 }
 
-inline bool fft_aux_layout(long long R, long long T, int W, int H, unsigned char *base, FftAux &a) {
+inline bool fft_aux_layout(long long R, long long T, int W, int H, unsigned char *base, FftAux &a, int nfft = 0) {
     if (R <= 0 || T <= 0 || W <= 0 || W > fftx::N / 2 || H < 0 || T - W - H + 1 <= 0) return false;
     const long long Tp = T - W - H + 1;
-    a.nfft = fft_length_for(W);
+    a.nfft = (nfft == 1024 || nfft == 4096) ? nfft : fft_length_for(W);   // (a scan takes the length its aux was prepared with)
     if (T <= a.nfft) { a.nsegv = 1; a.hop = a.nfft; a.span = (int)Tp; }
     else {
         a.hop = (a.nfft - W + 1) & ~3;                    // windows per piece

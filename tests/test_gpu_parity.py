@@ -160,6 +160,21 @@ def test_fft_flavours_bit_exact(R, T, W, H, k, B, nfft, monkeypatch):
     assert np.array_equal(paths, po)
 
 
+@pytest.mark.parametrize("prepared_with", ["4096", "1024"])
+def test_scan_uses_the_length_its_aux_was_prepared_with(prepared_with, monkeypatch):
+    """The PSH_FFT_N knob may change between psh_fft_prepare and the scan: the library remembers the transform
+    length every aux buffer was laid out with."""
+    ds, q = make_inputs(64, 2048, 100, 2, seed=11)
+    rows = torch.tensor(ds[:, 0, :]).cuda()
+    qd = torch.tensor(q[:, 0, :]).cuda()
+    monkeypatch.setenv("PSH_FFT_N", prepared_with)
+    aux = _lib.fft_prepare(rows, 2048, 100, 5)
+    monkeypatch.setenv("PSH_FFT_N", "1024" if prepared_with == "4096" else "4096")
+    d, idx, _ = _lib.scan_topk(rows, 2048, qd, 5, 50, 0, _lib.PSH_MODE_FFT, None, aux)
+    do, io = oracle.shadow_topk(ds, q, 50, 5)
+    assert_topk_equal(d.cpu().numpy(), idx.cpu().numpy(), do, io)
+
+
 def _perm_stride(R):
     if R <= 2:
         return 1
