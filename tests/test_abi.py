@@ -270,3 +270,33 @@ def test_share_sms_flag_encoding():
         v = _lib.share_sms(n)
         assert v & _lib.PSH_FLAG_SHARE_SMS and (v >> 12) & 0x3F == n
         assert v & 0xFF == 0          # never collides with the scan mode
+
+
+def test_fft_aux_sizing_follows_the_transform_length(monkeypatch):
+    """psh_fft_aux_bytes (host arithmetic only): 1024-point pieces for W <= 384 -- ceil(T'/hop) pieces per row,
+    hop = (1025 - W) & ~3, 8 KiB per pair of pieces -- and 4096-point row pairs beyond; PSH_FFT_N forces one."""
+    L = ctypes.CDLL(str(ROOT / "shadowing_b200" / "libpshadow.so"))
+    L.psh_fft_aux_bytes.restype = ctypes.c_size_t
+    L.psh_fft_aux_bytes.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int]
+    tables = 4096 * 8 + 4096 * 16 + 512 * 16
+
+    def expect(R, T, W, H, nfft):
+        Tp = T - W - H + 1
+        if T <= nfft:
+            nseg = 1
+        else:
+            hop = (nfft - W + 1) & ~3
+            nseg = -(-Tp // hop)
+        npairs = (R * nseg + 1) // 2
+        return tables + (npairs * 16 + 255) // 256 * 256 + 2 * 4 * nfft * npairs
+
+    monkeypatch.delenv("PSH_FFT_N", raising=False)
+    for (R, T, W, H), nfft in (((32768, 4096, 252, 20), 1024), ((7, 12001, 100, 0), 1024), ((37, 1024, 64, 0), 1024),
+                              ((600, 3000, 500, 10), 4096), ((24, 8192, 1024, 20), 4096)):
+        assert L.psh_fft_aux_bytes(R, T, W, H) == expect(R, T, W, H, nfft), (R, T, W, H)
+    monkeypatch.setenv("PSH_FFT_N", "4096")
+    assert L.psh_fft_aux_bytes(32768, 4096, 252, 20) == expect(32768, 4096, 252, 20, 4096)
+    monkeypatch.setenv("PSH_FFT_N", "1024")
+    assert L.psh_fft_aux_bytes(600, 3000, 500, 10) == expect(600, 3000, 500, 10, 1024)
+    assert L.psh_fft_aux_bytes(24, 8192, 1024, 20) == expect(24, 8192, 1024, 20, 4096)   # W > 768: never 1024-point
+    assert L.psh_fft_aux_bytes(10, 100, 2049, 0) == 0 and L.psh_fft_aux_bytes(10, 100, 90, 20) == 0
