@@ -387,11 +387,17 @@ __device__ __forceinline__ void fft3_append_candidates(const FftScanParams &p, i
 // memory: 2368 warps polling one L2 line every 200 ns kept the line so busy that the arrivals and the
 // publication themselves queued behind the polls (measured: 12 us from the median arrival to the release).
 // s_seed[0]: ticket of the CTA's poller, s_seed[1]: the launch's thresholds are published.
+// VIF (one query): the flag word CARRIES the threshold (its float bits, never 0), so the publication needs no
+// fence between threshold and flag and the waiting warps no load of the published threshold: two L2 round
+// trips less between the last arrival and the release.
+template <bool VIF>
 __device__ __forceinline__ void fft3_seed_rendezvous(const FftScanParams &p, const float *s_q2, float *s_thr, int lane,
                                                      volatile unsigned int *s_seed) {
     volatile unsigned int *done = p.hist + H_DONE;
+    unsigned int *relay = const_cast<unsigned int *>(&s_seed[1]);
     __syncwarp();
     int last = 0;
+    unsigned int seen = 0u;
     if (lane == 0) {
         __threadfence();
         const unsigned int ticket = atomicAdd(p.hist + H_ARR, 1u);
@@ -401,11 +407,15 @@ __device__ __forceinline__ void fft3_seed_rendezvous(const FftScanParams &p, con
             const unsigned long long t0 = globaltimer_ns();
             // (the relay flag is read and written with shared-memory atomics: a deliberate flag hand-off, and
             // compute-sanitizer's racecheck stays clean)
-            while (atomicOr(const_cast<unsigned int *>(&s_seed[1]), 0u) == 0u) {
-                if (poller && *done != 0u) { atomicExch(const_cast<unsigned int *>(&s_seed[1]), 1u); break; }
+            while ((seen = atomicOr(relay, 0u)) == 0u) {
+                if (poller) {
+                    seen = *done;
+                    if (seen != 0u) { atomicExch(relay, seen); break; }
+                }
                 if (globaltimer_ns() - t0 > 2000000ull) break;   // 2 ms: thresholds stay loose, the call re-runs safely
-                __nanosleep(poller ? 250 : 100);
+                __nanosleep(poller ? 200 : 100);
             }
+            if (VIF && seen != 0u) atomicMin(reinterpret_cast<unsigned int *>(&s_thr[0]), seen);
         }
     }
     last = __shfl_sync(FULL, last, 0);
@@ -413,13 +423,17 @@ __device__ __forceinline__ void fft3_seed_rendezvous(const FftScanParams &p, con
         for (int b = 0; b < p.nq; ++b) fft_refresh_threshold(p, b, s_q2[b], s_thr);
         __syncwarp();
         if (lane == 0) {
-            __threadfence();
-            *done = 1u;
-            atomicExch(const_cast<unsigned int *>(&s_seed[1]), 1u);
+            unsigned int word = 1u;
+            if (VIF) word = __float_as_uint(s_thr[0]);   // (positive float or +inf: never 0; lane 0 merged it itself)
+            else __threadfence();
+            *done = word;
+            atomicExch(relay, word);
         }
-    } else if (lane < p.nq) {
-        const unsigned int tb = *reinterpret_cast<volatile unsigned int *>(p.hist + (size_t)lane * HSTRIDE + H_THR);
-        atomicMin(reinterpret_cast<unsigned int *>(&s_thr[lane]), tb);
+    } else if (!VIF || __shfl_sync(FULL, seen, 0) == 0u) {   // (a group of queries, or the wait timed out)
+        if (lane < p.nq) {
+            const unsigned int tb = *reinterpret_cast<volatile unsigned int *>(p.hist + (size_t)lane * HSTRIDE + H_THR);
+            atomicMin(reinterpret_cast<unsigned int *>(&s_thr[lane]), tb);
+        }
     }
     __syncwarp();
 }
@@ -603,7 +617,7 @@ __global__ void __launch_bounds__(fx3::WARPS_SINGLE * 32, 1) fft_scan_warp_kerne
                 if (cnt && lane == __ffs(same) - 1) hist_add_ub(p.hist + (size_t)b * HSTRIDE, bin, (unsigned int)__popc(same));
                 if (rerun) continue;
                 PSH_STAMP3(1);
-                fft3_seed_rendezvous(p, s_q2, s_thr, lane, s_seed);
+                fft3_seed_rendezvous<SINGLE>(p, s_q2, s_thr, lane, s_seed);
                 PSH_STAMP3(2);
             }
             const float thr = s_thr[b];
@@ -628,7 +642,7 @@ __global__ void __launch_bounds__(fx3::WARPS_SINGLE * 32, 1) fft_scan_warp_kerne
         }
         if (seeding && rerun) {
             // a group of queries: arrive, wait for the thresholds, then the same pair again
-            fft3_seed_rendezvous(p, s_q2, s_thr, lane, s_seed);
+            fft3_seed_rendezvous<false>(p, s_q2, s_thr, lane, s_seed);
             seeding = false;
             staged = true;
             continue;
