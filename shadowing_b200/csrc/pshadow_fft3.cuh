@@ -531,6 +531,8 @@ __global__ void __launch_bounds__(fx3::WARPS_SINGLE * 32, 1) fft_scan_warp_kerne
         unsigned int drawn = 0;
         if (draw && lane == 0) drawn = atom_add_lane0(p.hist + H_SLOT, 1u);
         // thresholds other warps have published: fetched now, merged at the end of the iteration
+        // (measured and rejected: picking the thresholds up every iteration / re-deriving them more often during the
+        // first iterations after seeding, +0.4 % and +1.2 %)
         const bool pick = ((iter + gw) & 3) == 0;
         unsigned int pub = 0x7f800000u;
         if (pick && lane < nq) pub = __ldcg(p.hist + (size_t)lane * HSTRIDE + H_THR);
