@@ -442,7 +442,7 @@ __device__ __forceinline__ void fft3_seed_rendezvous(const FftScanParams &p, con
 // lower bound, thresholds, seeding and candidate lists of fft_scan_kernel (see there), at warp granularity:
 // every warp draws its own pairs (atomic slot counter, permuted order), owns two mbarriers and its staging
 // buffers (TMA bulk copies issued one pair ahead by lane 0), arrives at the seeding rendezvous on its own
-// and takes its turn re-deriving the thresholds.  The CTA (16 warps, one per SM; 12 for a group of queries)
+// and takes its turn re-deriving the thresholds.  The CTA (16 warps, one per SM; 13 for a group of queries)
 // only shares the twiddle table, the thresholds and -- one query -- the query's spectrum.
 // One query: the pair's spectrum is staged INSIDE the transpose tile (it is in registers before the tile
 // is written) and the next one is fetched when the tile has been read back.  A group of queries keeps the
